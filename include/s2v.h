@@ -1,0 +1,228 @@
+/*
+ * s2v.h - C ABI of libs2v.so, the B200 (sm_100a) kernels behind the per-frame
+ * lip-sync path of VideoReTalking (mel front end -> DNet -> LNet).
+ *
+ * The reference (Ryukhaan/speech-to-video-mpp) has no FFI for this path: its
+ * boundary is the Python call surface
+ *     futils/audio.py:45        melspectrogram(wav)
+ *     inference.py:209-216      mel-window chunking (inline loop)
+ *     futils/flow_util.py:3,41  convert_flow_to_deformation / warp_image
+ *     models/LNet.py:122        LNet.forward(audio_sequences, face_sequences)
+ *     models/DNet.py:20         DNet.forward(input_image, driving_source, stage)
+ * whose bodies are stock ATen calls (cuDNN conv, cuBLAS GEMM, cuFFT, ATen
+ * elementwise).  Each entry point below replaces the ATen/numpy call sequence
+ * named in its comment; the Python mirror in speech-to-video-mpp_b200/ keeps the
+ * reference's names, signatures and state_dict keys and calls these through
+ * ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *     the name ends in _host; the caller owns every buffer (no allocation here)
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*); no syncs
+ *   - returns 0 on success, a negative S2V_E* code otherwise; never throws
+ *   - activations between kernels are fp16, channels-last ("NHWC") views:
+ *     element (n,y,x,c) of a view lives at ptr + n*sN + y*sH + x*sW + c
+ *     (strides in ELEMENTS; channel stride is 1; C and strides multiples of 8)
+ *   - thread-safe for distinct streams; no mutable global state
+ */
+#ifndef S2V_H_
+#define S2V_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2V_OK            0
+#define S2V_EINVAL       -1   /* bad argument / unsupported shape            */
+#define S2V_ECUDA        -2   /* a CUDA runtime / driver call failed         */
+#define S2V_EUNSUPPORTED -3   /* device is not sm_100 / feature not available */
+
+/* activation codes used by every fused epilogue */
+#define S2V_ACT_NONE    0
+#define S2V_ACT_RELU    1
+#define S2V_ACT_LRELU   2     /* slope = act_param                            */
+#define S2V_ACT_SIGMOID 3
+#define S2V_ACT_TANH    4
+#define S2V_ACT_GELU    5     /* explicit tanh form, models/transformer.py:15 */
+
+/* output element formats */
+#define S2V_OUT_F16_NHWC 0
+#define S2V_OUT_F32_NCHW 1    /* y: contiguous [N,Cout,OH,OW] float           */
+
+#define S2V_PAD_ZERO    0
+#define S2V_PAD_REFLECT 1
+
+/* fp16 channels-last tensor view */
+typedef struct {
+  void*   ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;          /* strides in elements */
+} s2v_view;
+
+const char* s2v_strerror(int code);
+int s2v_version(void);
+/* 0 if the current device can run the tcgen05/TMA kernels (compute capability 10.x) */
+int s2v_device_ok(void);
+/* text of the last CUDA error seen by the library's runtime (diagnostics only) */
+const char* s2v_last_cuda_error(void);
+
+/* ------------------------------------------------------------------ mel ---
+ * replaces futils/audio.py:45-51 (preemphasis :20-23, librosa.stft :57-61,
+ * np.abs, _linear_to_mel :92-96, _amp_to_db :104-106, -ref_level_db,
+ * _normalize :111-115) for hparams n_fft=800 hop=200 win=800 sr=16000.
+ *   wav      float32 [n_samples]
+ *   basis    float32 [80,401] mel filterbank (built on the host exactly like
+ *            librosa.filters.mel; passed in so hparams stay a host concern)
+ *   mel_out  float32 [80, T], T = 1 + n_samples/200
+ * pad_reflect: 0 = zero centre padding (librosa>=0.9), 1 = reflect (<=0.8).    */
+int s2v_mel_num_frames(int64_t n_samples);
+/* band_range (nullable): int32 [80][2] = [first, last+1) non-zero bin of every
+ * filterbank row (a pure speed-up: the triangular rows are sparse).            */
+int s2v_melspectrogram_f32(const float* wav, int64_t n_samples, const float* basis,
+                           const int32_t* band_range, float* mel_out, int pad_reflect, void* stream);
+/* uploads the constant DFT-25 twiddle table; call once per device before the first mel call */
+int s2v_mel_init(void);
+
+/* replaces the loop of inference.py:209-216 (+ layout of :399/:261):
+ * number of 80x16 windows for T mel columns at `fps` (bit-exact int(i*80./fps)) */
+int64_t s2v_mel_window_count(int64_t n_cols, double fps);
+/* host helper: writes the start column of every window (count entries) */
+int s2v_mel_window_starts_host(int64_t n_cols, double fps, int32_t* starts_host, int64_t count);
+/* gathers windows [first, first+count) of mel [80,T] into out float32 [count,1,80,16] */
+int s2v_mel_windows_f32(const float* mel, int64_t n_cols, double fps, int64_t first, int64_t count,
+                        float* out, void* stream);
+
+/* ----------------------------------------------------------- flow warp ---
+ * replaces futils/flow_util.py:3-15 + :41-56 (convert_flow_to_deformation,
+ * bilinear resize of the grid, F.grid_sample bilinear/zeros/align_corners=False)
+ * as ONE kernel.  src/out float32 NCHW [B,C,H,W]; flow float32 NCHW [B,2,h,w].
+ * out16 (nullable): additionally writes the warped image as fp16 NHWC into the
+ * view's channels [c_off, c_off+C) (feeds DNet's editing net).                */
+int s2v_flow_warp_f32(const float* src, const float* flow, float* out,
+                      int B, int C, int H, int W, int h, int w,
+                      const s2v_view* out16, int c_off, void* stream);
+/* futils/flow_util.py:3-15 alone: flow [B,2,h,w] -> deformation [B,h,w,2] */
+int s2v_flow_to_deformation_f32(const float* flow, float* deformation, int B, int h, int w, void* stream);
+/* futils/flow_util.py:41-56 for an explicit deformation grid [B,h,w,2] */
+int s2v_warp_deformation_f32(const float* src, const float* deformation, float* out,
+                             int B, int C, int H, int W, int h, int w, void* stream);
+
+/* ------------------------------------------------------------- layout ---
+ * NCHW float32 [N,C,H,W] -> fp16 NHWC view channels [c_off, c_off+C); channels
+ * [c_off+C, c_off+c_fill) are zero-filled (channel padding to a multiple of 8).
+ * values are written as src*scale + shift.                                      */
+int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, const s2v_view* dst,
+                      int c_off, int c_fill, float scale, float shift, void* stream);
+int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, float* dst, void* stream);
+
+/* ----------------------------------------------------------------- conv ---
+ * One descriptor for both convolution kernels.  Replaces nn.Conv2d /
+ * nn.ConvTranspose2d (as sub-pixel phases) / nn.Conv1d / nn.Linear (1x1) calls
+ * of models/base_blocks.py, models/ffc.py, models/transformer.py, models/DNet.py
+ * with the epilogue   y = act( conv(x) * scale[c] + bias[c] + res1 ) + res2
+ * (res1: added before the activation - the audio encoder's residual
+ *  base_blocks.py:22-25; res2: after - residual streams / partial sums).        */
+typedef struct {
+  s2v_view x;                  /* input  [N,H,W,Cin]                                   */
+  s2v_view y;                  /* output [N,OH,OW,Cout] (view; may be strided phases)  */
+  const void*  w;              /* packed weights (layout per kernel, see below)        */
+  const float* scale;          /* [Cout] or NULL                                       */
+  const float* bias;           /* [Cout] or NULL                                       */
+  s2v_view res1;               /* ptr NULL => absent; same dims as y                   */
+  s2v_view res2;
+  int32_t kh, kw;
+  int32_t stride_h, stride_w;
+  int32_t pad_h, pad_w;        /* top/left padding                                     */
+  int32_t dil_h, dil_w;
+  int32_t pad_mode;            /* S2V_PAD_*; reflect is applied by index mirroring (simt)
+                                  or must be pre-materialised in x (tc)                */
+  int32_t up2;                 /* 1: x is nearest-upsampled x2 on the fly (simt only)  */
+  int32_t act;  float act_param;
+  int32_t out_mode;            /* S2V_OUT_*                                            */
+  float*  y_f32;               /* destination for S2V_OUT_F32_NCHW                     */
+} s2v_conv;
+
+/* SIMT direct convolution (small / awkward layers: Cin=3 7x7, Cout=3, audio
+ * encoder, AdaIN MLPs, MappingNet).  w: float32 [kh*kw][Cin][Cout_pad],
+ * Cout_pad = Cout rounded up to 4.                                             */
+int s2v_conv_simt(const s2v_conv* d, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit-GEMM convolution (stride 1, zero padding via
+ * TMA out-of-bounds fill; reflect padding pre-materialised by the producer).
+ * w: fp16 [Cout][kh*kw][Cin64] K-major, Cin64 = Cin rounded up to 64 (zero
+ * filled).  box_w*box_h*box_n must be 128 (the M tile is a box of pixels).
+ * pad_h/pad_w are the TOP/LEFT padding only; OH/OW may be smaller than the
+ * symmetric-padding formula (asymmetric padding of the sub-pixel phases of
+ * nearest-x2 + conv3x3 and of ConvTranspose2d).                                 */
+int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, void* stream);
+
+/* grouped small linears (all AdaIN gamma/beta heads of a net in one launch,
+ * models/base_blocks.py:136-141,149-151):
+ *   out[b][g.out_off + j] = bias_g[j] + sum_k hidden[b][g.in_off + k] * wt_g[k][j]
+ * hidden fp16 [B][hidden_stride]; wt float32 [K][nout] (transposed); out float32 */
+typedef struct {
+  const float* wt; const float* bias;
+  int32_t in_off, k, out_off, nout;
+} s2v_lin_group;
+int s2v_grouped_linear(const void* hidden_f16, int64_t hidden_stride, int B,
+                       const s2v_lin_group* groups_dev, const int32_t* tile2group_dev, int n_tiles,
+                       float* out, int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------- norms ---
+ * Deterministic (fixed-order) statistics + fused apply.
+ * stats: per (n, chunk, c) partial sum / sum-of-squares over the chunk's pixels.
+ *   partial float32 [N][chunks][C][2]                                           */
+int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, void* stream);
+/* LayerNorm2d over (C,H,W) (models/base_blocks.py:52-69, eps 1e-5):
+ *   a[n][c] = rstd[n]*gamma[c],  b[n][c] = beta[c] - mean[n]*a[n][c]            */
+int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                      const float* gamma, const float* beta, float eps, float* a, float* b, void* stream);
+/* InstanceNorm2d + AdaIN (models/base_blocks.py:127-157):
+ *   a = rstd[n][c]*(1+gamma[n][c]),  b = beta[n][c] - mean[n][c]*a
+ * gamma/beta float32 with row stride gb_stride (rows of the grouped_linear out) */
+int s2v_adain_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                       const float* gamma, const float* beta, int64_t gb_stride, float eps,
+                       float* a, float* b, void* stream);
+/* y = act(x*a[n][c] + b[n][c]) ; optional 2x2 average pool AFTER the activation
+ * (DownBlock2d, base_blocks.py:100); optional +res (after activation/pool);
+ * reflect1: additionally mirrors the result into a 1-pixel reflect border around
+ * y (y must be the interior view of a buffer padded by 1).                      */
+int s2v_affine_act(const s2v_view* x, const float* a, const float* b, int act, float act_param,
+                   int pool2, const s2v_view* res, const s2v_view* y, int reflect1, void* stream);
+/* nn.LayerNorm(C) over the channel dim of every pixel/token (transformer.py:27,35) */
+int s2v_token_layernorm(const s2v_view* x, const float* gamma, const float* beta, float eps,
+                        const s2v_view* y, void* stream);
+/* y = a + b (elementwise over views; used for Jump + Up, base LNet.py:75)       */
+int s2v_add(const s2v_view* a, const s2v_view* b, const s2v_view* y, void* stream);
+/* fills the 1-pixel reflect border of a padded buffer from its interior view    */
+int s2v_reflect_border(const s2v_view* interior, void* stream);
+
+/* ------------------------------------------------------------------ FFT ---
+ * FourierUnit halves (models/ffc.py:99-102 and :116-121), H,W in {12,24,48}:
+ * rfft2:  x [N,H,W,C] -> spec [N,H,W/2+1,2C] with channel 2c = Re, 2c+1 = Im
+ *         (torch.fft.rfftn norm='ortho' + stack/permute/view interleave)
+ * irfft2: spec -> y [N,H,W,C] (torch.fft.irfftn norm='ortho', Im of the DC and
+ *         Nyquist columns ignored after the H inverse) ; y += add (x + fu(x) of
+ *         ffc.py:172) when add.ptr != NULL                                      */
+/* uploads the constant W_48 twiddle table; call once per device before the first FFT call */
+int s2v_fft_init(void);
+int s2v_rfft2(const s2v_view* x, const s2v_view* spec, void* stream);
+int s2v_irfft2(const s2v_view* spec, const s2v_view* add, const s2v_view* y, void* stream);
+
+/* ------------------------------------------------------------ attention ---
+ * softmax(q k^T * scale) v per (n, head) (models/transformer.py:77-86).
+ * q,k,v,o: fp16 views [N,1,T,heads*dh] (T tokens <= 256, dh = 64)               */
+int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_view* v, const s2v_view* o,
+                  int heads, float scale, void* stream);
+
+/* MappingNet tail: AdaptiveAvgPool1d(1) over L (models/DNet.py:53)
+ * x [N,1,L,C] -> y [N,1,1,C]                                                    */
+int s2v_mean_over_w(const s2v_view* x, const s2v_view* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2V_H_ */

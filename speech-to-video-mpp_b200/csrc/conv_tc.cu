@@ -1,0 +1,350 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv2d (3x3 / 1x1, stride 1) and nn.Linear on
+// the hot path (models/base_blocks.py:99,116,433; models/ffc.py:139-153,197-204;
+// models/transformer.py:45-48,65-71).
+//
+//   D[M = pixels, N = Cout] = sum over taps (ky,kx) and 64-channel chunks of
+//                             A_tap[M, 64] * W_tap[64, N]          (fp16 x fp16 -> fp32)
+//
+// * The M tile is a BOX of 128 output pixels (box_n x box_h x box_w) of the channels-last
+//   activation.  For tap (ky,kx) the A operand is the same box shifted by the tap offset, so
+//   one tiled 4-D TMA load {64 ch, box_w, box_h, box_n} lands it in shared memory already in
+//   the K-major SWIZZLE_128B layout tcgen05.mma wants (row = pixel, 128 B = 64 fp16 channels).
+//   TMA out-of-bounds zero fill IS the zero padding; channel counts that are not a multiple
+//   of 64 are zero-filled the same way.  Reflect padding is pre-materialised by the producer
+//   (s2v_affine_act reflect1) and arrives here as pad = 0 on a padded view.
+// * Weights are packed [Cout][tap][Cin64] (K-major) and fetched by a 2-D TMA box {64, BN}.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//   warps 2..5 = epilogue (tcgen05.ld -> scale/bias/residual/activation -> fp16 stores).
+//   A multi-stage smem ring is handed over with mbarriers (TMA complete_tx -> MMA,
+//   tcgen05.commit -> producer); the accumulator (128 lanes x BN fp32 columns) lives in TMEM.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace s2v {
+
+constexpr int kTileM = 128, kChunkK = 64, kUmmaK = 16;
+constexpr int kABytes = kTileM * kChunkK * 2;        // 16 KB
+constexpr int kThreads = 192;
+constexpr unsigned kSpinLimit = 1u << 26;            // bounded waits: trap instead of hanging the GPU
+
+struct TcParams {
+  int N, OH, OW;
+  int box_w, box_h, box_n;
+  int tiles_w, tiles_h;
+  int kh, kw, pad_h, pad_w, dil_h, dil_w;
+  int cin_chunks, cout, bn, stages, tmem_cols;
+  View y, r1, r2;
+  const float* scale;
+  const float* bias;
+  int act;
+  float ap;
+  int out_mode;
+  float* yf;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+// start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(8 rows * 128 B = 1024 B)>>4 <<32 | version 1 <<46 | SW128 (2) <<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage][A 16 KB | B bn*128 B] ... then barriers
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;   // full[s], empty[s], tmem_full, tmem_ptr
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages, tfull = bar_base + 16u * p.stages;
+  const uint32_t tptr_addr = tfull + 8u;
+  volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+  const int x0 = tw * p.box_w, y0 = th * p.box_h, n0 = tn * p.box_n;
+  const int ntile = blockIdx.y;
+  const int KI = p.kh * p.kw * p.cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr_addr), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < KI; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(empty0 + 8u * s, ph ^ 1u);
+        const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
+        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+        const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+        mbar_expect_tx(full0 + 8u * s, stage_bytes);
+        tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 - p.pad_w + kx * p.dil_w, y0 - p.pad_h + ky * p.dil_h, n0);
+        tma_load_2d(a_dst + kABytes, &tmB, full0 + 8u * s, it * kChunkK, ntile * p.bn);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      for (int it = 0; it < KI; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(full0 + 8u * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+          // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
+          umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8u * s);          // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tfull);                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
+    const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
+    const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    for (int cb = 0; cb < p.bn; cb += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)cb, v);
+      const int c0 = ntile * p.bn + cb;
+      if (!valid || c0 >= p.cout) continue;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int c = c0 + 8 * hlf;
+        if (c >= p.cout) break;
+        float* o = v + 8 * hlf;
+        if (p.scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= p.scale[c + i];
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += p.bias[c + i];
+        }
+        if (p.r1.p) {
+          float f[8];
+          h8_to_f(ld_h8(p.r1.p + n * p.r1.sn + oy * p.r1.sh + ox * p.r1.sw + c), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += f[i];
+        }
+        if (p.act != S2V_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = act_apply(o[i], p.act, p.ap);
+        }
+        if (p.r2.p) {
+          float f[8];
+          h8_to_f(ld_h8(p.r2.p + n * p.r2.sn + oy * p.r2.sh + ox * p.r2.sw + c), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += f[i];
+        }
+        if (p.out_mode == S2V_OUT_F32_NCHW) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
+        } else {
+          st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;     // resolved once; immutable afterwards
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+}  // namespace s2v
+
+using namespace s2v;
+
+extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, void* stream) {
+  if (!d || !view_ok(&d->x) || !d->w) return S2V_EINVAL;
+  if (d->out_mode == S2V_OUT_F16_NHWC && !view_ok(&d->y)) return S2V_EINVAL;
+  if (d->out_mode == S2V_OUT_F32_NCHW && !d->y_f32) return S2V_EINVAL;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->up2 || d->pad_mode != S2V_PAD_ZERO) return S2V_EINVAL;
+  if (d->kh <= 0 || d->kw <= 0 || d->dil_h <= 0 || d->dil_w <= 0) return S2V_EINVAL;
+  if (box_w <= 0 || box_h <= 0 || box_n <= 0 || box_w * box_h * box_n != kTileM || box_w > 256 || box_h > 256 || box_n > 256) return S2V_EINVAL;
+  if ((box_w * box_h * box_n) % 8) return S2V_EINVAL;
+  const int N = d->x.n, OH = d->y.h, OW = d->y.w, cout = d->y.c;
+  if (d->y.n != N) return S2V_EINVAL;
+  if (OH <= 0 || OW <= 0) return S2V_EINVAL;   // rows/cols beyond the input are TMA zero fill (bottom/right padding)
+  if (cout % 8) return S2V_EINVAL;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return S2V_EUNSUPPORTED;
+
+  TcParams p;
+  p.N = N; p.OH = OH; p.OW = OW;
+  p.box_w = box_w; p.box_h = box_h; p.box_n = box_n;
+  p.tiles_w = ceil_div(OW, box_w); p.tiles_h = ceil_div(OH, box_h);
+  const int tiles_n = ceil_div(N, box_n);
+  p.kh = d->kh; p.kw = d->kw; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.dil_h = d->dil_h; p.dil_w = d->dil_w;
+  p.cin_chunks = ceil_div(d->x.c, kChunkK);
+  p.cout = cout;
+  int bn = cout <= 256 ? ((cout + 15) / 16) * 16 : 256;
+  if (cout > 256) {
+    // pick the N tile that wastes the least: 256, 192 or 128
+    const int cands[3] = {256, 192, 128};
+    int best = 256, best_waste = 1 << 30;
+    for (int i = 0; i < 3; ++i) {
+      const int w = ceil_div(cout, cands[i]) * cands[i] - cout;
+      if (w < best_waste) { best_waste = w; best = cands[i]; }
+    }
+    bn = best;
+  }
+  p.bn = bn;
+  p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+  const int stage_bytes = kABytes + bn * 128;
+  const int budget = (bn <= 128 ? 100 : 200) * 1024;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.y = mk(d->y);
+  p.r1 = mk(d->res1.ptr ? &d->res1 : nullptr);
+  p.r2 = mk(d->res2.ptr ? &d->res2 : nullptr);
+  p.scale = d->scale; p.bias = d->bias; p.act = d->act; p.ap = d->act_param;
+  p.out_mode = d->out_mode; p.yf = d->y_f32;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)d->x.c, (cuuint64_t)d->x.w, (cuuint64_t)d->x.h, (cuuint64_t)d->x.n};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->x.sw * 2, (cuuint64_t)d->x.sh * 2, (cuuint64_t)d->x.sn * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return S2V_ECUDA;
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)d->kh * d->kw * p.cin_chunks * kChunkK;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)cout};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return S2V_ECUDA;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  static bool attr = false;   // idempotent
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
+    attr = true;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_n, ceil_div(cout, bn));
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}

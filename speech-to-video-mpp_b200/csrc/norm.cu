@@ -1,0 +1,347 @@
+// Normalisation kernels (memory-bound, 128-bit vectorised, deterministic):
+//   chan_stats      per-(n, chunk, c) partial sum / sum of squares (fixed-order reduction)
+//   ln2d_finalize   LayerNorm2d over (C,H,W)   (models/base_blocks.py:52-69)  -> per-(n,c) affine
+//   adain_finalize  InstanceNorm2d + AdaIN     (models/base_blocks.py:127-157) -> per-(n,c) affine
+//   affine_act      y = act(x*a + b) [2x2 avg-pool] [+res] [reflect border]  (one read, one write)
+//   token_layernorm nn.LayerNorm(C) per token   (models/transformer.py:27,35-36)
+//   add, reflect_border, mean_over_w
+// No float atomics anywhere: sharded and unsharded runs give bit-identical frames.
+#include "common.cuh"
+
+namespace s2v {
+
+// grid (chunks, N); block = PG * C8 threads (C8 = C/8); thread (pg, c8) walks pixels pg, pg+PG, ...
+__global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict__ partial) {
+  extern __shared__ float sm[];   // [PG][C][2]
+  const int C8 = x.c >> 3;
+  const int c8 = threadIdx.x % C8, pg = threadIdx.x / C8;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int HW = x.h * x.w;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (pg < PG) {
+    for (int p = p0 + pg; p < p1; p += PG) {
+      const int yy = p / x.w, xx = p - yy * x.w;
+      float f[8];
+      h8_to_f(ld_h8(x.p + n * x.sn + yy * x.sh + xx * x.sw + c8 * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    float* o = sm + ((size_t)pg * x.c + c8 * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[2 * i] = s[i]; o[2 * i + 1] = q[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < x.c; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int g = 0; g < PG; ++g) { a += sm[((size_t)g * x.c + c) * 2]; b += sm[((size_t)g * x.c + c) * 2 + 1]; }
+    float* o = partial + (((size_t)n * chunks + chunk) * x.c + c) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// grid N, block 256: fixed-order reduction over chunks and channels (double accumulators)
+__global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
+                                                            double inv_count, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            float* __restrict__ a, float* __restrict__ b) {
+  __shared__ double ss[256], sq[256];
+  const int n = blockIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int c = threadIdx.x; c < C; c += 256)
+    for (int k = 0; k < chunks; ++k) {
+      const float* p = partial + (((size_t)n * chunks + k) * C + c) * 2;
+      s += (double)p[0]; q += (double)p[1];
+    }
+  ss[threadIdx.x] = s; sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double mean = ss[0] * inv_count;
+  double var = sq[0] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float fmean = (float)mean;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float av = rstd * gamma[c];
+    a[(size_t)n * C + c] = av;
+    b[(size_t)n * C + c] = beta[c] - fmean * av;
+  }
+}
+
+__global__ void __launch_bounds__(256) adain_finalize_kernel(const float* __restrict__ partial, int N, int chunks,
+                                                             int C, float inv_count, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long gb_stride,
+                                                             float eps, float* __restrict__ a, float* __restrict__ b) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int n = idx / C, c = idx - n * C;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* p = partial + (((size_t)n * chunks + k) * C + c) * 2;
+    s += (double)p[0]; q += (double)p[1];
+  }
+  const double mean = s * (double)inv_count;
+  double var = q * (double)inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[(size_t)n * gb_stride + c] : 0.f;
+  const float be = beta ? beta[(size_t)n * gb_stride + c] : 0.f;
+  const float av = rstd * (1.f + g);
+  a[idx] = av;
+  b[idx] = be - (float)mean * av;
+}
+
+// one thread per output vector (n, oy, ox, c8)
+__global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
+                                                         const float* __restrict__ b, int act, float ap, int pool2,
+                                                         View res, View y, int reflect1) {
+  const int C8 = x.c >> 3;
+  const long long total = (long long)y.n * y.h * y.w * C8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long r = idx / C8;
+  const int ox = (int)(r % y.w); r /= y.w;
+  const int oy = (int)(r % y.h);
+  const int n = (int)(r / y.h);
+  float av[8], bv[8], o[8];
+  {
+    const float4* pa = reinterpret_cast<const float4*>(a + (size_t)n * x.c + c8 * 8);
+    const float4* pb = reinterpret_cast<const float4*>(b + (size_t)n * x.c + c8 * 8);
+    float4 t0 = pa[0], t1 = pa[1], u0 = pb[0], u1 = pb[1];
+    av[0] = t0.x; av[1] = t0.y; av[2] = t0.z; av[3] = t0.w; av[4] = t1.x; av[5] = t1.y; av[6] = t1.z; av[7] = t1.w;
+    bv[0] = u0.x; bv[1] = u0.y; bv[2] = u0.z; bv[3] = u0.w; bv[4] = u1.x; bv[5] = u1.y; bv[6] = u1.z; bv[7] = u1.w;
+  }
+  if (pool2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        h8_to_f(ld_h8(x.p + n * x.sn + (2 * oy + dy) * x.sh + (2 * ox + dx) * x.sw + c8 * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= 0.25f;
+  } else {
+    float f[8];
+    h8_to_f(ld_h8(x.p + n * x.sn + oy * x.sh + ox * x.sw + c8 * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+  }
+  if (res.p) {
+    float f[8];
+    h8_to_f(ld_h8(res.p + n * res.sn + oy * res.sh + ox * res.sw + c8 * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += f[i];
+  }
+  const H8 hv = f_to_h8(o);
+  __half* yp = y.p + n * y.sn + c8 * 8;
+  st_h8(yp + oy * y.sh + ox * y.sw, hv);
+  if (reflect1) {
+    // padded(-1) = in(1), padded(H) = in(H-2)
+    const int my = (oy == 1) ? -1 : (oy == y.h - 2 ? y.h : -2);
+    const int mx = (ox == 1) ? -1 : (ox == y.w - 2 ? y.w : -2);
+    if (my != -2) st_h8(yp + my * y.sh + ox * y.sw, hv);
+    if (mx != -2) st_h8(yp + oy * y.sh + mx * y.sw, hv);
+    if (my != -2 && mx != -2) st_h8(yp + my * y.sh + mx * y.sw, hv);
+    // a 2-wide dimension maps both borders from different pixels; h,w >= 3 is enforced on the host
+  }
+}
+
+__global__ void __launch_bounds__(256) reflect_border_kernel(View v) {
+  // v = interior view; fills rows -1 / H and cols -1 / W (pad 1, reflect)
+  const int C8 = v.c >> 3;
+  const int PW = v.w + 2, PH = v.h + 2;
+  const int border = 2 * PW + 2 * v.h;
+  const long long total = (long long)v.n * border * C8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long r = idx / C8;
+  const int e = (int)(r % border);
+  const int n = (int)(r / border);
+  int py, px;   // padded coords in [-1, H] x [-1, W]
+  if (e < PW) { py = -1; px = e - 1; }
+  else if (e < 2 * PW) { py = v.h; px = e - PW - 1; }
+  else { const int k = e - 2 * PW; py = k >> 1; px = (k & 1) ? v.w : -1; }
+  (void)PH;
+  const int sy = py < 0 ? 1 : (py >= v.h ? v.h - 2 : py);
+  const int sx = px < 0 ? 1 : (px >= v.w ? v.w - 2 : px);
+  __half* base = v.p + n * v.sn + c8 * 8;
+  st_h8(base + py * v.sh + px * v.sw, ld_h8(base + sy * v.sh + sx * v.sw));
+}
+
+// one warp per token; C <= 1024 (C/8 vectors spread over lanes)
+__global__ void __launch_bounds__(256) token_ln_kernel(View x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, View y) {
+  const int lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)x.n * x.h * x.w;
+  if (tok >= total) return;
+  const int xx = (int)(tok % x.w);
+  const int yy = (int)((tok / x.w) % x.h);
+  const int n = (int)(tok / ((long long)x.w * x.h));
+  const __half* px = x.p + n * x.sn + yy * x.sh + xx * x.sw;
+  __half* py = y.p + n * y.sn + yy * y.sh + xx * y.sw;
+  const int C8 = x.c >> 3;
+  float f[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c8 = lane + 32 * k;
+    if (c8 < C8) {
+      h8_to_f(ld_h8(px + c8 * 8), f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)x.c;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c8 = lane + 32 * k;
+    if (c8 < C8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; q = fmaf(d, d, q); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)x.c + eps);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c8 = lane + 32 * k;
+    if (c8 < C8) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * gamma[c8 * 8 + i] + beta[c8 * 8 + i];
+      st_h8(py + c8 * 8, f_to_h8(o));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(View a, View b, View y) {
+  const int C8 = y.c >> 3;
+  const long long total = (long long)y.n * y.h * y.w * C8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long r = idx / C8;
+  const int xx = (int)(r % y.w); r /= y.w;
+  const int yy = (int)(r % y.h);
+  const int n = (int)(r / y.h);
+  float fa[8], fb[8];
+  h8_to_f(ld_h8(a.p + n * a.sn + yy * a.sh + xx * a.sw + c8 * 8), fa);
+  h8_to_f(ld_h8(b.p + n * b.sn + yy * b.sh + xx * b.sw + c8 * 8), fb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fa[i] += fb[i];
+  st_h8(y.p + n * y.sn + yy * y.sh + xx * y.sw + c8 * 8, f_to_h8(fa));
+}
+
+__global__ void __launch_bounds__(256) mean_over_w_kernel(View x, View y) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= x.n * x.c) return;
+  const int n = idx / x.c, c = idx - n * x.c;
+  float s = 0.f;
+  for (int i = 0; i < x.w; ++i) s += __half2float(x.p[n * x.sn + i * x.sw + c]);
+  y.p[n * y.sn + c] = __float2half_rn(s / (float)x.w);
+}
+
+}  // namespace s2v
+
+using namespace s2v;
+
+extern "C" int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, void* stream) {
+  if (!view_ok(x) || !partial || chunks <= 0 || chunks > 65535 || x->n > 65535) return S2V_EINVAL;
+  const int C8 = x->c >> 3;
+  if (C8 > 1024) return S2V_EINVAL;
+  int PG = 256 / C8;
+  if (PG < 1) PG = 1;
+  if (PG > 32) PG = 32;
+  const int threads = PG * C8;
+  const size_t smem = (size_t)PG * x->c * 2 * sizeof(float);
+  if (smem > 48 * 1024) return S2V_EINVAL;
+  chan_stats_kernel<<<dim3(chunks, x->n), threads, smem, (cudaStream_t)stream>>>(mk(x), chunks, PG, partial);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                                 const float* gamma, const float* beta, float eps, float* a, float* b, void* stream) {
+  if (!partial || !gamma || !beta || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
+  ln2d_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(partial, chunks, C, 1.0 / ((double)count_per_channel * C),
+                                                            gamma, beta, eps, a, b);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_adain_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                                  const float* gamma, const float* beta, int64_t gb_stride, float eps, float* a,
+                                  float* b, void* stream) {
+  if (!partial || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
+  adain_finalize_kernel<<<ceil_div((long long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      partial, N, chunks, C, 1.f / (float)count_per_channel, gamma, beta, gb_stride, eps, a, b);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b, int act, float act_param, int pool2,
+                              const s2v_view* res, const s2v_view* y, int reflect1, void* stream) {
+  if (!view_ok(x) || !view_ok(y) || !a || !b) return S2V_EINVAL;
+  if (y->c != x->c || y->n != x->n) return S2V_EINVAL;
+  if (pool2 ? (x->h != 2 * y->h || x->w != 2 * y->w) : (x->h != y->h || x->w != y->w)) return S2V_EINVAL;
+  if (res && res->ptr && (!view_ok(res) || res->c != y->c || res->h != y->h || res->w != y->w || res->n != y->n)) return S2V_EINVAL;
+  if (reflect1 && (y->h < 4 || y->w < 4)) return S2V_EINVAL;
+  const long long total = (long long)y->n * y->h * y->w * (y->c >> 3);
+  affine_act_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param, pool2,
+                                                                           mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_reflect_border(const s2v_view* interior, void* stream) {
+  if (!view_ok(interior) || interior->h < 2 || interior->w < 2) return S2V_EINVAL;
+  const long long total = (long long)interior->n * (2 * (interior->w + 2) + 2 * interior->h) * (interior->c >> 3);
+  reflect_border_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(interior));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_token_layernorm(const s2v_view* x, const float* gamma, const float* beta, float eps,
+                                   const s2v_view* y, void* stream) {
+  if (!view_ok(x) || !view_ok(y) || !gamma || !beta || x->c > 1024) return S2V_EINVAL;
+  if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return S2V_EINVAL;
+  const long long total = (long long)x->n * x->h * x->w;
+  token_ln_kernel<<<ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(mk(x), gamma, beta, eps, mk(y));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_add(const s2v_view* a, const s2v_view* b, const s2v_view* y, void* stream) {
+  if (!view_ok(a) || !view_ok(b) || !view_ok(y)) return S2V_EINVAL;
+  if (a->n != y->n || a->h != y->h || a->w != y->w || a->c != y->c) return S2V_EINVAL;
+  if (b->n != y->n || b->h != y->h || b->w != y->w || b->c != y->c) return S2V_EINVAL;
+  const long long total = (long long)y->n * y->h * y->w * (y->c >> 3);
+  add_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(a), mk(b), mk(y));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_mean_over_w(const s2v_view* x, const s2v_view* y, void* stream) {
+  if (!view_ok(x) || !view_ok(y) || x->h != 1 || y->h != 1 || y->w != 1 || x->c != y->c || x->n != y->n) return S2V_EINVAL;
+  mean_over_w_kernel<<<ceil_div((long long)x->n * x->c, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}

@@ -1,0 +1,152 @@
+// Fused flow warp: convert_flow_to_deformation + bilinear grid resize + grid_sample
+// (reference: futils/flow_util.py:3-15, :41-56; closed form SURVEY A.4) as ONE
+// memory-bound kernel.  fp32 NCHW in/out (the module boundary), optional fp16 NHWC
+// side output feeding DNet's editing net.
+//
+// Algorithmic bytes per frame (C=3, 256^2, flow 64^2): src 786432 + flow 32768 +
+// out 786432 = 1605632 B.  One thread per output pixel, consecutive threads along X
+// (coalesced stores; gathers are spatially local and hit L1/L2).
+#include "common.cuh"
+
+namespace s2v {
+
+// deformation value at flow cell (i,j): grid + 2*flow/(size-1)   (flow_util.py:12-14,30-31)
+__device__ __forceinline__ float2 deform_at(const float* __restrict__ fx, const float* __restrict__ fy, int i, int j,
+                                            int w, float inv_wm1, float inv_hm1) {
+  float gx = __fadd_rn(__fmul_rn(2.f, __fmul_rn((float)j, inv_wm1)), -1.f);
+  float gy = __fadd_rn(__fmul_rn(2.f, __fmul_rn((float)i, inv_hm1)), -1.f);
+  float dx = __fadd_rn(gx, __fmul_rn(2.f, __fmul_rn(fx[i * w + j], inv_wm1)));
+  float dy = __fadd_rn(gy, __fmul_rn(2.f, __fmul_rn(fy[i * w + j], inv_hm1)));
+  return make_float2(dx, dy);
+}
+
+__device__ __forceinline__ void sample_store(const float* __restrict__ src, float* __restrict__ out, int C, int H,
+                                             int W, int Y, int X, float gx, float gy, __half* out16) {
+  // grid_sample, bilinear, zeros padding, align_corners=False
+  float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), -1.f), 0.5f);
+  float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), -1.f), 0.5f);
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  // guard against huge/NaN coordinates before the int conversion
+  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+  int x0 = finite ? (int)fx0 : -10, y0 = finite ? (int)fy0 : -10;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+  bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+  float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+  const size_t plane = (size_t)H * W;
+  for (int c = 0; c < C; ++c) {
+    const float* s = src + c * plane;
+    float v = 0.f;
+    if (vy0 && vx0) v += s[y0 * W + x0] * w00;
+    if (vy0 && vx1) v += s[y0 * W + x1] * w01;
+    if (vy1 && vx0) v += s[y1 * W + x0] * w10;
+    if (vy1 && vx1) v += s[y1 * W + x1] * w11;
+    out[c * plane + (size_t)Y * W + X] = v;
+    if (out16) out16[c] = __float2half_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) flow_warp_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                        float* __restrict__ out, int C, int H, int W, int h, int w,
+                                                        View o16, int c_off) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (X >= W) return;
+  const float* fx = flow + (size_t)b * 2 * h * w;
+  const float* fy = fx + (size_t)h * w;
+  const float inv_wm1 = 1.f / (float)(w - 1), inv_hm1 = 1.f / (float)(h - 1);
+  float gx, gy;
+  if (h == H && w == W) {
+    float2 d = deform_at(fx, fy, Y, X, w, inv_wm1, inv_hm1);
+    gx = d.x; gy = d.y;
+  } else {
+    // F.interpolate(mode='bilinear', align_corners=False) of the deformation grid
+    const float sch = (float)h / (float)H, scw = (float)w / (float)W;
+    float sy = fmaxf(sch * ((float)Y + 0.5f) - 0.5f, 0.f);
+    float sx = fmaxf(scw * ((float)X + 0.5f) - 0.5f, 0.f);
+    int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f);
+    float hy = 1.f - ly, hx = 1.f - lx;
+    float2 d00 = deform_at(fx, fy, y0, x0, w, inv_wm1, inv_hm1);
+    float2 d01 = deform_at(fx, fy, y0, x1, w, inv_wm1, inv_hm1);
+    float2 d10 = deform_at(fx, fy, y1, x0, w, inv_wm1, inv_hm1);
+    float2 d11 = deform_at(fx, fy, y1, x1, w, inv_wm1, inv_hm1);
+    gx = hy * (hx * d00.x + lx * d01.x) + ly * (hx * d10.x + lx * d11.x);
+    gy = hy * (hx * d00.y + lx * d01.y) + ly * (hx * d10.y + lx * d11.y);
+  }
+  __half* p16 = o16.p ? o16.p + (size_t)b * o16.sn + (size_t)Y * o16.sh + (size_t)X * o16.sw + c_off : nullptr;
+  sample_store(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, p16);
+}
+
+__global__ void flow_to_deformation_kernel(const float* __restrict__ flow, float* __restrict__ def, int h, int w) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+  if (j >= w) return;
+  const float* fx = flow + (size_t)b * 2 * h * w;
+  float2 d = deform_at(fx, fx + (size_t)h * w, i, j, w, 1.f / (float)(w - 1), 1.f / (float)(h - 1));
+  reinterpret_cast<float2*>(def)[((size_t)b * h + i) * w + j] = d;
+}
+
+__global__ void __launch_bounds__(256) warp_deformation_kernel(const float* __restrict__ src,
+                                                               const float* __restrict__ def, float* __restrict__ out,
+                                                               int C, int H, int W, int h, int w) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, b = blockIdx.z;
+  if (X >= W) return;
+  const float2* d = reinterpret_cast<const float2*>(def) + (size_t)b * h * w;
+  float gx, gy;
+  if (h == H && w == W) {
+    float2 v = d[Y * w + X];
+    gx = v.x; gy = v.y;
+  } else {
+    const float sch = (float)h / (float)H, scw = (float)w / (float)W;
+    float sy = fmaxf(sch * ((float)Y + 0.5f) - 0.5f, 0.f);
+    float sx = fmaxf(scw * ((float)X + 0.5f) - 0.5f, 0.f);
+    int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f);
+    float hy = 1.f - ly, hx = 1.f - lx;
+    float2 d00 = d[y0 * w + x0], d01 = d[y0 * w + x1], d10 = d[y1 * w + x0], d11 = d[y1 * w + x1];
+    gx = hy * (hx * d00.x + lx * d01.x) + ly * (hx * d10.x + lx * d11.x);
+    gy = hy * (hx * d00.y + lx * d01.y) + ly * (hx * d10.y + lx * d11.y);
+  }
+  sample_store(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, nullptr);
+}
+
+}  // namespace s2v
+
+using namespace s2v;
+
+extern "C" int s2v_flow_warp_f32(const float* src, const float* flow, float* out, int B, int C, int H, int W, int h,
+                                 int w, const s2v_view* out16, int c_off, void* stream) {
+  if (B == 0) return S2V_OK;
+  if (!src || !flow || !out || B < 0 || C <= 0 || H <= 0 || W <= 0 || h < 2 || w < 2) return S2V_EINVAL;
+  if (B > 65535 || H > 65535) return S2V_EINVAL;
+  View o16 = mk(out16);
+  if (out16 && out16->ptr && (out16->n < B || out16->h != H || out16->w != W || c_off + C > out16->c)) return S2V_EINVAL;
+  dim3 grid(ceil_div(W, 256), H, B);
+  flow_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, flow, out, C, H, W, h, w, o16, c_off);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_flow_to_deformation_f32(const float* flow, float* deformation, int B, int h, int w, void* stream) {
+  if (B == 0) return S2V_OK;
+  if (!flow || !deformation || B < 0 || h < 2 || w < 2 || B > 65535 || h > 65535) return S2V_EINVAL;
+  dim3 grid(ceil_div(w, 128), h, B);
+  flow_to_deformation_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(flow, deformation, h, w);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_warp_deformation_f32(const float* src, const float* deformation, float* out, int B, int C, int H,
+                                        int W, int h, int w, void* stream) {
+  if (B == 0) return S2V_OK;
+  if (!src || !deformation || !out || B < 0 || C <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return S2V_EINVAL;
+  if (B > 65535 || H > 65535) return S2V_EINVAL;
+  dim3 grid(ceil_div(W, 256), H, B);
+  warp_deformation_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, deformation, out, C, H, W, h, w);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}

@@ -1,0 +1,235 @@
+"""Thin Python layer over the C ABI: tensor -> s2v_view marshalling and op builders.
+
+Every builder returns an ``Op`` (C function + prepared ctypes arguments + keep-alive
+references).  Engines collect Ops into a ``Plan`` once per batch size and replay the
+plan (directly, or captured into a CUDA graph); the eager helpers at the bottom run a
+single Op on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib as L
+
+
+def view(t: torch.Tensor) -> L.View:
+    """fp16 channels-last [N,H,W,C] tensor (any strides, channel stride 1) -> s2v_view."""
+    assert t.dtype == torch.float16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    return L.View(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.stride(0), t.stride(1), t.stride(2))
+
+
+def null_view() -> L.View:
+    return L.View(None, 0, 0, 0, 0, 0, 0, 0)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def cur_stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class Op:
+    name: str
+    fn: object
+    args: tuple
+    keep: tuple = field(default_factory=tuple, repr=False)
+
+    def run(self, stream=None):
+        L.check(self.fn(*self.args, stream if stream is not None else cur_stream()), self.name)
+
+
+class Plan:
+    """Ordered list of Ops replayed on one stream."""
+
+    def __init__(self):
+        self.ops: list[Op] = []
+
+    def add(self, op: Op) -> Op:
+        self.ops.append(op)
+        return op
+
+    def run(self, stream=None):
+        s = stream if stream is not None else cur_stream()
+        for op in self.ops:
+            rc = op.fn(*op.args, s)
+            if rc != 0:
+                L.check(rc, op.name)
+
+    def __len__(self):
+        return len(self.ops)
+
+
+def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
+    """Box of 128 output pixels (box_w, box_h, box_n) with the least padding waste."""
+    best, best_key = None, None
+    for bw in (128, 64, 32, 16, 8, 4, 2, 1):
+        for bh in (128, 64, 32, 16, 8, 4, 2, 1):
+            if bw * bh > 128:
+                continue
+            bn = 128 // (bw * bh)
+            tiles = -(-w // bw) * -(-h // bh) * -(-n // bn)
+            waste = tiles * 128 / float(n * h * w)
+            key = (round(waste, 6), bn, -bw)
+            if best_key is None or key < best_key:
+                best, best_key = (bw, bh, bn), key
+    return best
+
+
+def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
+            scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
+            out_shape=None, impl="tc", box=None, name="conv") -> Op:
+    """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
+    d = L.Conv()
+    d.x = view(x)
+    if y is not None:
+        d.y = view(y)
+        d.out_mode = L.OUT_F16_NHWC
+    else:
+        n, co, oh, ow = out_shape
+        d.y = L.View(None, n, oh, ow, co, 0, 0, 0)
+        d.out_mode = L.OUT_F32_NCHW
+        d.y_f32 = y_f32.data_ptr()
+    d.w = w.data_ptr()
+    d.scale = None if scale is None else scale.data_ptr()
+    d.bias = None if bias is None else bias.data_ptr()
+    d.res1 = view(res1) if res1 is not None else null_view()
+    d.res2 = view(res2) if res2 is not None else null_view()
+    d.kh, d.kw = k
+    d.stride_h, d.stride_w = stride
+    d.pad_h, d.pad_w = pad
+    d.dil_h, d.dil_w = dil
+    d.pad_mode, d.up2, d.act, d.act_param = pad_mode, up2, act, float(act_param)
+    keep = (d, x, w, y, scale, bias, res1, res2, y_f32)
+    if impl == "simt":
+        return Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
+    if box is None:
+        box = choose_box(d.y.h, d.y.w, d.y.n)
+    return Op(name + "[tc]", lib.s2v_conv_tc, (C.byref(d), box[0], box[1], box[2]), keep)
+
+
+def stats_chunks(n: int, hw: int) -> int:
+    """Pixel chunks per image for chan_stats: aim at >= ~600 blocks, >= 32 pixels each."""
+    return max(1, min(hw // 32, -(-600 // max(n, 1)), 256))
+
+
+def op_chan_stats(lib, x, chunks, partial) -> Op:
+    v = view(x)
+    return Op("chan_stats", lib.s2v_chan_stats, (C.byref(v), chunks, _ptr(partial)), (v, x, partial))
+
+
+def op_ln2d_finalize(lib, partial, n, chunks, c, count, gamma, beta, a, b, eps=1e-5) -> Op:
+    return Op("ln2d_finalize", lib.s2v_ln2d_finalize,
+              (_ptr(partial), n, chunks, c, count, _ptr(gamma), _ptr(beta), eps, _ptr(a), _ptr(b)),
+              (partial, gamma, beta, a, b))
+
+
+def op_adain_finalize(lib, partial, n, chunks, c, count, gamma, beta, gb_stride, a, b, eps=1e-5) -> Op:
+    return Op("adain_finalize", lib.s2v_adain_finalize,
+              (_ptr(partial), n, chunks, c, count, _ptr(gamma), _ptr(beta), gb_stride, eps, _ptr(a), _ptr(b)),
+              (partial, gamma, beta, a, b))
+
+
+def op_affine_act(lib, x, a, b, y, *, act=L.ACT_NONE, act_param=0.0, pool2=0, res=None, reflect1=0) -> Op:
+    vx, vy = view(x), view(y)
+    vr = view(res) if res is not None else null_view()
+    return Op("affine_act", lib.s2v_affine_act,
+              (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), pool2, C.byref(vr), C.byref(vy), reflect1),
+              (vx, vy, vr, x, y, res, a, b))
+
+
+def op_token_ln(lib, x, gamma, beta, y, eps=1e-5) -> Op:
+    vx, vy = view(x), view(y)
+    return Op("token_layernorm", lib.s2v_token_layernorm, (C.byref(vx), _ptr(gamma), _ptr(beta), eps, C.byref(vy)),
+              (vx, vy, x, y, gamma, beta))
+
+
+def op_add(lib, a, b, y) -> Op:
+    va, vb, vy = view(a), view(b), view(y)
+    return Op("add", lib.s2v_add, (C.byref(va), C.byref(vb), C.byref(vy)), (va, vb, vy, a, b, y))
+
+
+def op_reflect_border(lib, interior) -> Op:
+    v = view(interior)
+    return Op("reflect_border", lib.s2v_reflect_border, (C.byref(v),), (v, interior))
+
+
+def op_rfft2(lib, x, spec) -> Op:
+    vx, vs = view(x), view(spec)
+    return Op("rfft2", lib.s2v_rfft2, (C.byref(vx), C.byref(vs)), (vx, vs, x, spec))
+
+
+def op_irfft2(lib, spec, add, y) -> Op:
+    vs, vy = view(spec), view(y)
+    va = view(add) if add is not None else null_view()
+    return Op("irfft2", lib.s2v_irfft2, (C.byref(vs), C.byref(va), C.byref(vy)), (vs, va, vy, spec, add, y))
+
+
+def op_attention(lib, q, k, v, o, heads, scale) -> Op:
+    vq, vk, vv, vo = view(q), view(k), view(v), view(o)
+    return Op("attention", lib.s2v_attention, (C.byref(vq), C.byref(vk), C.byref(vv), C.byref(vo), heads, float(scale)),
+              (vq, vk, vv, vo, q, k, v, o))
+
+
+def op_pack(lib, src, dst, c_off=0, c_fill=None, scale=1.0, shift=0.0) -> Op:
+    n, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    vd = view(dst)
+    c_fill = c if c_fill is None else c_fill
+    return Op("pack_nchw", lib.s2v_pack_nchw_f32, (_ptr(src), n, c, h, w, C.byref(vd), c_off, c_fill, float(scale), float(shift)),
+              (vd, src, dst))
+
+
+def op_unpack(lib, src, c_off, c, dst) -> Op:
+    vs = view(src)
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    return Op("unpack_nchw", lib.s2v_unpack_to_nchw_f32, (C.byref(vs), c_off, c, _ptr(dst)), (vs, src, dst))
+
+
+def op_grouped_linear(lib, hidden, groups_dev, tile2group_dev, n_tiles, out) -> Op:
+    b = hidden.shape[0]
+    h2 = hidden.reshape(b, -1)
+    assert h2.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
+    return Op("grouped_linear", lib.s2v_grouped_linear,
+              (_ptr(h2), h2.stride(0), b, _ptr(groups_dev), _ptr(tile2group_dev), n_tiles, _ptr(out), out.stride(0)),
+              (hidden, h2, groups_dev, tile2group_dev, out))
+
+
+def op_mean_over_w(lib, x, y) -> Op:
+    vx, vy = view(x), view(y)
+    return Op("mean_over_w", lib.s2v_mean_over_w, (C.byref(vx), C.byref(vy)), (vx, vy, x, y))
+
+
+def op_flow_warp(lib, src, flow, out, out16=None, c_off=0) -> Op:
+    b, c, h, w = src.shape
+    fh, fw = flow.shape[2], flow.shape[3]
+    v16 = view(out16) if out16 is not None else null_view()
+    return Op("flow_warp", lib.s2v_flow_warp_f32, (_ptr(src), _ptr(flow), _ptr(out), b, c, h, w, fh, fw, C.byref(v16), c_off),
+              (src, flow, out, out16, v16))
+
+
+# ------------------------------------------------------------------ weight packing
+
+
+def pack_w_tc(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] float -> fp16 [Cout][kh*kw][Cin64] (K-major, zero-filled channel pad)."""
+    co, ci, kh, kw = w.shape
+    ci64 = -(-ci // 64) * 64
+    out = torch.zeros(co, kh * kw, ci64, dtype=torch.float16, device=w.device)
+    out[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16)
+    return out.reshape(co, kh * kw * ci64).contiguous()
+
+
+def pack_w_simt(w: torch.Tensor, cin_pad: int | None = None) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] float -> float32 [kh*kw][Cin_pad][Cout_pad]."""
+    co, ci, kh, kw = w.shape
+    cin_pad = cin_pad or -(-ci // 8) * 8
+    co_pad = -(-co // 16) * 16 if co >= 16 else -(-co // 4) * 4
+    out = torch.zeros(kh * kw, cin_pad, co_pad, dtype=torch.float32, device=w.device)
+    out[:, :ci, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).float()
+    return out.contiguous()

@@ -1,0 +1,305 @@
+"""-m gpu parity tests of the individual kernels, called through the C ABI, against the
+oracle (oracle/) or a plain PyTorch fp32 reference of the same op."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    gpu_util.lib()
+    return gpu_util
+
+
+def test_flow_warp_vs_oracle_and_golden(G):
+    import os
+    from oracle import nets, synth
+    lib = G.lib()
+    # golden produced by the real reference (small)
+    s, fl = synth.warp_inputs(2, seed=0, c=3, hw=64, fhw=16)
+    gold = torch.from_numpy(np.load(os.path.join(GOLDEN, "warp_seed0_b2_64_16.npy")))
+    s, fl = s.cuda(), fl.cuda()
+    out = torch.empty_like(s)
+    G.ops.op_flow_warp(lib, s, fl, out).run()
+    m, _ = G.report("warp vs reference golden 64/16", out.cpu(), gold)
+    assert m < 1e-4          # fp32; coordinate rounding (ulp(64)*|dsrc|) bounds this
+    # BASELINE config 3(iii) shape, vs the torch restatement of flow_util on the GPU
+    s, fl = synth.warp_inputs(4, seed=1)
+    s, fl = s.cuda(), fl.cuda()
+    out = torch.empty_like(s)
+    G.ops.op_flow_warp(lib, s, fl, out).run()
+    ref = nets.warp_image(s, nets.convert_flow_to_deformation(fl))
+    m, _ = G.report("warp vs oracle 256/64", out, ref)
+    assert m < 2e-4 and (out - ref).abs().mean().item() < 2e-6
+    # same-size grid (no resize branch) + fp16 NHWC side output
+    fl2 = torch.randn(2, 2, 32, 32, device="cuda") * 2
+    s2 = torch.rand(2, 3, 32, 32, device="cuda")
+    out2 = torch.empty_like(s2)
+    side = torch.zeros(2, 32, 32, 8, dtype=torch.float16, device="cuda")
+    G.ops.op_flow_warp(lib, s2, fl2, out2, side, 3).run()
+    ref2 = nets.warp_image(s2, nets.convert_flow_to_deformation(fl2))
+    assert G.report("warp same-size", out2, ref2)[0] < 1e-4
+    assert (side[..., 3:6].permute(0, 3, 1, 2).float() - out2).abs().max().item() < 1e-3
+    assert side[..., :3].abs().max().item() == 0
+
+
+def test_mel_vs_oracle(G):
+    from oracle import mel as omel, synth
+    from s2v_b200.futils import audio
+    for seconds, seed in ((1.0, 0), (5.0, 0), (0.3, 3)):
+        wav = synth.wav(seconds, seed=seed)
+        ref = omel.melspectrogram(wav)
+        got = audio.melspectrogram(wav)
+        assert got.dtype == np.float64 and got.shape == ref.shape
+        d = np.abs(got - ref)
+        tol = 1e-4 * np.maximum(np.abs(ref), 1.0)
+        print("mel %.1fs max_abs=%.3e" % (seconds, d.max()))
+        assert (d <= tol).all()
+    # reflect padding variant and the windows
+    wav = synth.wav(5.0, seed=0)
+    ref = omel.melspectrogram(wav, pad_mode="reflect")
+    got = audio.melspectrogram(wav, pad_mode="reflect")
+    assert (np.abs(got - ref) <= 1e-4 * np.maximum(np.abs(ref), 1.0)).all()
+    mel_dev = audio.melspectrogram_device(torch.from_numpy(wav).cuda())
+    win = audio.mel_windows(mel_dev, fps=25.0)
+    assert win.shape == (122, 1, 80, 16)
+    starts = omel.mel_window_starts(mel_dev.shape[1], 25.0)
+    assert audio.mel_window_starts(mel_dev.shape[1], 25.0) == starts          # bit-exact indices
+    m = mel_dev.cpu()
+    for i in (0, 1, 5, 60, 120, 121):
+        assert torch.equal(win[i, 0].cpu(), m[:, starts[i]:starts[i] + 16])   # pure gather: bit-exact
+    for fps in (23.976, 30.0, 60.0):
+        for T in (16, 17, 401, 4801):
+            assert audio.mel_window_starts(T, fps) == omel.mel_window_starts(T, fps)
+
+
+def test_pack_unpack(G):
+    lib = G.lib()
+    src = torch.randn(3, 3, 20, 12, device="cuda")
+    dst = torch.full((3, 20, 12, 16), 7.0, dtype=torch.float16, device="cuda")
+    G.ops.op_pack(lib, src, dst, c_off=8, c_fill=8, scale=2.0, shift=-1.0).run()
+    assert (dst[..., :8] == 7).all() and (dst[..., 11:] == 0).all()
+    assert (dst[..., 8:11].permute(0, 3, 1, 2).float() - (src * 2 - 1)).abs().max().item() < 2e-3
+    back = torch.empty(3, 3, 20, 12, device="cuda")
+    G.ops.op_unpack(lib, dst, 8, 3, back).run()
+    assert torch.equal(back, dst[..., 8:11].permute(0, 3, 1, 2).float())
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=2, cin=3, cout=64, k=7, pad=3, h=20, w=24),
+    dict(n=2, cin=64, cout=3, k=7, pad=3, h=12, w=12, f32=True, act="sigmoid"),
+    dict(n=3, cin=32, cout=64, k=3, pad=1, h=20, w=16, stride=(3, 1), act="relu", scale=True),
+    dict(n=2, cin=64, cout=64, k=3, pad=1, h=9, w=6, act="relu", res1=True, scale=True),
+    dict(n=2, cin=16, cout=32, k=3, pad=1, h=10, w=10, reflect=True),
+    dict(n=2, cin=16, cout=32, k=3, pad=1, h=6, w=6, up2=True, act="lrelu"),
+    dict(n=2, cin=32, cout=64, k=4, pad=1, h=16, w=16, stride=(2, 2)),
+    dict(n=4, cin=512, cout=128, k=1, pad=0, h=1, w=1, act="relu"),
+    dict(n=2, cin=256, cout=2, k=7, pad=3, h=8, w=8, f32=True),
+    dict(n=2, cin=80, cout=48, k=(1, 3), pad=(0, 0), h=1, w=20, dil=(1, 3), res2=True),
+])
+def test_conv_simt(G, case):
+    lib = G.lib()
+    L = G.L
+    torch.manual_seed(1)
+    n, cin, cout, h, w = case["n"], case["cin"], case["cout"], case["h"], case["w"]
+    k = case["k"] if isinstance(case["k"], tuple) else (case["k"], case["k"])
+    pad = case["pad"] if isinstance(case["pad"], tuple) else (case["pad"], case["pad"])
+    stride, dil = case.get("stride", (1, 1)), case.get("dil", (1, 1))
+    x = torch.randn(n, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, *k, device="cuda") / (cin * k[0] * k[1]) ** 0.5
+    bias = torch.randn(cout, device="cuda")
+    scale = torch.rand(cout, device="cuda") + 0.5 if case.get("scale") else None
+    cin_p = -(-cin // 8) * 8
+    xh = torch.zeros(n, h, w, cin_p, dtype=torch.float16, device="cuda")
+    xh[..., :cin] = G.nhwc(x)
+    xr = xh[..., :cin].permute(0, 3, 1, 2).float()
+    xin = F.interpolate(xr, scale_factor=2) if case.get("up2") else xr
+    if case.get("reflect"):
+        ref = F.conv2d(F.pad(xin, (pad[1], pad[1], pad[0], pad[0]), mode="reflect"), wt, None, stride, 0, dil)
+    else:
+        ref = F.conv2d(xin, wt, None, stride, pad, dil)
+    if scale is not None:
+        ref = ref * scale[None, :, None, None]
+    ref = ref + bias[None, :, None, None]
+    oh, ow = ref.shape[2:]
+    r1 = r2 = None
+    if case.get("res1"):
+        r1 = torch.randn(n, oh, ow, cout, device="cuda").half()
+        ref = ref + r1.permute(0, 3, 1, 2).float()
+    act = {"relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "sigmoid": L.ACT_SIGMOID, None: L.ACT_NONE}[case.get("act")]
+    ref = {"relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.1), "sigmoid": torch.sigmoid, None: lambda t: t}[case.get("act")](ref)
+    if case.get("res2"):
+        r2 = torch.randn(n, oh, ow, cout, device="cuda").half()
+        ref = ref + r2.permute(0, 3, 1, 2).float()
+    wp = G.ops.pack_w_simt(wt, cin_p)
+    kw = dict(k=k, stride=stride, pad=pad, dil=dil, pad_mode=L.PAD_REFLECT if case.get("reflect") else L.PAD_ZERO,
+              up2=1 if case.get("up2") else 0, scale=scale, bias=bias, res1=r1, res2=r2, act=act, act_param=0.1, impl="simt")
+    if case.get("f32"):
+        y = torch.zeros(n, cout, oh, ow, device="cuda")
+        G.ops.op_conv(lib, xh, wp, None, y_f32=y, out_shape=(n, cout, oh, ow), **kw).run()
+        got = y
+        tol = 2e-4
+    else:
+        y = torch.zeros(n, oh, ow, -(-cout // 8) * 8, dtype=torch.float16, device="cuda")
+        yv = y[..., :cout] if cout % 8 == 0 else y
+        G.ops.op_conv(lib, xh, wp, yv, **kw).run()
+        got = G.nchw(y[..., :cout])
+        tol = 4e-3
+    torch.cuda.synchronize()
+    m, rel = G.report("conv_simt %s" % case, got, ref)
+    assert rel < tol
+
+
+def _norm_inputs(n, c, h, w):
+    torch.manual_seed(2)
+    x = torch.randn(n, c, h, w, device="cuda") * 1.7 + 0.3
+    return x, G_nhwc(x)
+
+
+def G_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().half()
+
+
+@pytest.mark.parametrize("n,c,h,w,pool", [(3, 64, 24, 24, 0), (2, 128, 16, 16, 1), (2, 512, 12, 12, 0), (1, 1024, 12, 12, 0)])
+def test_layernorm2d(G, n, c, h, w, pool):
+    lib = G.lib()
+    L = G.L
+    x, xh = _norm_inputs(n, c, h, w)
+    xf = xh.permute(0, 3, 1, 2).float()
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    ref = F.leaky_relu(F.layer_norm(xf, xf.shape[1:], gamma[:, None, None].expand(c, h, w), beta[:, None, None].expand(c, h, w)), 0.1)
+    if pool:
+        ref = F.avg_pool2d(ref, 2)
+    res = torch.randn(n, ref.shape[2], ref.shape[3], c, device="cuda").half()
+    ref = ref + res.permute(0, 3, 1, 2).float()
+    chunks = G.ops.stats_chunks(n, h * w)
+    partial = torch.empty(n, chunks, c, 2, device="cuda")
+    a, b = torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda")
+    y = torch.empty(n, ref.shape[2], ref.shape[3], c, dtype=torch.float16, device="cuda")
+    G.ops.op_chan_stats(lib, xh, chunks, partial).run()
+    G.ops.op_ln2d_finalize(lib, partial, n, chunks, c, h * w, gamma, beta, a, b).run()
+    G.ops.op_affine_act(lib, xh, a, b, y, act=L.ACT_LRELU, act_param=0.1, pool2=pool, res=res).run()
+    m, rel = G.report("layernorm2d n%d c%d %dx%d pool%d" % (n, c, h, w, pool), G.nchw(y), ref)
+    assert rel < 2e-3
+
+
+@pytest.mark.parametrize("n,c,h,w", [(3, 64, 12, 12), (2, 1024, 12, 12), (2, 256, 24, 24), (2, 32, 40, 40)])
+def test_adain_reflect(G, n, c, h, w):
+    lib = G.lib()
+    L = G.L
+    x, xh = _norm_inputs(n, c, h, w)
+    xf = xh.permute(0, 3, 1, 2).float()
+    gb = torch.randn(n, 2 * c + 5, device="cuda") * 0.3
+    gamma, beta = gb[:, :c], gb[:, c:2 * c]
+    ref = F.leaky_relu(F.instance_norm(xf, eps=1e-5) * (1 + gamma[:, :, None, None]) + beta[:, :, None, None], 0.01)
+    res = torch.randn(n, h, w, c, device="cuda").half()
+    ref = ref + res.permute(0, 3, 1, 2).float()
+    refp = F.pad(ref, (1, 1, 1, 1), mode="reflect")
+    chunks = G.ops.stats_chunks(n, h * w)
+    partial = torch.empty(n, chunks, c, 2, device="cuda")
+    a, b = torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda")
+    yp = torch.zeros(n, h + 2, w + 2, c, dtype=torch.float16, device="cuda")
+    G.ops.op_chan_stats(lib, xh, chunks, partial).run()
+    G.ops.op_adain_finalize(lib, partial, n, chunks, c, h * w, gamma, beta, gb.stride(0), a, b).run()
+    G.ops.op_affine_act(lib, xh, a, b, yp[:, 1:-1, 1:-1, :], act=L.ACT_LRELU, act_param=0.01, res=res, reflect1=1).run()
+    m, rel = G.report("adain+reflect n%d c%d %dx%d" % (n, c, h, w), G.nchw(yp), refp)
+    assert rel < 2e-3
+    # standalone border fill
+    yp2 = yp.clone()
+    yp2[:, 0] = 0; yp2[:, -1] = 0; yp2[:, :, 0] = 0; yp2[:, :, -1] = 0
+    G.ops.op_reflect_border(lib, yp2[:, 1:-1, 1:-1, :]).run()
+    assert torch.equal(yp2, yp)
+
+
+def test_token_layernorm_add_mean(G):
+    lib = G.lib()
+    torch.manual_seed(3)
+    x = torch.randn(2, 12, 12, 1024, device="cuda").half()
+    xs = x[..., :512]
+    g, b = torch.rand(512, device="cuda") + 0.5, torch.randn(512, device="cuda") * 0.1
+    y = torch.empty(2, 12, 12, 512, dtype=torch.float16, device="cuda")
+    G.ops.op_token_ln(lib, xs, g, b, y).run()
+    ref = F.layer_norm(xs.float(), (512,), g, b)
+    assert G.report("token_layernorm", y, ref)[1] < 2e-3
+    a2 = torch.randn(2, 6, 6, 64, device="cuda").half()
+    b2 = torch.randn(2, 6, 6, 64, device="cuda").half()
+    y2 = torch.empty_like(a2)
+    G.ops.op_add(lib, a2, b2, y2).run()
+    assert torch.equal(y2, (a2.float() + b2.float()).half())
+    xm = torch.randn(3, 1, 2, 256, device="cuda").half()
+    ym = torch.empty(3, 1, 1, 256, dtype=torch.float16, device="cuda")
+    G.ops.op_mean_over_w(lib, xm, ym).run()
+    assert (ym.float() - xm.float().mean(2, keepdim=True)).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("s,c", [(12, 384), (24, 96), (48, 48), (12, 8), (24, 24)])
+def test_fft2(G, s, c):
+    lib = G.lib()
+    torch.manual_seed(4)
+    n = 3
+    x = torch.randn(n, c, s, s, device="cuda")
+    xh = G.nhwc(x)
+    xf = xh.permute(0, 3, 1, 2).float()
+    spec = torch.empty(n, s, s // 2 + 1, 2 * c, dtype=torch.float16, device="cuda")
+    G.ops.op_rfft2(lib, xh, spec).run()
+    ff = torch.fft.rfftn(xf, dim=(-2, -1), norm="ortho")
+    ref = torch.stack((ff.real, ff.imag), dim=-1).permute(0, 1, 4, 2, 3).reshape(n, 2 * c, s, s // 2 + 1)
+    assert G.report("rfft2 %dx%d c%d" % (s, s, c), G.nchw(spec), ref)[1] < 2e-3
+    # inverse on a NON-Hermitian spectrum (post-ReLU in the reference), + residual add
+    z = F.relu(torch.randn(n, 2 * c, s, s // 2 + 1, device="cuda"))
+    zh = G.nhwc(z)
+    zf = zh.permute(0, 3, 1, 2).float().reshape(n, c, 2, s, s // 2 + 1).permute(0, 1, 3, 4, 2)
+    refi = torch.fft.irfftn(torch.complex(zf[..., 0].contiguous(), zf[..., 1].contiguous()), s=(s, s), dim=(-2, -1), norm="ortho")
+    add = torch.randn(n, s, s, c, device="cuda").half()
+    y = torch.empty(n, s, s, c, dtype=torch.float16, device="cuda")
+    G.ops.op_irfft2(lib, zh, add, y).run()
+    assert G.report("irfft2 %dx%d c%d" % (s, s, c), G.nchw(y), refi + add.permute(0, 3, 1, 2).float())[1] < 2e-3
+
+
+def test_attention(G):
+    lib = G.lib()
+    torch.manual_seed(5)
+    n, t, heads, dh = 3, 144, 4, 64
+    qk = torch.randn(n, 1, t, 2 * heads * dh, device="cuda").half()
+    v = torch.randn(n, 1, t, heads * dh, device="cuda").half()
+    o = torch.empty(n, 1, t, heads * dh, dtype=torch.float16, device="cuda")
+    G.ops.op_attention(lib, qk[..., :256], qk[..., 256:], v, o, heads, dh ** -0.5).run()
+    q, k = (qk[..., i * 256:(i + 1) * 256].float().reshape(n, t, heads, dh).permute(0, 2, 1, 3) for i in (0, 1))
+    vv = v.float().reshape(n, t, heads, dh).permute(0, 2, 1, 3)
+    ref = (torch.matmul(q, k.transpose(-1, -2)) * dh ** -0.5).softmax(-1) @ vv
+    ref = ref.permute(0, 2, 1, 3).reshape(n, 1, t, heads * dh)
+    assert G.report("attention", o, ref)[1] < 3e-3
+
+
+def test_grouped_linear(G):
+    import ctypes as C
+    lib = G.lib()
+    L = G.L
+    torch.manual_seed(6)
+    B = 11
+    hidden = F.relu(torch.randn(B, 1, 1, 3 * 128, device="cuda")).half()
+    specs = [(0, 256), (128, 768), (256, 40)]
+    wts = [torch.randn(128, no, device="cuda") * 0.1 for _, no in specs]
+    bs = [torch.randn(no, device="cuda") for _, no in specs]
+    total = sum(no for _, no in specs)
+    groups = (L.LinGroup * len(specs))()
+    tiles, off = [], 0
+    for i, (ino, no) in enumerate(specs):
+        groups[i] = L.LinGroup(wts[i].data_ptr(), bs[i].data_ptr(), ino, 128, off, no)
+        tiles += [(i, j) for j in range(0, no, 128)]
+        off += no
+    gdev = torch.frombuffer(bytearray(bytes(groups)), dtype=torch.uint8).cuda()
+    tdev = torch.tensor(tiles, dtype=torch.int32, device="cuda")
+    out = torch.zeros(B, total, device="cuda")
+    G.ops.op_grouped_linear(lib, hidden, gdev, tdev, len(tiles), out).run()
+    ref = torch.cat([hidden.reshape(B, -1)[:, ino:ino + 128].float() @ wts[i] + bs[i] for i, (ino, _) in enumerate(specs)], 1)
+    assert G.report("grouped_linear", out, ref)[1] < 1e-5
