@@ -1,0 +1,32 @@
+"""Drop-in mirrors of the reference's models package for the hot path (LNet, DNet).
+
+``load_checkpoint`` / ``load_network`` / ``load_DNet`` keep the behaviour of the reference's
+models/__init__.py:12-56 (strip ``module.``, drop ``low_res`` keys, strict=False; DNet from
+``checkpoint['net_G_ema']``)."""
+import torch
+
+
+def _load(checkpoint_path):
+    return torch.load(checkpoint_path, map_location=lambda storage, loc: storage)
+
+
+def load_checkpoint(path, model):
+    print("Load checkpoint from: {}".format(path))
+    checkpoint = _load(path)
+    s = checkpoint["state_dict"] if "arcface" not in path else checkpoint
+    new_s = {}
+    for k, v in s.items():
+        if "low_res" in k:
+            continue
+        new_s[k.replace("module.", "")] = v
+    model.load_state_dict(new_s, strict=False)
+    return model
+
+
+def load_DNet(args):
+    from .DNet import DNet
+    device = "cuda"
+    net = DNet()
+    checkpoint = torch.load(args.DNet_path, map_location=lambda storage, loc: storage)
+    net.load_state_dict(checkpoint["net_G_ema"], strict=False)
+    return net.to(device).eval()
