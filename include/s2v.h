@@ -113,8 +113,10 @@ int s2v_warp_deformation_f32(const float* src, const float* deformation, float* 
 /* ------------------------------------------------------------- layout ---
  * NCHW float32 [N,C,H,W] -> fp16 NHWC view channels [c_off, c_off+C); channels
  * [c_off+C, c_off+c_fill) are zero-filled (channel padding to a multiple of 8).
- * values are written as src*scale + shift.                                      */
-int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, const s2v_view* dst,
+ * values are written as src*scale + shift.  src_sn = elements between samples
+ * (>= C*H*W; lets a channel window of a wider NCHW tensor be packed in place,
+ * e.g. the masked / reference halves of LNet's 6-channel face input).           */
+int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, int64_t src_sn, const s2v_view* dst,
                       int c_off, int c_fill, float scale, float shift, void* stream);
 int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, float* dst, void* stream);
 

@@ -6,8 +6,9 @@ namespace s2v {
 
 // one thread per (n, y, x): reads C strided floats (coalesced along x per channel),
 // writes c_fill contiguous halves.
-__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, int N, int C, int H, int W, View d,
-                                                   int c_off, int c_fill, float scale, float shift) {
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, int N, int C, int H, int W,
+                                                   long long src_sn, View d, int c_off, int c_fill, float scale,
+                                                   float shift) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * H * W;
   if (idx >= total) return;
@@ -15,7 +16,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
   const int y = (int)((idx / W) % H);
   const int n = (int)(idx / ((long long)W * H));
   __half* o = d.p + n * d.sn + y * d.sh + x * d.sw + c_off;
-  const float* s = src + ((size_t)n * C * H + y) * W + x;
+  const float* s = src + (size_t)n * src_sn + (size_t)y * W + x;
   const size_t plane = (size_t)H * W;
   for (int c = 0; c < c_fill; ++c) o[c] = __float2half_rn(c < C ? fmaf(s[c * plane], scale, shift) : 0.f);
 }
@@ -37,13 +38,13 @@ __global__ void __launch_bounds__(256) unpack_kernel(View s, int c_off, int C, f
 
 using namespace s2v;
 
-extern "C" int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, const s2v_view* dst, int c_off,
-                                 int c_fill, float scale, float shift, void* stream) {
+extern "C" int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, int64_t src_sn, const s2v_view* dst,
+                                 int c_off, int c_fill, float scale, float shift, void* stream) {
   if (N == 0) return S2V_OK;
   if (!src || !view_ok(dst) || C <= 0 || c_fill < C || c_off < 0 || c_off + c_fill > dst->c) return S2V_EINVAL;
-  if (dst->n < N || dst->h != H || dst->w != W) return S2V_EINVAL;
+  if (dst->n < N || dst->h != H || dst->w != W || src_sn < (int64_t)C * H * W) return S2V_EINVAL;
   const long long total = (long long)N * H * W;
-  pack_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(src, N, C, H, W, mk(dst), c_off, c_fill, scale, shift);
+  pack_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(src, N, C, H, W, src_sn, mk(dst), c_off, c_fill, scale, shift);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

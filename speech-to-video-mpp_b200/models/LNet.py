@@ -1,0 +1,303 @@
+"""Drop-in for the reference's models/LNet.py: same constructor defaults, ``forward(audio_sequences,
+face_sequences)`` signature (4-D and 5-D forms, models/LNet.py:122-139) and state_dict schema
+(1721 tensors incl. spectral-norm ``weight_orig/_u/_v`` and BatchNorm buffers), executed by
+hand-written sm_100a kernels through libs2v's C ABI.
+
+Precision recipe (plain bf16 operands give ~39 dB, below the 45 dB gate): fp16 operands /
+fp32 accumulation on the tcgen05 convs and linears, fp16 channels-last activations between kernels,
+fp32 for all statistics, affine parameters, FFT butterflies, softmax and the SIMT layers' weights.
+
+Data flow per forward (B frames):
+  pack NCHW f32 -> NHWC f16 | audio encoder (13 SIMT convs, BN folded) -> z | all 108 AdaIN MLPs in
+  2 launches | two visual towers (7x7 SIMT stem, 3x3 tcgen05 convs, LayerNorm2d+LReLU+AvgPool fused
+  apply) | 2-layer cross-attention at 12x12 | 54 FFC layers (two 3x3 reflect tcgen05 convs on a
+  pre-padded buffer, 1x1 -> rfft2 -> 1x1 -> irfft2 -> 1x1 spectral branch, InstanceNorm-AdaIN apply
+  that also writes the reflect border) | sub-pixel up convs, Jump skips | 7x7 SIMT head + sigmoid.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from . import _schema
+from ._engine import EngineBase, bn_fold, sn_fold, up2_phase_weights
+
+
+class LNetEngine(EngineBase):
+    def __init__(self, sd, device, layer=3, base_nc=64, max_nc=512, num_res_blocks=9, descriptor_nc=512,
+                 conv_impl="tc", use_graph=True):
+        super().__init__(device, conv_impl, use_graph)
+        self.layer, self.base_nc, self.max_nc, self.nblk, self.dnc = layer, base_nc, max_nc, num_res_blocks, descriptor_nc
+        assert layer == 3 and base_nc == 64 and max_nc == 512, "kernels are specialised for the default LNet geometry"
+        sd = {k: v.detach().to(device) for k, v in sd.items()}
+        self._pack(sd)
+
+    # ------------------------------------------------------------------ weights
+    def _pack(self, sd):
+        f32 = lambda t: t.float().contiguous()
+        self.P = {}                                   # small fp32 parameter vectors
+        for t in ("inp", "ref"):
+            p = f"encoder.first_{t}.model"
+            self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"], impl="simt", cin_pad=8)
+            self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
+            for i in range(self.layer):
+                p = f"encoder.{t}_down{i}.model"
+                self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"])
+                self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
+        for l in range(2):
+            a, f = f"encoder.ca2.layers.{l}.0", f"encoder.ca2.layers.{l}.1"
+            for nm in ("normx", "normy"):
+                self.P[f"{a}.{nm}.g"], self.P[f"{a}.{nm}.b"] = f32(sd[f"{a}.{nm}.weight"]), f32(sd[f"{a}.{nm}.bias"])
+            self.P[f + ".norm.g"], self.P[f + ".norm.b"] = f32(sd[f + ".norm.weight"]), f32(sd[f + ".norm.bias"])
+            wqk = torch.cat([sd[a + ".fn.to_q.weight"], sd[a + ".fn.to_k.weight"]], 0).float()
+            self.pack_conv(a + ".qk", wqk[:, :, None, None])
+            self.pack_conv(a + ".v", sd[a + ".fn.to_v.weight"].float()[:, :, None, None])
+            self.pack_conv(a + ".out", sd[a + ".fn.to_out.0.weight"].float()[:, :, None, None], sd[a + ".fn.to_out.0.bias"])
+            self.pack_conv(f + ".fc1", sd[f + ".fn.net.0.weight"].float()[:, :, None, None], sd[f + ".fn.net.0.bias"])
+            self.pack_conv(f + ".fc2", sd[f + ".fn.net.3.weight"].float()[:, :, None, None], sd[f + ".fn.net.3.bias"])
+        # decoder
+        shared_w, shared_b, groups = [], [], []
+        inst, off = 0, 0
+        self.gb_off = {}
+        for i in range(self.layer)[::-1]:
+            c = self.base_nc * 2 ** (i + 1) * 2 if i == self.layer - 1 else min(self.base_nc * 2 ** (i + 1), self.max_nc)
+            cg = int(c * 0.75)
+            cl = c - cg
+            for b in range(self.nblk):
+                for cv in ("conv1", "conv2"):
+                    p = f"decoder.res{i}.res{b}.{cv}"
+                    q = p + ".ffc"
+                    self.pack_conv(q + ".to_l", torch.cat([sd[q + ".convl2l.weight"], sd[q + ".convg2l.weight"]], 1).float())
+                    self.pack_conv(q + ".l2g", sd[q + ".convl2g.weight"].float())
+                    s1, b1 = bn_fold(sd, q + ".convg2g.conv1.1")
+                    self.pack_conv(q + ".st1", sd[q + ".convg2g.conv1.0.weight"].float(), b1, s1)
+                    s2, b2 = bn_fold(sd, q + ".convg2g.fu.bn")
+                    self.pack_conv(q + ".fu", sd[q + ".convg2g.fu.conv_layer.weight"].float(), b2, s2)
+                    self.pack_conv(q + ".st2", sd[q + ".convg2g.conv2.weight"].float())
+                    # AdaIN heads: output row layout per FFC layer  [gamma_l | gamma_g | beta_l | beta_g]
+                    self.gb_off[p] = off
+                    for br, o_g, o_b in (("bn_l", 0, c), ("bn_g", cl, c + cl)):
+                        r = f"{p}.{br}"
+                        shared_w.append(sd[r + ".mlp_shared.0.weight"].float())
+                        shared_b.append(sd[r + ".mlp_shared.0.bias"].float())
+                        groups.append((sd[r + ".mlp_gamma.weight"].float().t(), sd[r + ".mlp_gamma.bias"], inst * 128, off + o_g))
+                        groups.append((sd[r + ".mlp_beta.weight"].float().t(), sd[r + ".mlp_beta.bias"], inst * 128, off + o_b))
+                        inst += 1
+                    off += 2 * c
+            p = f"decoder.up{i}.model"
+            w_up = sn_fold(sd, p + ".0")
+            if self.impl == "tc":
+                for (ph, qh), w4 in up2_phase_weights(w_up).items():
+                    self.pack_conv(f"{p}.ph{ph}{qh}", w4, sd[p + ".0.bias"])
+            else:
+                self.pack_conv(p, w_up, sd[p + ".0.bias"])
+            self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
+            p = f"decoder.jump{i}.model"
+            self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"])
+            self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
+        self.gb_total, self.n_inst = off, inst
+        self.pack_conv("adain.shared", torch.cat(shared_w, 0)[:, :, None, None], torch.cat(shared_b, 0), impl="simt")
+        self.pack_lin_groups("adain.heads", groups)
+        p = "decoder.final.model.0"
+        self.pack_conv(p, sn_fold(sd, p), sd[p + ".bias"], impl="simt")
+        for i, (cin, cout, k, stride, pad, res) in enumerate(_schema.AUDIO_CFG):
+            p = f"audio_encoder.{i}.conv_block"
+            s, b = bn_fold(sd, p + ".1", sd[p + ".0.bias"])
+            self.pack_conv(p, sd[p + ".0.weight"].float(), b, s, impl="simt", cin_pad=8 if cin == 1 else None)
+
+    # ------------------------------------------------------------------ plan
+    def _build(self, B):
+        def builder(plan, ws):
+            lib, buf = self.lib, lambda *a, **k: self.buf(ws, *a, **k)
+            mel_in = buf("in.mel", (B, 1, 80, 16), torch.float32)
+            face_in = buf("in.face", (B, 6, 96, 96), torch.float32)
+            out = buf("out", (B, 3, 96, 96), torch.float32)
+
+            # ---- audio encoder -> z [B,1,1,512] ------------------------------------------
+            x = buf("aud.in", (B, 80, 16, 8))
+            plan.add(ops.op_pack(lib, mel_in, x, 0, 8))
+            for i, (cin, cout, k, stride, pad, res) in enumerate(_schema.AUDIO_CFG):
+                h, w = x.shape[1], x.shape[2]
+                oh, ow = (h + 2 * pad - k) // stride[0] + 1, (w + 2 * pad - k) // stride[1] + 1
+                y = buf(f"aud.{i}", (B, oh, ow, cout))
+                self.conv(plan, f"audio_encoder.{i}.conv_block", x, y, stride=stride, pad=(pad, pad),
+                          res1=x if res else None, act=L.ACT_RELU)
+                x = y
+            z = x
+            # ---- every AdaIN gamma/beta of the decoder (depends only on z) -----------------
+            hidden = buf("adain.hidden", (B, 1, 1, self.n_inst * 128))
+            self.conv(plan, "adain.shared", z, hidden, act=L.ACT_RELU)
+            gb = buf("adain.gb", (B, self.gb_total), torch.float32)
+            hd = self.W["adain.heads"]
+            plan.add(ops.op_grouped_linear(lib, hidden, hd["groups"], hd["tiles"], hd["n_tiles"], gb))
+
+            # ---- visual encoder --------------------------------------------------------------
+            xp2 = [buf(f"dec2.xp{j}", (B, 14, 14, 1024), zero=True) for j in range(3)]
+            cat = xp2[0][:, 1:-1, 1:-1, :]
+            feats = {}
+            for t, c_lo in (("inp", 0), ("ref", 3)):       # masked face = planes 0-2, reference = planes 3-5
+                feats[t] = buf(f"enc.{t}.in8", (B, 96, 96, 8))
+                plan.add(ops.op_pack(lib, face_in[:, c_lo:c_lo + 3], feats[t], 0, 8))
+            skips = []
+            for t in ("inp", "ref"):
+                x = feats[t]
+                p = f"encoder.first_{t}.model"
+                raw = buf("enc.raw0", (B, 96, 96, 64))
+                self.conv(plan, p, x, raw, pad=(3, 3))
+                a0 = buf(f"enc.{t}.a0", (B, 96, 96, 64))
+                self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0)
+                x = a0
+                if t == "inp":
+                    skips.append(a0)
+                for i in range(3):
+                    p = f"encoder.{t}_down{i}.model"
+                    s, co = 96 >> i, 128 << i
+                    raw = buf(f"enc.raw{i + 1}", (B, s, s, co))
+                    self.conv(plan, p, x, raw, pad=(1, 1))
+                    if i < 2:
+                        y = buf(f"enc.{t}.a{i + 1}", (B, s // 2, s // 2, co))
+                        if t == "inp":
+                            skips.append(y)
+                    else:
+                        y = cat[..., :512] if t == "inp" else cat[..., 512:]
+                    self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], y, pool2=1)
+                    x = y
+            # ---- cross attention at 12x12 (tokens = pixels) ----------------------------------
+            X, Y = cat[..., :512], cat[..., 512:]
+            lnx, lny, ln2 = buf("ca.lnx", (B, 12, 12, 512)), buf("ca.lny", (B, 12, 12, 512)), buf("ca.ln2", (B, 12, 12, 512))
+            qk, v, o, hdn = buf("ca.qk", (B, 12, 12, 512)), buf("ca.v", (B, 12, 12, 256)), buf("ca.o", (B, 12, 12, 256)), buf("ca.h", (B, 12, 12, 256))
+            tok = lambda t: t.reshape(B, 1, 144, t.shape[-1])
+            for l in range(2):
+                a, f = f"encoder.ca2.layers.{l}.0", f"encoder.ca2.layers.{l}.1"
+                plan.add(ops.op_token_ln(lib, X, self.P[a + ".normx.g"], self.P[a + ".normx.b"], lnx))
+                plan.add(ops.op_token_ln(lib, Y, self.P[a + ".normy.g"], self.P[a + ".normy.b"], lny))
+                self.conv(plan, a + ".qk", lnx, qk)
+                self.conv(plan, a + ".v", lny, v)
+                plan.add(ops.op_attention(lib, tok(qk)[..., :256], tok(qk)[..., 256:], tok(v), tok(o), 4, 64 ** -0.5))
+                self.conv(plan, a + ".out", o, X, res2=X)
+                plan.add(ops.op_token_ln(lib, X, self.P[f + ".norm.g"], self.P[f + ".norm.b"], ln2))
+                self.conv(plan, f + ".fc1", ln2, hdn, act=L.ACT_GELU)
+                self.conv(plan, f + ".fc2", hdn, X, res2=X)
+            plan.add(ops.op_reflect_border(lib, cat))
+
+            # ---- decoder ---------------------------------------------------------------------
+            xps = xp2
+            for i in (2, 1, 0):
+                S = 12 << (2 - i)
+                c = xps[0].shape[-1]
+                cg = int(c * 0.75)
+                cl, ch = c - cg, int(c * 0.75) // 2
+                R = buf(f"dec{i}.R", (B, S, S, c))
+                s1, s2 = buf(f"dec{i}.s1", (B, S, S, ch)), buf(f"dec{i}.s2", (B, S, S, ch))
+                F1, F2 = buf(f"dec{i}.F1", (B, S, S // 2 + 1, 2 * ch)), buf(f"dec{i}.F2", (B, S, S // 2 + 1, 2 * ch))
+                flat = lambda t: t.reshape(1, 1, -1, t.shape[-1])
+                cur = 0
+                for b in range(self.nblk):
+                    xin = xps[cur]
+                    mid, nxt = xps[(cur + 1) % 3], xps[(cur + 2) % 3]
+                    for cv, src, dst, res in (("conv1", xin, mid, None), ("conv2", mid, nxt, xin)):
+                        p = f"decoder.res{i}.res{b}.{cv}"
+                        q = p + ".ffc"
+                        inter = src[:, 1:-1, 1:-1, :]
+                        self.conv(plan, q + ".to_l", src, R[..., :cl])                     # l2l + g2l, 3x3 reflect
+                        self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])            # l2g, 3x3 reflect
+                        self.conv(plan, q + ".st1", inter[..., cl:], s1, act=L.ACT_RELU)   # 1x1 + BN + ReLU
+                        plan.add(ops.op_rfft2(lib, s1, F1))
+                        self.conv(plan, q + ".fu", flat(F1), flat(F2), act=L.ACT_RELU)     # spectral 1x1 + BN + ReLU
+                        plan.add(ops.op_irfft2(lib, F2, s1, s2))                           # x + fu(x)
+                        self.conv(plan, q + ".st2", s2, R[..., cl:], res2=R[..., cl:])     # + l2g partial sum
+                        off = self.gb_off[p]
+                        self.adain(plan, ws, p, R, gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0),
+                                   dst[:, 1:-1, 1:-1, :], slope=0.01,
+                                   res=None if res is None else res[:, 1:-1, 1:-1, :], reflect1=1)
+                    cur = (cur + 2) % 3
+                dec_out = xps[cur][:, 1:-1, 1:-1, :]
+                co = c // 4 if i == 2 else c // 2
+                S2 = 2 * S
+                p = f"decoder.up{i}.model"
+                uraw = buf(f"dec{i}.uraw", (B, S2, S2, co))
+                if self.impl == "tc":
+                    for ph in (0, 1):
+                        for qh in (0, 1):
+                            self.conv(plan, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], pad=(1 - ph, 1 - qh))
+                else:
+                    self.conv(plan, p, dec_out, uraw, pad=(1, 1), up2=1)
+                uact = buf(f"dec{i}.uact", (B, S2, S2, co))
+                self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact)
+                p = f"decoder.jump{i}.model"
+                jraw = buf(f"dec{i}.jraw", (B, S2, S2, co))
+                self.conv(plan, p, skips[i], jraw, pad=(1, 1))
+                if i > 0:
+                    xps = [buf(f"dec{i - 1}.xp{j}", (B, S2 + 2, S2 + 2, co), zero=True) for j in range(3)]
+                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], xps[0][:, 1:-1, 1:-1, :],
+                                     res=uact, reflect1=1)
+                else:
+                    last = buf("dec.last", (B, 96, 96, 64))
+                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uact)
+            self.conv(plan, "decoder.final.model.0", last, None, pad=(3, 3), act=L.ACT_SIGMOID, y_f32=out,
+                      out_shape=(B, 3, 96, 96))
+            return dict(mel=mel_in, face=face_in, out=out)
+
+        return builder
+
+    def forward(self, mel, face):
+        """mel [B,1,80,16], face [B,6,96,96] float32 CUDA -> [B,3,96,96] float32 (a fresh tensor)."""
+        B = mel.shape[0]
+        ent = self._get_plan(B, self._build(B))
+        io = ent["io"]
+        io["mel"].copy_(mel, non_blocking=True)
+        io["face"].copy_(face, non_blocking=True)
+        self._run(ent)
+        return io["out"].clone()
+
+
+class LNet(nn.Module):
+    """Same constructor arguments as the reference (models/LNet.py:81-92); ``encoder`` / ``decoder``
+    class hooks are accepted for signature compatibility but the architecture is fixed."""
+
+    def __init__(self, image_nc=3, descriptor_nc=512, layer=3, base_nc=64, max_nc=512, num_res_blocks=9,
+                 use_spect=True, encoder=None, decoder=None, conv_impl="tc", use_graph=True):
+        super().__init__()
+        self.descriptor_nc = descriptor_nc
+        self._cfg = dict(layer=layer, base_nc=base_nc, max_nc=max_nc, num_res_blocks=num_res_blocks,
+                         descriptor_nc=descriptor_nc)
+        self._conv_impl, self._use_graph = conv_impl, use_graph
+        _schema.build_param_tree(self, _schema.lnet_spec(image_nc, descriptor_nc, layer, base_nc, max_nc,
+                                                         num_res_blocks, use_spect))
+        self._engine = None
+        self._engine_key = None
+        self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
+
+    def _invalidate(self):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self) -> LNetEngine:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise L.S2VError("LNet runs on CUDA only (sm_100a kernels, no CPU fallback); call .cuda() first")
+        if self._engine is None or self._engine_key != dev:
+            self._engine = LNetEngine(self.state_dict(), dev, conv_impl=self._conv_impl, use_graph=self._use_graph,
+                                      **self._cfg)
+            self._engine_key = dev
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, audio_sequences, face_sequences):
+        if self.training:
+            raise L.S2VError("this LNet is an inference engine (eval-mode semantics); call .eval()")
+        B = audio_sequences.size(0)
+        five_d = face_sequences.dim() > 4
+        if five_d:            # time-major flatten, models/LNet.py:125-127
+            audio_sequences = torch.cat([audio_sequences[:, i] for i in range(audio_sequences.size(1))], dim=0)
+            face_sequences = torch.cat([face_sequences[:, :, i] for i in range(face_sequences.size(2))], dim=0)
+        eng = self.engine()
+        out = eng.forward(audio_sequences.float().contiguous(), face_sequences.float().contiguous())
+        if five_d:
+            out = torch.stack(torch.split(out, B, dim=0), dim=2)
+        return out

@@ -1,0 +1,157 @@
+"""Shared machinery of the LNet / DNet CUDA engines: weight folding, workspace arena, norm
+helpers, CUDA-graph capture.  Everything here only *orders* C-ABI calls; all arithmetic on the
+path happens in libs2v's kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+from .. import ops
+
+
+def sn_fold(sd, p):
+    """Eval-mode spectral norm: W / (u^T W_mat v) with the STORED u, v (reference quirk C.4,
+    models/base_blocks.py:72-76); plain ``weight`` when the conv has no spectral norm."""
+    if p + ".weight" in sd:
+        return sd[p + ".weight"].float()
+    w = sd[p + ".weight_orig"].float()
+    sigma = torch.dot(sd[p + ".weight_u"].float(), torch.mv(w.flatten(1), sd[p + ".weight_v"].float()))
+    return w / sigma
+
+
+def bn_fold(sd, p, conv_bias=None, eps=1e-5):
+    """Eval BatchNorm after a conv -> per-channel (scale, shift) for the conv epilogue."""
+    s = sd[p + ".weight"].float() / torch.sqrt(sd[p + ".running_var"].float() + eps)
+    b = sd[p + ".bias"].float() - sd[p + ".running_mean"].float() * s
+    if conv_bias is not None:
+        b = b + conv_bias.float() * s
+    return s.contiguous(), b.contiguous()
+
+
+def up2_phase_weights(w):
+    """nearest-x2 upsample followed by a 3x3 zero-padded conv == four 2x2 convs on the low-res
+    input, one per output parity (p,q), with top/left padding (1-p, 1-q).  Returns {(p,q): w2x2}."""
+    grp = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = {}
+    for p in (0, 1):
+        for q in (0, 1):
+            w4 = torch.zeros(w.shape[0], w.shape[1], 2, 2, dtype=w.dtype, device=w.device)
+            for a in (0, 1):
+                for b in (0, 1):
+                    for ky in grp[p][a]:
+                        for kx in grp[q][b]:
+                            w4[:, :, a, b] += w[:, :, ky, kx]
+            out[(p, q)] = w4
+    return out
+
+
+class EngineBase:
+    """Holds packed weights + per-batch-size plans (workspace + op list + optional CUDA graph)."""
+
+    def __init__(self, device: torch.device, conv_impl: str = "tc", use_graph: bool = True):
+        self.dev = device
+        # a CPU "device" only builds plans (shape/ABI validation in the -m "not gpu" tests); nothing can run there
+        self.lib = L.require_device(device.index) if device.type == "cuda" else L.load_library()
+        self.impl = conv_impl
+        self.use_graph = use_graph
+        self.W = {}
+        self._plans = {}
+
+    # ---- workspace ---------------------------------------------------------------------
+    def buf(self, ws, name, shape, dtype=torch.float16, zero=False):
+        if name in ws:
+            t = ws[name]
+            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, name
+            return t
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
+        ws[name] = t
+        return t
+
+    # ---- conv helpers ------------------------------------------------------------------
+    def pack_conv(self, name, w, bias=None, scale=None, impl=None, cin_pad=None):
+        """w: folded fp32 [Cout,Cin,kh,kw]."""
+        impl = impl or self.impl
+        ent = dict(impl=impl, k=(w.shape[2], w.shape[3]), cout=w.shape[0],
+                   bias=None if bias is None else bias.float().contiguous(),
+                   scale=None if scale is None else scale.float().contiguous())
+        ent["w"] = ops.pack_w_tc(w) if impl == "tc" else ops.pack_w_simt(w, cin_pad)
+        self.W[name] = ent
+        return ent
+
+    def conv(self, plan, name, x, y, **kw):
+        e = self.W[name]
+        kw.setdefault("k", e["k"])
+        kw.setdefault("bias", e["bias"])
+        kw.setdefault("scale", e["scale"])
+        return plan.add(ops.op_conv(self.lib, x, e["w"], y, impl=e["impl"], name=name, **kw))
+
+    # ---- norm helpers ------------------------------------------------------------------
+    def _stats(self, plan, ws, tag, x):
+        n, h, w, c = x.shape
+        chunks = ops.stats_chunks(n, h * w)
+        partial = self.buf(ws, tag + ".partial", (n, chunks, c, 2), torch.float32)
+        a = self.buf(ws, tag + ".a", (n, c), torch.float32)
+        b = self.buf(ws, tag + ".b", (n, c), torch.float32)
+        plan.add(ops.op_chan_stats(self.lib, x, chunks, partial))
+        return partial, chunks, a, b
+
+    def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0):
+        """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124)."""
+        n, h, w, c = x.shape
+        partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        plan.add(ops.op_ln2d_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, a, b))
+        plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=L.ACT_LRELU, act_param=slope, pool2=pool2, res=res,
+                                   reflect1=reflect1))
+
+    def adain(self, plan, ws, tag, x, gamma, beta, gb_stride, y, *, act=L.ACT_LRELU, slope=0.01, res=None, reflect1=0):
+        """InstanceNorm2d*(1+gamma)+beta + activation [+ res] (base_blocks.py:127-157)."""
+        n, h, w, c = x.shape
+        partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        plan.add(ops.op_adain_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, gb_stride, a, b))
+        plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=act, act_param=slope, res=res, reflect1=reflect1))
+
+    # ---- grouped AdaIN heads -----------------------------------------------------------
+    def pack_lin_groups(self, name, groups):
+        """groups: list of (wt [K,nout] fp32, bias [nout], in_off, out_off)."""
+        arr = (L.LinGroup * len(groups))()
+        tiles, keep = [], []
+        for i, (wt, bias, in_off, out_off) in enumerate(groups):
+            wt, bias = wt.float().contiguous(), bias.float().contiguous()
+            keep += [wt, bias]
+            arr[i] = L.LinGroup(wt.data_ptr(), bias.data_ptr(), in_off, wt.shape[0], out_off, wt.shape[1])
+            tiles += [(i, j) for j in range(0, wt.shape[1], 128)]
+        gdev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+        tdev = torch.tensor(tiles, dtype=torch.int32, device=self.dev)
+        self.W[name] = dict(groups=gdev, tiles=tdev, n_tiles=len(tiles), keep=keep)
+
+    # ---- plan execution ----------------------------------------------------------------
+    def _get_plan(self, key, builder):
+        if key not in self._plans:
+            ws = {}
+            plan = ops.Plan()
+            io = builder(plan, ws)
+            self._plans[key] = dict(plan=plan, ws=ws, io=io, graph=None, warm=0)
+        return self._plans[key]
+
+    def _run(self, ent):
+        """Runs the plan on the current stream; after two eager runs the op list is captured into a
+        CUDA graph (launch-bound: ~600 small kernels per LNet forward) and replayed."""
+        if not self.use_graph:
+            ent["plan"].run()
+            return
+        if ent["graph"] is None:
+            ent["plan"].run()
+            ent["warm"] += 1
+            if ent["warm"] >= 2 and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["plan"].run()
+                ent["graph"] = g
+            return
+        ent["graph"].replay()
+
+    def launches_per_forward(self, key):
+        return len(self._plans[key]["plan"]) if key in self._plans else 0

@@ -106,6 +106,16 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     d.dil_h, d.dil_w = dil
     d.pad_mode, d.up2, d.act, d.act_param = pad_mode, up2, act, float(act_param)
     keep = (d, x, w, y, scale, bias, res1, res2, y_f32)
+    cout, taps = d.y.c, k[0] * k[1]
+    for t in (scale, bias):
+        assert t is None or (t.dtype == torch.float32 and t.numel() == cout), (name, cout)
+    for r in (res1, res2):
+        assert r is None or tuple(r.shape) == (d.y.n, d.y.h, d.y.w, cout), (name, r.shape)
+    if impl == "simt":
+        co_pad = -(-cout // 16) * 16 if cout >= 16 else -(-cout // 4) * 4
+        assert w.dtype == torch.float32 and tuple(w.shape) == (taps, x.shape[3], co_pad), (name, w.shape, x.shape, cout)
+    else:
+        assert w.dtype == torch.float16 and tuple(w.shape) == (cout, taps * (-(-x.shape[3] // 64) * 64)), (name, w.shape, x.shape, cout)
     if impl == "simt":
         return Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
     if box is None:
@@ -177,11 +187,13 @@ def op_attention(lib, q, k, v, o, heads, scale) -> Op:
 
 
 def op_pack(lib, src, dst, c_off=0, c_fill=None, scale=1.0, shift=0.0) -> Op:
+    """src: float32 [N,C,H,W], contiguous or a channel window (narrow on dim 1) of a contiguous tensor."""
     n, c, h, w = src.shape
-    assert src.dtype == torch.float32 and src.is_contiguous()
+    assert src.dtype == torch.float32 and src.stride(3) == 1 and src.stride(2) == w and src.stride(1) == h * w
     vd = view(dst)
     c_fill = c if c_fill is None else c_fill
-    return Op("pack_nchw", lib.s2v_pack_nchw_f32, (_ptr(src), n, c, h, w, C.byref(vd), c_off, c_fill, float(scale), float(shift)),
+    return Op("pack_nchw", lib.s2v_pack_nchw_f32,
+              (_ptr(src), n, c, h, w, src.stride(0) if n > 1 else c * h * w, C.byref(vd), c_off, c_fill, float(scale), float(shift)),
               (vd, src, dst))
 
 

@@ -87,6 +87,10 @@ def test_pack_unpack(G):
     src = torch.randn(3, 3, 20, 12, device="cuda")
     dst = torch.full((3, 20, 12, 16), 7.0, dtype=torch.float16, device="cuda")
     G.ops.op_pack(lib, src, dst, c_off=8, c_fill=8, scale=2.0, shift=-1.0).run()
+    wide = torch.randn(3, 6, 20, 12, device="cuda")
+    d2 = torch.zeros(3, 20, 12, 8, dtype=torch.float16, device="cuda")
+    G.ops.op_pack(lib, wide[:, 3:6], d2, 0, 8).run()
+    assert torch.equal(d2[..., :3], wide[:, 3:6].permute(0, 2, 3, 1).half()) and (d2[..., 3:] == 0).all()
     assert (dst[..., :8] == 7).all() and (dst[..., 11:] == 0).all()
     assert (dst[..., 8:11].permute(0, 3, 1, 2).float() - (src * 2 - 1)).abs().max().item() < 2e-3
     back = torch.empty(3, 3, 20, 12, device="cuda")

@@ -1,0 +1,99 @@
+"""CPU (-m "not gpu") tests of the host logic: the C-ABI library loads and exports every symbol the
+header declares, the drop-in modules keep the reference's state_dict schema, plans build with
+consistent shapes, box selection, weight packing, window index helper (host C function)."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import s2v_b200
+from s2v_b200 import _lib as L
+from s2v_b200 import ops
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    lib = s2v_b200.load_library()
+    hdr = open(os.path.join(ROOT, "include", "s2v.h")).read()
+    declared = set(re.findall(r"\b(s2v_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), "libs2v.so does not export %s" % name
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    assert lib.s2v_version() >= 100
+    assert lib.s2v_strerror(-1).decode().startswith("invalid")
+
+
+def test_window_helpers_match_oracle():
+    from oracle import mel as omel
+    from s2v_b200.futils import audio
+    for T in (16, 17, 31, 401, 4801, 48001):
+        for fps in (25.0, 23.976, 30.0, 60.0):
+            assert audio.mel_window_starts(T, fps) == omel.mel_window_starts(T, fps)
+    assert audio.mel_window_count(401) == 122 and audio.mel_window_count(4801) == 1497 and audio.mel_window_count(48001) == 14997
+    with pytest.raises(ValueError):
+        audio.mel_window_count(15)
+
+
+def test_mel_basis_matches_oracle():
+    import numpy as np
+    from oracle import mel as omel
+    from s2v_b200.futils import audio
+    assert np.array_equal(audio._build_mel_basis(), omel.mel_basis())
+
+
+def test_no_cpu_fallback():
+    import numpy as np
+    from s2v_b200.futils import audio, flow_util
+    if torch.cuda.is_available():
+        pytest.skip("GPU box")
+    with pytest.raises(L.S2VError):
+        audio.melspectrogram(np.zeros(1600, np.float32))
+    with pytest.raises(L.S2VError):
+        flow_util.warp_image(torch.zeros(1, 3, 8, 8), torch.zeros(1, 8, 8, 2))
+
+
+def test_choose_box():
+    assert ops.choose_box(96, 96, 128) == (32, 4, 1)
+    assert ops.choose_box(48, 48, 128) == (16, 8, 1)
+    assert ops.choose_box(24, 24, 128) == (8, 8, 2)
+    assert ops.choose_box(12, 12, 128) == (4, 4, 8)
+    assert ops.choose_box(1, 10752, 1) == (128, 1, 1)
+    for h, w, n in ((256, 256, 64), (64, 64, 3), (8, 8, 5), (7, 12, 9)):
+        bw, bh, bn = ops.choose_box(h, w, n)
+        assert bw * bh * bn == 128
+
+
+def test_weight_packing_layouts():
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = ops.pack_w_tc(w)
+    assert p.shape == (2, 9 * 64) and p.dtype == torch.float16
+    assert p[1, 4 * 64 + 2].item() == w[1, 2, 1, 1].item() and p[1, 4 * 64 + 3].item() == 0
+    s = ops.pack_w_simt(w, 8)
+    assert s.shape == (9, 8, 4) and s[5, 1, 1].item() == w[1, 1, 1, 2].item()
+
+
+@pytest.mark.parametrize("net", ["lnet", "dnet"])
+def test_schema_enumeration_matches_reference(net):
+    from s2v_b200.models import _schema
+    spec = _schema.lnet_spec() if net == "lnet" else _schema.dnet_spec()
+    ref = json.load(open(os.path.join(GOLDEN, f"{net}_schema.json")))
+    assert [n for n, _, _ in spec] == list(ref.keys())
+    assert all(list(s) == ref[n] for n, s, _ in spec)
+
+
+def test_lnet_module_state_dict_and_plan():
+    from oracle import weights
+    from s2v_b200.models.LNet import LNet, LNetEngine
+    sd = weights.make_state_dict("lnet", 0)
+    net = LNet().eval()
+    net.load_state_dict(sd, strict=True)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    for impl in ("tc", "simt"):
+        eng = LNetEngine(sd, torch.device("cpu"), conv_impl=impl)       # plan build only: validates shapes/ABI structs
+        ent = eng._get_plan(3, eng._build(3))
+        assert len(ent["plan"]) > 600
+        assert ent["io"]["out"].shape == (3, 3, 96, 96)
