@@ -124,8 +124,10 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
 
 
 def stats_chunks(n: int, hw: int) -> int:
-    """Pixel chunks per image for chan_stats: aim at >= ~600 blocks, >= 32 pixels each."""
-    return max(1, min(hw // 32, -(-600 // max(n, 1)), 256))
+    """Pixel chunks per image for chan_stats.  A function of the image size ONLY: the reduction
+    tree must not depend on the batch size, so that a frame's result is bit-identical whichever
+    batch / GPU shard it is computed in."""
+    return max(1, min(hw // 36, 64))
 
 
 def op_chan_stats(lib, x, chunks, partial) -> Op:
