@@ -1,0 +1,249 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame lip-sync hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one LNet forward (BASELINE.json configs[1]: batch 128, 96x96 faces, 80x16 mel windows,
+16-bit operands / fp32 accumulation) over a batch of synthetic frames already resident in HBM.
+`value` is whole-job frames/s (all ranks); `e2e` is the same metric through the public drop-in
+module (`LNet.forward`) with pinned HOST inputs, H2D + D2H inside the timed region.
+N > 1 (torchrun): frames are independent, every rank runs its own batch (weak scaling, no data-path
+collective); time = max over ranks.  --impl reference times the oracle port of the reference's
+PyTorch path on the box's host cores (the reference tree itself cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAME_GFLOP = 56.10            # LNet conv+linear FLOPs per frame (SURVEY A.2 / BASELINE.md section 3)
+METRIC = "generated frames/sec (LNet, 96 px, batch 128)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sus=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(sample_frames: int, reps: int = 1):
+    """The reference's PyTorch fp32 eager path (oracle port, oracle/nets.py) on the host cores."""
+    import torch
+    from oracle import nets, synth, weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = weights.make_state_dict("lnet", 0)
+    mel, face = synth.lnet_inputs(sample_frames, seed=0)
+    with torch.no_grad():
+        nets.lnet_forward(sd, mel[:1], face[:1])          # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            nets.lnet_forward(sd, mel, face)
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle/nets.py lnet_forward fp32 eager, batch %d of the 128-frame step, %d rep(s), %.2f s/rep" % (sample_frames, reps, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.ref_frames, reps=1)
+    # each "step" = the bounded sample; K steps + W warm-ups would repeat it; one rep is already ~10-30 s of CPU work
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_frames / cb["value"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LNet forward, 96x96, 80x16 mel windows; bounded sample of %d frames per step on host cores" % args.ref_frames},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--ref-frames", type=int, default=32)
+    ap.add_argument("--cpu-frames", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel-class time table to this file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import s2v_b200  # noqa: F401
+    from oracle import synth, weights           # synthetic inputs + seeded weights (not on the timed path)
+    from s2v_b200.models.LNet import LNet
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    net = LNet().to(dev).eval()
+    net.load_state_dict(weights.make_state_dict("lnet", 0), strict=True)
+    mel, face = synth.lnet_inputs(B, seed=rank)
+    mel_d, face_d = mel.to(dev), face.to(dev)
+    eng = net.engine()
+    ent = eng._get_plan(B, eng._build(B))
+    ent["io"]["mel"].copy_(mel_d)
+    ent["io"]["face"].copy_(face_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(W):
+        eng._run(ent)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        eng._run(ent)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = tms.item() / K
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host -> device -> LNet.forward -> host ---------
+    mel_h, face_h = mel.pin_memory(), face.pin_memory()
+    out_h = torch.empty(B, 3, 96, 96, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        out_h.copy_(net(mel_h.to(dev, non_blocking=True), face_h.to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        out_h.copy_(net(mel_h.to(dev, non_blocking=True), face_h.to(dev, non_blocking=True)), non_blocking=True)
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (tms.item() / K * 1e-3)
+
+    # ---- per-kernel-class device times (CUDA events around every launch, eager replay) ------------
+    roof, table = None, None
+    if rank == 0:
+        ops_l = ent["plan"].ops
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops_l]
+        reps = 3
+        acc = {}
+        for r in range(reps):
+            torch.cuda.synchronize(dev)
+            for op, (a, b) in zip(ops_l, evs):
+                a.record()
+                op.run()
+                b.record()
+            torch.cuda.synchronize(dev)
+            if r == 0:
+                continue                      # first eager pass = warm-up
+            for op, (a, b) in zip(ops_l, evs):
+                cls = "conv_tc" if op.name.endswith("[tc]") else "conv_simt" if op.name.endswith("[simt]") else op.name
+                d = acc.setdefault(cls, [0.0, 0, 0.0])
+                d[0] += a.elapsed_time(b) / (reps - 1)
+                d[1] += 1 if r == 1 else 0
+                d[2] += getattr(op, "alg_flops", 0.0) if r == 1 else 0.0
+        total = sum(v[0] for v in acc.values())
+        table = {k: {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)} for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
+        peaks = _peaks()
+        tc = acc.get("conv_tc")
+        if tc:
+            ach = tc[2] / (tc[0] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % tc[1],
+                    "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
+                    "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                    "alg_gflop_per_step": round(tc[2] / 1e9, 1), "kernel_ms_per_step": round(tc[0], 3),
+                    "share_of_step": round(tc[0] / total, 4)}
+        if args.breakdown:
+            with open(args.breakdown, "w") as f:
+                json.dump({"per_class": table, "sum_ms": total, "ms_per_step_graph": ms_step}, f, indent=1)
+
+    if rank == 0:
+        cb = None if args.no_cpu_baseline else cpu_baseline(args.cpu_frames)
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[1]: LNet forward, batch %d per GPU, 96x96 faces, 80x16 mel windows, "
+                                       "seeded random-init weights (oracle/weights.py seed 0)" % B,
+                           "frames_per_step_per_gpu": B, "l2": "per-step working set (>1 GB of activations + 255 MB weights) exceeds the 126 MB L2; no explicit flush",
+                           "parallelism": "frame-sharded x%d, no data-path collective" % world,
+                           "gflop_per_frame": FRAME_GFLOP},
+                "tflops_algorithmic": round(value * FRAME_GFLOP / 1e3, 1),
+                "clocks": clocks,
+                "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
+                        "h2d_bytes_per_step": int(mel.numel() * 4 + face.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "gpu_launches": K * len(ent["plan"]),
+                "launches_per_step": len(ent["plan"]),
+                "roofline": roof, "cpu_baseline": cb, "kernel_classes": table}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

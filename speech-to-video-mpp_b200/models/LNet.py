@@ -145,7 +145,7 @@ class LNetEngine(EngineBase):
                 x = feats[t]
                 p = f"encoder.first_{t}.model"
                 raw = buf("enc.raw0", (B, 96, 96, 64))
-                self.conv(plan, p, x, raw, pad=(3, 3))
+                self.conv(plan, p, x, raw, pad=(3, 3), cin_true=3)
                 a0 = buf(f"enc.{t}.a0", (B, 96, 96, 64))
                 self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0)
                 x = a0
@@ -221,7 +221,7 @@ class LNetEngine(EngineBase):
                 if self.impl == "tc":
                     for ph in (0, 1):
                         for qh in (0, 1):
-                            self.conv(plan, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], pad=(1 - ph, 1 - qh))
+                            self.conv(plan, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0)
                 else:
                     self.conv(plan, p, dec_out, uraw, pad=(1, 1), up2=1)
                 uact = buf(f"dec{i}.uact", (B, S2, S2, co))

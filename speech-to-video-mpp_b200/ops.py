@@ -83,10 +83,11 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
-            out_shape=None, impl="tc", box=None, name="conv") -> Op:
+            out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
+    cin_true = x.shape[3] if cin_true is None else cin_true
     if y is not None:
         d.y = view(y)
         d.out_mode = L.OUT_F16_NHWC
@@ -117,10 +118,15 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     else:
         assert w.dtype == torch.float16 and tuple(w.shape) == (cout, taps * (-(-x.shape[3] // 64) * 64)), (name, w.shape, x.shape, cout)
     if impl == "simt":
-        return Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
-    if box is None:
-        box = choose_box(d.y.h, d.y.w, d.y.n)
-    return Op(name + "[tc]", lib.s2v_conv_tc, (C.byref(d), box[0], box[1], box[2]), keep)
+        op = Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
+    else:
+        if box is None:
+            box = choose_box(d.y.h, d.y.w, d.y.n)
+        op = Op(name + "[tc]", lib.s2v_conv_tc, (C.byref(d), box[0], box[1], box[2]), keep)
+    # algorithmic FLOPs of the reference op this launch replaces (2*MACs on true channel counts);
+    # alg_scale lets the sub-pixel phases of nearest-x2 + conv3x3 report the reference's 3x3 work
+    op.alg_flops = 2.0 * d.y.n * d.y.h * d.y.w * cout * taps * cin_true * alg_scale
+    return op
 
 
 def stats_chunks(n: int, hw: int) -> int:
