@@ -192,7 +192,7 @@ def main():
         ops_l = ent["plan"].ops
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops_l]
         reps = 3
-        acc = {}
+        acc, per_op = {}, {}
         for r in range(reps):
             torch.cuda.synchronize(dev)
             for op, (a, b) in zip(ops_l, evs):
@@ -204,6 +204,10 @@ def main():
                 continue                      # first eager pass = warm-up
             for op, (a, b) in zip(ops_l, evs):
                 cls = "conv_tc" if op.name.endswith("[tc]") else "conv_simt" if op.name.endswith("[simt]") else op.name
+                po = per_op.setdefault(op.name, [0.0, 0, 0.0])
+                po[0] += a.elapsed_time(b) / (reps - 1)
+                po[1] += 1 if r == 1 else 0
+                po[2] += getattr(op, "alg_flops", 0.0) if r == 1 else 0.0
                 d = acc.setdefault(cls, [0.0, 0, 0.0])
                 d[0] += a.elapsed_time(b) / (reps - 1)
                 d[1] += 1 if r == 1 else 0
@@ -221,7 +225,18 @@ def main():
                     "share_of_step": round(tc[0] / total, 4)}
         if args.breakdown:
             with open(args.breakdown, "w") as f:
-                json.dump({"per_class": table, "sum_ms": total, "ms_per_step_graph": ms_step}, f, indent=1)
+                import re
+                grouped = {}
+                for name, v in per_op.items():          # fold the 9 blocks x 2 convs of a decoder level together
+                    key = re.sub(r"res(\d)\.res\d\.conv\d", r"res\1.*", name)
+                    key = re.sub(r"layers\.\d", "layers.*", key)
+                    key = re.sub(r"audio_encoder\.\d+", "audio_encoder.*", key)
+                    g = grouped.setdefault(key, [0.0, 0, 0.0])
+                    g[0] += v[0]; g[1] += v[1]; g[2] += v[2]
+                rows = [{"op": k, "ms": round(v[0], 4), "launches": v[1], "us_per_launch": round(1e3 * v[0] / max(v[1], 1), 2),
+                         "tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1) if v[2] and v[0] > 0 else None}
+                        for k, v in sorted(grouped.items(), key=lambda kv: -kv[1][0])]
+                json.dump({"per_class": table, "sum_ms": total, "ms_per_step_graph": ms_step, "per_op_group": rows}, f, indent=1)
 
     if rank == 0:
         cb = None if args.no_cpu_baseline else cpu_baseline(args.cpu_frames)

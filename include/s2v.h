@@ -152,8 +152,10 @@ typedef struct {
  * Cout_pad = Cout rounded up to 4.                                             */
 int s2v_conv_simt(const s2v_conv* d, void* stream);
 
-/* tcgen05 / TMEM / TMA implicit-GEMM convolution (stride 1, zero padding via
- * TMA out-of-bounds fill; reflect padding pre-materialised by the producer).
+/* tcgen05 / TMEM / TMA implicit-GEMM convolution (zero padding via TMA
+ * out-of-bounds fill, strides via TMA element strides; reflect padding is
+ * pre-materialised by the producer).  Cout must be a multiple of 8 except for
+ * S2V_OUT_F32_NCHW heads (weight rows then zero-padded to 8).
  * w: fp16 [Cout][kh*kw][Cin64] K-major, Cin64 = Cin rounded up to 64 (zero
  * filled).  box_w*box_h*box_n must be 128 (the M tile is a box of pixels).
  * pad_h/pad_w are the TOP/LEFT padding only; OH/OW may be smaller than the

@@ -34,7 +34,7 @@ struct TcParams {
   int N, OH, OW;
   int box_w, box_h, box_n;
   int tiles_w, tiles_h;
-  int kh, kw, pad_h, pad_w, dil_h, dil_w;
+  int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols;
   View y, r1, r2;
   const float* scale;
@@ -161,7 +161,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ky = tap / p.kw, kx = tap - ky * p.kw;
         const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
         mbar_expect_tx(full0 + 8u * s, stage_bytes);
-        tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 - p.pad_w + kx * p.dil_w, y0 - p.pad_h + ky * p.dil_h, n0);
+        tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
+                    y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
         tma_load_2d(a_dst + kABytes, &tmB, full0 + 8u * s, it * kChunkK, ntile * p.bn);
       }
     }
@@ -208,11 +209,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* o = v + 8 * hlf;
         if (p.scale) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] *= p.scale[c + i];
+          for (int i = 0; i < 8; ++i) o[i] *= (c + i < p.cout) ? p.scale[c + i] : 0.f;
         }
         if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += p.bias[c + i];
+          for (int i = 0; i < 8; ++i) o[i] += (c + i < p.cout) ? p.bias[c + i] : 0.f;
         }
         if (p.r1.p) {
           float f[8];
@@ -233,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.out_mode == S2V_OUT_F32_NCHW) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
+            if (c + i < p.cout) p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
         } else {
           st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
         }
@@ -272,14 +273,15 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (!d || !view_ok(&d->x) || !d->w) return S2V_EINVAL;
   if (d->out_mode == S2V_OUT_F16_NHWC && !view_ok(&d->y)) return S2V_EINVAL;
   if (d->out_mode == S2V_OUT_F32_NCHW && !d->y_f32) return S2V_EINVAL;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->up2 || d->pad_mode != S2V_PAD_ZERO) return S2V_EINVAL;
+  if (d->stride_h <= 0 || d->stride_w <= 0 || d->up2 || d->pad_mode != S2V_PAD_ZERO) return S2V_EINVAL;
+  if (box_w * d->stride_w > 256 || box_h * d->stride_h > 256) return S2V_EINVAL;
   if (d->kh <= 0 || d->kw <= 0 || d->dil_h <= 0 || d->dil_w <= 0) return S2V_EINVAL;
   if (box_w <= 0 || box_h <= 0 || box_n <= 0 || box_w * box_h * box_n != kTileM || box_w > 256 || box_h > 256 || box_n > 256) return S2V_EINVAL;
   if ((box_w * box_h * box_n) % 8) return S2V_EINVAL;
   const int N = d->x.n, OH = d->y.h, OW = d->y.w, cout = d->y.c;
   if (d->y.n != N) return S2V_EINVAL;
   if (OH <= 0 || OW <= 0) return S2V_EINVAL;   // rows/cols beyond the input are TMA zero fill (bottom/right padding)
-  if (cout % 8) return S2V_EINVAL;
+  if ((cout % 8) && (d->out_mode != S2V_OUT_F32_NCHW || d->res1.ptr || d->res2.ptr)) return S2V_EINVAL;
   EncodeTiledFn enc = get_encode();
   if (!enc) return S2V_EUNSUPPORTED;
 
@@ -289,6 +291,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.tiles_w = ceil_div(OW, box_w); p.tiles_h = ceil_div(OH, box_h);
   const int tiles_n = ceil_div(N, box_n);
   p.kh = d->kh; p.kw = d->kw; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.dil_h = d->dil_h; p.dil_w = d->dil_w;
+  p.str_h = d->stride_h; p.str_w = d->stride_w;
   p.cin_chunks = ceil_div(d->x.c, kChunkK);
   p.cout = cout;
   int bn = cout <= 256 ? ((cout + 15) / 16) * 16 : 256;
@@ -308,7 +311,9 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   const int budget = (bn <= 128 ? 100 : 200) * 1024;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
+  const int ki = d->kh * d->kw * p.cin_chunks;
+  if (stages > ki) stages = ki;          // short K loops: less smem per CTA -> more CTAs resident per SM
+  if (stages < 1) stages = 1;
   p.stages = stages;
   p.y = mk(d->y);
   p.r1 = mk(d->res1.ptr ? &d->res1 : nullptr);
@@ -320,15 +325,16 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   {
     cuuint64_t gdim[4] = {(cuuint64_t)d->x.c, (cuuint64_t)d->x.w, (cuuint64_t)d->x.h, (cuuint64_t)d->x.n};
     cuuint64_t gstr[3] = {(cuuint64_t)d->x.sw * 2, (cuuint64_t)d->x.sh * 2, (cuuint64_t)d->x.sn * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // strided convs: the box spans box*stride input pixels and TMA's element stride picks every stride-th one
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(box_w * d->stride_w), (cuuint32_t)(box_h * d->stride_h), (cuuint32_t)box_n};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
     if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
   {
     const cuuint64_t ktot = (cuuint64_t)d->kh * d->kw * p.cin_chunks * kChunkK;
-    cuuint64_t gdim[2] = {ktot, (cuuint64_t)cout};
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)((cout + 7) / 8 * 8)};   // weight rows are padded to 8 by the packer
     cuuint64_t gstr[1] = {ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)bn};
     cuuint32_t es[2] = {1, 1};

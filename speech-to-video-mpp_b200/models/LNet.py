@@ -40,7 +40,7 @@ class LNetEngine(EngineBase):
         self.P = {}                                   # small fp32 parameter vectors
         for t in ("inp", "ref"):
             p = f"encoder.first_{t}.model"
-            self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"], impl="simt", cin_pad=8)
+            self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"], cin_pad=8, rowtaps=True)
             self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
             for i in range(self.layer):
                 p = f"encoder.{t}_down{i}.model"
@@ -98,14 +98,14 @@ class LNetEngine(EngineBase):
             self.pack_conv(p, sn_fold(sd, p + ".0"), sd[p + ".0.bias"])
             self.P[p + ".g"], self.P[p + ".b"] = f32(sd[p + ".1.weight"].flatten()), f32(sd[p + ".1.bias"].flatten())
         self.gb_total, self.n_inst = off, inst
-        self.pack_conv("adain.shared", torch.cat(shared_w, 0)[:, :, None, None], torch.cat(shared_b, 0), impl="simt")
+        self.pack_conv("adain.shared", torch.cat(shared_w, 0)[:, :, None, None], torch.cat(shared_b, 0))
         self.pack_lin_groups("adain.heads", groups)
         p = "decoder.final.model.0"
-        self.pack_conv(p, sn_fold(sd, p), sd[p + ".bias"], impl="simt")
+        self.pack_conv(p, sn_fold(sd, p), sd[p + ".bias"])
         for i, (cin, cout, k, stride, pad, res) in enumerate(_schema.AUDIO_CFG):
             p = f"audio_encoder.{i}.conv_block"
             s, b = bn_fold(sd, p + ".1", sd[p + ".0.bias"])
-            self.pack_conv(p, sd[p + ".0.weight"].float(), b, s, impl="simt", cin_pad=8 if cin == 1 else None)
+            self.pack_conv(p, sd[p + ".0.weight"].float(), b, s, cin_pad=8 if cin == 1 else None)
 
     # ------------------------------------------------------------------ plan
     def _build(self, B):
@@ -123,7 +123,7 @@ class LNetEngine(EngineBase):
                 oh, ow = (h + 2 * pad - k) // stride[0] + 1, (w + 2 * pad - k) // stride[1] + 1
                 y = buf(f"aud.{i}", (B, oh, ow, cout))
                 self.conv(plan, f"audio_encoder.{i}.conv_block", x, y, stride=stride, pad=(pad, pad),
-                          res1=x if res else None, act=L.ACT_RELU)
+                          res1=x if res else None, act=L.ACT_RELU, cin_true=cin)
                 x = y
             z = x
             # ---- every AdaIN gamma/beta of the decoder (depends only on z) -----------------
@@ -136,16 +136,11 @@ class LNetEngine(EngineBase):
             # ---- visual encoder --------------------------------------------------------------
             xp2 = [buf(f"dec2.xp{j}", (B, 14, 14, 1024), zero=True) for j in range(3)]
             cat = xp2[0][:, 1:-1, 1:-1, :]
-            feats = {}
-            for t, c_lo in (("inp", 0), ("ref", 3)):       # masked face = planes 0-2, reference = planes 3-5
-                feats[t] = buf(f"enc.{t}.in8", (B, 96, 96, 8))
-                plan.add(ops.op_pack(lib, face_in[:, c_lo:c_lo + 3], feats[t], 0, 8))
             skips = []
-            for t in ("inp", "ref"):
-                x = feats[t]
+            for t, c_lo in (("inp", 0), ("ref", 3)):       # masked face = planes 0-2, reference = planes 3-5
                 p = f"encoder.first_{t}.model"
                 raw = buf("enc.raw0", (B, 96, 96, 64))
-                self.conv(plan, p, x, raw, pad=(3, 3), cin_true=3)
+                self.stem_conv(plan, ws, p, face_in[:, c_lo:c_lo + 3], raw)
                 a0 = buf(f"enc.{t}.a0", (B, 96, 96, 64))
                 self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0)
                 x = a0

@@ -70,13 +70,17 @@ class EngineBase:
         return t
 
     # ---- conv helpers ------------------------------------------------------------------
-    def pack_conv(self, name, w, bias=None, scale=None, impl=None, cin_pad=None):
-        """w: folded fp32 [Cout,Cin,kh,kw]."""
+    def pack_conv(self, name, w, bias=None, scale=None, impl=None, cin_pad=None, rowtaps=False):
+        """w: folded fp32 [Cout,Cin,kh,kw].  rowtaps (tc only): tiny-Cin stem packed for the
+        overlapping-view trick (ops.pack_w_tc_rowtaps); the conv then runs as a kh x 1 conv."""
         impl = impl or self.impl
         ent = dict(impl=impl, k=(w.shape[2], w.shape[3]), cout=w.shape[0],
                    bias=None if bias is None else bias.float().contiguous(),
                    scale=None if scale is None else scale.float().contiguous())
-        ent["w"] = ops.pack_w_tc(w) if impl == "tc" else ops.pack_w_simt(w, cin_pad)
+        if impl == "tc" and rowtaps:
+            ent["w"], ent["k"] = ops.pack_w_tc_rowtaps(w, cin_pad or 8), (w.shape[2], 1)
+        else:
+            ent["w"] = ops.pack_w_tc(w) if impl == "tc" else ops.pack_w_simt(w, cin_pad)
         self.W[name] = ent
         return ent
 
@@ -86,6 +90,23 @@ class EngineBase:
         kw.setdefault("bias", e["bias"])
         kw.setdefault("scale", e["scale"])
         return plan.add(ops.op_conv(self.lib, x, e["w"], y, impl=e["impl"], name=name, **kw))
+
+    def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3):
+        """k x k zero-padded stem conv on a tiny-Cin NCHW float input (FirstBlock2d / input_layer,
+        models/base_blocks.py:79-92,312).  tc path: the input is packed to 8 channels into a buffer
+        padded by k//2; one row tap's k x 8 = 56 (+8 zero-weight) consecutive values are exactly one
+        64-wide K chunk, exposed to TMA as an OVERLAPPING view (pixel stride 8, 64 'channels')."""
+        n, c, h, w = src_nchw.shape
+        pad = k // 2
+        if self.W[name]["impl"] != "tc":
+            x8 = self.buf(ws, name + ".in8", (n, h, w, 8))
+            plan.add(ops.op_pack(self.lib, src_nchw, x8, 0, 8))
+            return self.conv(plan, name, x8, y, pad=(pad, pad), cin_true=cin_true)
+        wp = w + 2 * pad + 2                        # +2: the 8th (zero-weight) pixel of the last window stays in the row
+        xp = self.buf(ws, name + ".in8p", (n, h + 2 * pad, wp, 8), zero=True)
+        plan.add(ops.op_pack(self.lib, src_nchw, xp[:, pad:pad + h, pad:pad + w, :], 0, 8))
+        win = torch.as_strided(xp, (n, h + 2 * pad, w, 64), (xp.stride(0), xp.stride(1), 8, 1))
+        return self.conv(plan, name, win, y, pad=(0, 0), cin_true=cin_true * k)
 
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):

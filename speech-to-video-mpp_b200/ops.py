@@ -116,7 +116,7 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
         co_pad = -(-cout // 16) * 16 if cout >= 16 else -(-cout // 4) * 4
         assert w.dtype == torch.float32 and tuple(w.shape) == (taps, x.shape[3], co_pad), (name, w.shape, x.shape, cout)
     else:
-        assert w.dtype == torch.float16 and tuple(w.shape) == (cout, taps * (-(-x.shape[3] // 64) * 64)), (name, w.shape, x.shape, cout)
+        assert w.dtype == torch.float16 and tuple(w.shape) == (-(-cout // 8) * 8, taps * (-(-x.shape[3] // 64) * 64)), (name, w.shape, x.shape, cout)
     if impl == "simt":
         op = Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
     else:
@@ -240,9 +240,21 @@ def pack_w_tc(w: torch.Tensor) -> torch.Tensor:
     """[Cout,Cin,kh,kw] float -> fp16 [Cout][kh*kw][Cin64] (K-major, zero-filled channel pad)."""
     co, ci, kh, kw = w.shape
     ci64 = -(-ci // 64) * 64
-    out = torch.zeros(co, kh * kw, ci64, dtype=torch.float16, device=w.device)
-    out[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16)
-    return out.reshape(co, kh * kw * ci64).contiguous()
+    co8 = -(-co // 8) * 8                       # rows padded to 8 (Cout = 3 heads)
+    out = torch.zeros(co8, kh * kw, ci64, dtype=torch.float16, device=w.device)
+    out[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16)
+    return out.reshape(co8, kh * kw * ci64).contiguous()
+
+
+def pack_w_tc_rowtaps(w: torch.Tensor, cpad: int = 8) -> torch.Tensor:
+    """Stem convs with tiny Cin (3 or 6): [Cout,Cin,kh,kw] -> fp16 [Cout][kh][64] where the 64-wide K
+    chunk of row tap ky holds (kx, c) = kx*cpad + c, i.e. kw consecutive pixels of a channels-last
+    buffer with cpad channels (read by an OVERLAPPING view: pixel stride cpad, 64 'channels')."""
+    co, ci, kh, kw = w.shape
+    assert kw * cpad <= 64 and ci <= cpad
+    out = torch.zeros(co, kh, 64 // cpad, cpad, dtype=torch.float16, device=w.device)
+    out[:, :, :kw, :ci] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return out.reshape(co, kh * 64).contiguous()
 
 
 def pack_w_simt(w: torch.Tensor, cin_pad: int | None = None) -> torch.Tensor:

@@ -37,11 +37,21 @@ CASES = [
     # asymmetric 2x2 phases of nearest-x2 + conv3x3 (sub-pixel decomposition) into strided outputs
     dict(name="up2_phases", n=2, h=12, w=12, cin=128, cout=64, k=3, pad=1, up2=True),
     dict(name="c3_res1_lrelu", n=2, h=24, w=24, cin=64, cout=64, k=3, pad=1, res1=True, act="lrelu", bias=True),
+    # strided convs through TMA element strides (audio encoder models/LNet.py:102-120; DNet 4x4 s2)
+    dict(name="s31_audio3", n=3, h=80, w=16, cin=32, cout=64, k=3, pad=1, stride=(3, 1), scale=True, bias=True, act="relu"),
+    dict(name="s33_audio6", n=5, h=27, w=16, cin=64, cout=128, k=3, pad=1, stride=(3, 3), bias=True),
+    dict(name="s32_audio9", n=70, h=9, w=6, cin=128, cout=256, k=3, pad=1, stride=(3, 2), bias=True),
+    dict(name="k4s2_dnet", n=2, h=64, w=64, cin=32, cout=64, k=4, pad=1, stride=(2, 2), bias=True),
+    dict(name="audio0_cin1", n=3, h=80, w=16, cin=1, cout=32, k=3, pad=1, bias=True, act="relu"),
+    dict(name="audio11_3x3_to_1x1", n=9, h=3, w=3, cin=256, cout=512, k=3, pad=0, bias=True),
+    dict(name="mlp_rows", n=37, h=1, w=1, cin=512, cout=1280, k=1, pad=0, bias=True, act="relu"),
+    # Cout = 3 head with fp32 NCHW output + sigmoid (FinalBlock2d)
+    dict(name="head_7x7_cout3", n=2, h=24, w=24, cin=64, cout=3, k=7, pad=3, bias=True, act="sigmoid", f32=True),
 ]
 
 
 def _act(name, L):
-    return {None: L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "gelu": L.ACT_GELU}[name]
+    return {None: L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "gelu": L.ACT_GELU, "sigmoid": L.ACT_SIGMOID}[name]
 
 
 def _act_ref(name, t):
@@ -49,6 +59,8 @@ def _act_ref(name, t):
         return F.relu(t)
     if name == "lrelu":
         return F.leaky_relu(t, 0.1)
+    if name == "sigmoid":
+        return torch.sigmoid(t)
     if name == "gelu":
         return 0.5 * t * (1 + torch.tanh(0.7978845608028654 * (t + 0.044715 * t ** 3)))
     return t
@@ -63,8 +75,13 @@ def test_conv_tc(G, case):
     wt = torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5
     bias = torch.randn(cout, device="cuda") if case.get("bias") else None
     scale = torch.rand(cout, device="cuda") + 0.5 if case.get("scale") else None
-    xh = G.nhwc(x)
-    xr = xh.permute(0, 3, 1, 2).float()
+    stride = case.get("stride", (1, 1))
+    if cin % 8:
+        xh = torch.zeros(n, h, w, -(-cin // 8) * 8, dtype=torch.float16, device="cuda")
+        xh[..., :cin] = G.nhwc(x)
+    else:
+        xh = G.nhwc(x)
+    xr = xh[..., :cin].permute(0, 3, 1, 2).float()
     wr = wt.half().float()
 
     if case.get("up2"):
@@ -89,19 +106,27 @@ def test_conv_tc(G, case):
     if case.get("reflect"):
         ref = F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="reflect"), wr, bias)
     else:
-        ref = F.conv2d(xr, wr, bias, padding=pad)
+        ref = F.conv2d(xr, wr, bias, stride=stride, padding=pad)
     if scale is not None:
-        ref = F.conv2d(xr, wr, None, padding=pad) * scale[None, :, None, None] + (bias[None, :, None, None] if bias is not None else 0)
+        ref = F.conv2d(xr, wr, None, stride=stride, padding=pad) * scale[None, :, None, None] + (bias[None, :, None, None] if bias is not None else 0)
+    oh, ow = ref.shape[2:]
     r1 = r2 = None
     if case.get("res1"):
-        r1 = torch.randn(n, h, w, cout, device="cuda").half()
+        r1 = torch.randn(n, oh, ow, cout, device="cuda").half()
         ref = ref + r1.permute(0, 3, 1, 2).float()
     ref = _act_ref(case.get("act"), ref)
     if case.get("res2"):
-        r2 = torch.randn(n, h, w, cout, device="cuda").half()
+        r2 = torch.randn(n, oh, ow, cout, device="cuda").half()
         ref = ref + r2.permute(0, 3, 1, 2).float()
 
-    kw = dict(k=(k, k), pad=(pad, pad), scale=scale, bias=bias, res1=r1, res2=r2, act=_act(case.get("act"), L), act_param=0.1)
+    kw = dict(k=(k, k), stride=stride, pad=(pad, pad), scale=scale, bias=bias, res1=r1, res2=r2, act=_act(case.get("act"), L), act_param=0.1)
+    if case.get("f32"):
+        yf = torch.zeros(n, cout, oh, ow, device="cuda")
+        ops.op_conv(lib, xh, ops.pack_w_tc(wt), None, y_f32=yf, out_shape=(n, cout, oh, ow), **kw).run()
+        torch.cuda.synchronize()
+        m, rel = G.report("conv_tc %s" % case["name"], yf, ref)
+        assert rel < 3e-3
+        return
     if case.get("views"):
         # x lives in channels [64, 64+cin) of a reflect-padded buffer; y in channels [8, 8+cout) of a wider one
         big = torch.randn(n, h + 2, w + 2, cin + 128, device="cuda").half()
@@ -115,9 +140,32 @@ def test_conv_tc(G, case):
         assert (ybig[..., :8] == 3).all() and (ybig[..., 8 + cout:] == 3).all()
         got = G.nchw(yv)
     else:
-        y = torch.zeros(n, h, w, cout, dtype=torch.float16, device="cuda")
+        y = torch.zeros(n, oh, ow, cout, dtype=torch.float16, device="cuda")
         ops.op_conv(lib, xh, ops.pack_w_tc(wt), y, **kw).run()
         torch.cuda.synchronize()
         got = G.nchw(y)
     m, rel = G.report("conv_tc %s" % case["name"], got, ref)
+    assert rel < 3e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(3, 64, 7, 96), (6, 64, 7, 64), (3, 32, 7, 40)])
+def test_stem_conv_overlapping_view(G, cin, cout, k, hw):
+    """Tiny-Cin stems (FirstBlock2d / ADAINEncoder.input_layer): one 64-wide K chunk = k x 8 consecutive
+    values of a row of the padded 8-channel buffer, read through an overlapping TMA view."""
+    from s2v_b200.models._engine import EngineBase
+    lib, L, ops = G.lib(), G.L, G.ops
+    torch.manual_seed(9)
+    n = 3
+    src = torch.randn(n, cin + 2, hw, hw, device="cuda")[:, 1:1 + cin]        # a channel window, like LNet's face halves
+    wt = torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5
+    bias = torch.randn(cout, device="cuda")
+    eng = EngineBase(torch.device("cuda", torch.cuda.current_device()))
+    eng.pack_conv("stem", wt, bias, cin_pad=8, rowtaps=True)
+    plan, ws = ops.Plan(), {}
+    y = torch.zeros(n, hw, hw, cout, dtype=torch.float16, device="cuda")
+    eng.stem_conv(plan, ws, "stem", src, y, k=k, cin_true=cin)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(src.half().float(), wt.half().float(), bias, padding=k // 2)
+    m, rel = G.report("stem conv cin%d k%d %d" % (cin, k, hw), G.nchw(y), ref)
     assert rel < 3e-3
