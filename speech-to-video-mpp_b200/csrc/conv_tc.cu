@@ -35,7 +35,7 @@ struct TcParams {
   int box_w, box_h, box_n;
   int tiles_w, tiles_h;
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
-  int cin_chunks, cout, bn, stages, tmem_cols;
+  int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   View y, r1, r2;
   const float* scale;
   const float* bias;
@@ -115,6 +115,140 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct EpiCtx {
+  uint8_t* smem_raw;
+  uint32_t smem_base, tptr_addr, tfull, tmem;
+  int n0, y0, x0, ntile, warp, lane;
+};
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float ap) {
+  if (ACT == S2V_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == S2V_ACT_LRELU) return v > 0.f ? v : v * ap;
+  if (ACT == S2V_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (ACT == S2V_ACT_TANH) return tanhf(v);
+  if (ACT == S2V_ACT_GELU) {
+    const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+    return 0.5f * v * (1.f + tanhf(u));
+  }
+  return v;
+}
+
+// TMEM -> registers -> scale/bias/activation -> (staged, coalesced | direct) stores.  TMEM lane quarter = warp % 4.
+template <int ACT>
+__device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
+  uint8_t* smem_raw = cx.smem_raw;
+  const uint32_t smem_base = cx.smem_base, tptr_addr = cx.tptr_addr, tfull = cx.tfull, tmem = cx.tmem;
+  const int n0 = cx.n0, y0 = cx.y0, x0 = cx.x0, ntile = cx.ntile, warp = cx.warp, lane = cx.lane;
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;                 // 0..127 within the epilogue warps
+    const int m = q * 32 + lane;
+    const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
+    const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
+    const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
+    // per-channel scale / bias of this N tile -> shared memory (overlaps the main loop)
+    float* s_scale = reinterpret_cast<float*>(smem_raw + (tptr_addr + 8u - smem_u32(smem_raw)));
+    float* s_bias = s_scale + 256;
+    for (int i = et; i < p.bn; i += 128) {
+      const int c = ntile * p.bn + i;
+      s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
+      s_bias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
+    // staged path: the smem ring is idle once the accumulator is complete (every MMA has retired, so
+    // every TMA load has landed and been consumed) -> reuse it as a [128][bn + 8] fp16 tile, then
+    // write it out with coalesced 16-byte stores (+ residual) instead of one pixel row per thread.
+    const int pitch = p.bn + 8;                      // +16 B per row: conflict-free 16-byte smem stores
+    __half* stage = reinterpret_cast<__half*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    for (int cb = 0; cb < p.bn; cb += 32) {
+      float v[32];
+      tmem_ld16_nowait(trow + (uint32_t)cb, v);
+      if (cb + 16 < p.bn) tmem_ld16_nowait(trow + (uint32_t)(cb + 16), v + 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cl = cb + 8 * g;                  // column within the N tile
+        if (cl >= p.bn) break;
+        const int c = ntile * p.bn + cl;
+        float* o = v + 8 * g;
+        const float4 s0 = *reinterpret_cast<const float4*>(s_scale + cl), s1 = *reinterpret_cast<const float4*>(s_scale + cl + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl), b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
+        o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
+        o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
+        if (!direct) {
+          if (ACT != S2V_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
+          }
+          st_h8(stage + (size_t)m * pitch + cl, f_to_h8(o));
+          continue;
+        }
+        if (!valid || c >= p.cout) continue;
+        if (p.r1.p) {
+          float f[8];
+          h8_to_f(ld_h8(p.r1.p + n * p.r1.sn + oy * p.r1.sh + ox * p.r1.sw + c), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += f[i];
+        }
+        if (ACT != S2V_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
+        }
+        if (p.r2.p) {
+          float f[8];
+          h8_to_f(ld_h8(p.r2.p + n * p.r2.sn + oy * p.r2.sh + ox * p.r2.sw + c), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += f[i];
+        }
+        if (p.out_mode == S2V_OUT_F32_NCHW) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (c + i < p.cout) p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
+        } else {
+          st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (!direct) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int cpr = p.bn >> 3;                     // 16-byte chunks per tile row
+      const int total = kTileM * cpr;
+      for (int idx = et; idx < total; idx += 128) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        const int c = ntile * p.bn + ch * 8;
+        const int rw = row % p.box_w, rh = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
+        const int pn = n0 + rn, py = y0 + rh, px = x0 + rw;
+        if (pn >= p.N || py >= p.OH || px >= p.OW || c >= p.cout) continue;
+        H8 hv = ld_h8(stage + (size_t)row * pitch + ch * 8);
+        if (p.r2.p) {
+          float a[8], f[8];
+          h8_to_f(hv, a);
+          h8_to_f(ld_h8(p.r2.p + pn * p.r2.sn + py * p.r2.sh + px * p.r2.sw + c), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += f[i];
+          hv = f_to_h8(a);
+        }
+        st_h8(p.y.p + pn * p.y.sn + py * p.y.sh + px * p.y.sw + c, hv);
+      }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -122,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;   // full[s], empty[s], tmem_full, tmem_ptr
+  const uint32_t bar_base = smem_base + (uint32_t)p.ring_bytes;   // full[s], empty[s], tmem_full, tmem_ptr, scale/bias
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages, tfull = bar_base + 16u * p.stages;
   const uint32_t tptr_addr = tfull + 8u;
   volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
@@ -188,59 +322,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tfull);                      // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
-    const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
-    const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    for (int cb = 0; cb < p.bn; cb += 16) {
-      float v[16];
-      tmem_ld16(trow + (uint32_t)cb, v);
-      const int c0 = ntile * p.bn + cb;
-      if (!valid || c0 >= p.cout) continue;
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        const int c = c0 + 8 * hlf;
-        if (c >= p.cout) break;
-        float* o = v + 8 * hlf;
-        if (p.scale) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] *= (c + i < p.cout) ? p.scale[c + i] : 0.f;
-        }
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += (c + i < p.cout) ? p.bias[c + i] : 0.f;
-        }
-        if (p.r1.p) {
-          float f[8];
-          h8_to_f(ld_h8(p.r1.p + n * p.r1.sn + oy * p.r1.sh + ox * p.r1.sw + c), f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += f[i];
-        }
-        if (p.act != S2V_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = act_apply(o[i], p.act, p.ap);
-        }
-        if (p.r2.p) {
-          float f[8];
-          h8_to_f(ld_h8(p.r2.p + n * p.r2.sn + oy * p.r2.sh + ox * p.r2.sw + c), f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += f[i];
-        }
-        if (p.out_mode == S2V_OUT_F32_NCHW) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (c + i < p.cout) p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
-        } else {
-          st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
-        }
-      }
+    // ===== epilogue: warps 2..5 (activation resolved once, outside the per-element loops) =====
+    const EpiCtx cx{smem_raw, smem_base, tptr_addr, tfull, tmem, n0, y0, x0, ntile, warp, lane};
+    switch (p.act) {
+      case S2V_ACT_RELU: epilogue<S2V_ACT_RELU>(p, cx); break;
+      case S2V_ACT_LRELU: epilogue<S2V_ACT_LRELU>(p, cx); break;
+      case S2V_ACT_SIGMOID: epilogue<S2V_ACT_SIGMOID>(p, cx); break;
+      case S2V_ACT_TANH: epilogue<S2V_ACT_TANH>(p, cx); break;
+      case S2V_ACT_GELU: epilogue<S2V_ACT_GELU>(p, cx); break;
+      default: epilogue<S2V_ACT_NONE>(p, cx); break;
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -343,7 +434,12 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  size_t ring = (size_t)stages * stage_bytes;
+  const size_t staging = (((size_t)kTileM * (bn + 8) * 2) + 1023) / 1024 * 1024;
+  if (staging > ring) ring = staging;       // the ring doubles as the epilogue's output staging tile
+  p.ring_bytes = (int)ring;
+  // barriers + tmem ptr + scale/bias tables sit behind the ring
+  const size_t smem = ring + 16 * stages + 16 + 2 * 256 * sizeof(float) + 64 + 1024;
   static bool attr = false;   // idempotent
   if (!attr) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;

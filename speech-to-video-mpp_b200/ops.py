@@ -17,8 +17,13 @@ from . import _lib as L
 
 def view(t: torch.Tensor) -> L.View:
     """fp16 channels-last [N,H,W,C] tensor (any strides, channel stride 1) -> s2v_view."""
-    assert t.dtype == torch.float16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
-    return L.View(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.stride(0), t.stride(1), t.stride(2))
+    assert t.dtype == torch.float16 and t.dim() == 4 and (t.stride(3) == 1 or t.shape[3] == 1), (t.dtype, t.shape, t.stride())
+    n, h, w, c = t.shape
+    # PyTorch leaves arbitrary strides on size-1 dims; give them the canonical (dense) value
+    sw = t.stride(2) if w > 1 else c
+    sh = t.stride(1) if h > 1 else sw * w
+    sn = t.stride(0) if n > 1 else sh * h
+    return L.View(t.data_ptr(), n, h, w, c, sn, sh, sw)
 
 
 def null_view() -> L.View:
