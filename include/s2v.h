@@ -119,6 +119,12 @@ int s2v_warp_deformation_f32(const float* src, const float* deformation, float* 
 int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, int64_t src_sn, const s2v_view* dst,
                       int c_off, int c_fill, float scale, float shift, void* stream);
 int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, float* dst, void* stream);
+/* DNet -> LNet glue of the synthetic full-path configuration (harness convention standing in for
+ * the CPU image code of inference.py:188-239,341-411; cf. models/ENet.py:103-104):
+ *   ref  = bilinear((clamp(fake,-1,1)+1)/2 -> [oh,ow], align_corners=False)
+ *   face = cat(ref with rows >= mask_row zeroed, ref)      float32 [B,2C,oh,ow]                 */
+int s2v_glue_fake_to_face_f32(const float* fake, float* face, int B, int C, int H, int W, int oh, int ow,
+                              int mask_row, void* stream);
 
 /* ----------------------------------------------------------------- conv ---
  * One descriptor for both convolution kernels.  Replaces nn.Conv2d /

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "s2v_warp_deformation_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "s2v_pack_nchw_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_i64, VP, C.c_int, C.c_int, c_f32, c_f32, c_vp]),
     "s2v_unpack_to_nchw_f32": (C.c_int, [VP, C.c_int, C.c_int, c_vp, c_vp]),
+    "s2v_glue_fake_to_face_f32": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "s2v_conv_simt": (C.c_int, [C.POINTER(Conv), c_vp]),
     "s2v_conv_tc": (C.c_int, [C.POINTER(Conv), C.c_int, C.c_int, C.c_int, c_vp]),
     "s2v_grouped_linear": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_i64, c_vp]),

@@ -34,9 +34,46 @@ __global__ void __launch_bounds__(256) unpack_kernel(View s, int c_off, int C, f
   for (int c = 0; c < C; ++c) o[c * plane] = __half2float(p[c]);
 }
 
+// DNet -> LNet glue of the synthetic full-path configuration (the real glue is
+// CPU image code, inference.py:188-239,341-411):  ref = bilinear((clamp(fake,-1,1)+1)/2 -> oh x ow,
+// align_corners=False), face = cat(ref with rows >= mask_row zeroed, ref).
+__global__ void __launch_bounds__(256) glue_kernel(const float* __restrict__ fake, float* __restrict__ face, int B,
+                                                   int C, int H, int W, int oh, int ow, int mask_row) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * C * oh * ow;
+  if (idx >= total) return;
+  const int x = (int)(idx % ow);
+  const int y = (int)((idx / ow) % oh);
+  const int c = (int)((idx / ((long long)ow * oh)) % C);
+  const int n = (int)(idx / ((long long)ow * oh * C));
+  const float sch = (float)H / (float)oh, scw = (float)W / (float)ow;
+  const float sy = fmaxf(sch * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f);
+  const float* s = fake + ((size_t)n * C + c) * H * W;
+  auto t = [](float v) { return (fminf(fmaxf(v, -1.f), 1.f) + 1.f) * 0.5f; };
+  const float v = (1.f - ly) * ((1.f - lx) * t(s[y0 * W + x0]) + lx * t(s[y0 * W + x1])) +
+                  ly * ((1.f - lx) * t(s[y1 * W + x0]) + lx * t(s[y1 * W + x1]));
+  const size_t plane = (size_t)oh * ow;
+  float* o = face + (size_t)n * 2 * C * plane + (size_t)y * ow + x;
+  o[c * plane] = y >= mask_row ? 0.f : v;
+  o[(C + c) * plane] = v;
+}
+
 }  // namespace s2v
 
 using namespace s2v;
+
+extern "C" int s2v_glue_fake_to_face_f32(const float* fake, float* face, int B, int C, int H, int W, int oh, int ow,
+                                         int mask_row, void* stream) {
+  if (B == 0) return S2V_OK;
+  if (!fake || !face || B < 0 || C <= 0 || H <= 0 || W <= 0 || oh <= 0 || ow <= 0) return S2V_EINVAL;
+  const long long total = (long long)B * C * oh * ow;
+  glue_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(fake, face, B, C, H, W, oh, ow, mask_row);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
 
 extern "C" int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, int64_t src_sn, const s2v_view* dst,
                                  int c_off, int c_fill, float scale, float shift, void* stream) {

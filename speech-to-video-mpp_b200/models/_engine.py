@@ -126,12 +126,20 @@ class EngineBase:
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=L.ACT_LRELU, act_param=slope, pool2=pool2, res=res,
                                    reflect1=reflect1))
 
-    def adain(self, plan, ws, tag, x, gamma, beta, gb_stride, y, *, act=L.ACT_LRELU, slope=0.01, res=None, reflect1=0):
-        """InstanceNorm2d*(1+gamma)+beta + activation [+ res] (base_blocks.py:127-157)."""
+    def adain(self, plan, ws, tag, x, gamma, beta, gb_stride, y, *, act=L.ACT_LRELU, slope=0.01, res=None, reflect1=0,
+              stats=None):
+        """InstanceNorm2d*(1+gamma)+beta + activation [+ res] (base_blocks.py:127-157).
+        ``stats``: reuse the (partial, chunks) of an earlier call on the same x (two AdaINs of one tensor)."""
         n, h, w, c = x.shape
-        partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        if stats is None:
+            partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        else:
+            partial, chunks = stats
+            a = self.buf(ws, tag + ".a", (n, c), torch.float32)
+            b = self.buf(ws, tag + ".b", (n, c), torch.float32)
         plan.add(ops.op_adain_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, gb_stride, a, b))
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=act, act_param=slope, res=res, reflect1=reflect1))
+        return partial, chunks
 
     # ---- grouped AdaIN heads -----------------------------------------------------------
     def pack_lin_groups(self, name, groups):

@@ -97,3 +97,39 @@ def test_lnet_module_state_dict_and_plan():
         ent = eng._get_plan(3, eng._build(3))
         assert len(ent["plan"]) > 600
         assert ent["io"]["out"].shape == (3, 3, 96, 96)
+
+
+def test_dnet_module_state_dict_and_plan():
+    from oracle import weights
+    from s2v_b200.models.DNet import DNet, DNetEngine
+    sd = weights.make_state_dict("dnet", 0)
+    net = DNet().eval()
+    net.load_state_dict(sd, strict=True)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    eng = DNetEngine(sd, torch.device("cpu"))                          # plan build only
+    full = eng._get_plan((2, 26, "full"), eng._build(2, 26, "full"))
+    warp = eng._get_plan((2, 26, "warp"), eng._build(2, 26, "warp"))
+    assert "fake" in full["io"] and "fake" not in warp["io"]
+    gf = sum(getattr(op, "alg_flops", 0.0) for op in full["plan"].ops) / 2 / 1e9
+    assert abs(gf - 101.45) < 0.1                                       # useful GFLOP/frame (dead conv1 skipped)
+
+
+def test_convT_and_up2_phase_weights_match_torch():
+    import torch.nn.functional as F
+    from s2v_b200.models.DNet import convT_phase_weights
+    from s2v_b200.models._engine import up2_phase_weights
+    torch.manual_seed(0)
+    x = torch.randn(1, 5, 6, 7, dtype=torch.float64)
+    wt = torch.randn(5, 4, 3, 3, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, wt, stride=2, padding=1, output_padding=1)
+    out = torch.zeros_like(ref)
+    for (p, q), w4 in convT_phase_weights(wt).items():
+        kh, kw = w4.shape[2:]
+        out[:, :, p::2, q::2] = F.conv2d(F.pad(x, (0, kw - 1, 0, kh - 1)), w4)
+    assert (out - ref).abs().max() < 1e-12
+    w3 = torch.randn(4, 5, 3, 3, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2), w3, padding=1)
+    out = torch.zeros_like(ref)
+    for (p, q), w4 in up2_phase_weights(w3).items():
+        out[:, :, p::2, q::2] = F.conv2d(F.pad(x, (1 - q, q, 1 - p, p)), w4)
+    assert (out - ref).abs().max() < 1e-12
