@@ -89,6 +89,77 @@ def cpu_baseline(sample_frames: int, reps: int = 1):
             "sample": "oracle/nets.py lnet_forward fp32 eager, batch %d of the 128-frame step, %d rep(s), %.2f s/rep" % (sample_frames, reps, dt)}
 
 
+def _time(fn, reps, dev):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / reps
+
+
+def measure_extras(dev, lnet):
+    """The other rows of the hot path, each timed on the device with inputs resident in
+    HBM: DNet B=64 (configs[2]), the fused warp kernel against the HBM roofline, the mel front end, and
+    the chained full path (configs[3]: 60 s clip, 1497 frames)."""
+    import torch
+    from oracle import synth, weights
+    from s2v_b200.futils import audio, flow_util
+    from s2v_b200.models.DNet import DNet
+    from s2v_b200.pipeline import LipSyncPipeline
+    peaks = _peaks()
+    out = {}
+    dnet = DNet().to(dev).eval()
+    dnet.load_state_dict(weights.make_state_dict("dnet", 0), strict=True)
+    src, coeff = synth.dnet_inputs(64, seed=0)
+    src, coeff = src.to(dev), coeff.to(dev)
+    ms = _time(lambda: dnet(src, coeff), 5, dev)
+    out["dnet_b64"] = {"frames_per_s": round(64 / ms * 1e3, 1), "ms": round(ms, 3),
+                       "tflops_useful": round(64 * 101.45 / ms, 1), "note": "DNet full forward, 256x256, batch 64 (configs[2]); 101.45 useful GFLOP/frame"}
+    ms = _time(lambda: dnet(src, coeff, stage="warp"), 5, dev)
+    out["dnet_b64_stage_warp"] = {"frames_per_s": round(64 / ms * 1e3, 1), "ms": round(ms, 3)}
+    s, fl = synth.warp_inputs(64, seed=0)
+    s, fl = s.to(dev), fl.to(dev)
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def warp_flushed():
+        scratch.zero_()                       # 256 MiB write: evicts the 126 MB L2 between timed launches
+        flow_util.warp_flow(s, fl)
+    ms_both = _time(warp_flushed, 10, dev)
+    ms_flush = _time(lambda: scratch.zero_(), 10, dev)
+    ms = max(ms_both - ms_flush, 1e-3)
+    gb = 64 * 1605632 / 1e9
+    out["warp_kernel_b64"] = {"us": round(ms * 1e3, 2), "GBps_algorithmic": round(gb / (ms * 1e-3), 1),
+                              "frac_of_hbm_peak": round(gb / (ms * 1e-3) / peaks["hbm"], 3), "hbm_peak_GBps": peaks["hbm"],
+                              "alg_bytes_per_frame": 1605632, "note": "fused flow_to_deformation+resize+grid_sample, fp32, L2 flushed between launches"}
+    wav = torch.from_numpy(synth.wav(60.0, seed=0)).to(dev)
+    ms = _time(lambda: audio.mel_windows(audio.melspectrogram_device(wav)), 10, dev)
+    out["mel_60s_clip"] = {"ms": round(ms, 4), "stft_columns": 4801, "windows": 1497,
+                           "GBps_algorithmic": round((4801 * 1120 + 1497 * 5120) / 1e9 / (ms * 1e-3), 2),
+                           "note": "melspectrogram + 80x16 window gather; launch/latency-bound at this size"}
+    n = 1497
+    srcs, coeffs = synth.dnet_inputs(64, seed=1)
+    srcs = srcs.to(dev).repeat((n + 63) // 64, 1, 1, 1)[:n]
+    coeffs = coeffs.to(dev).repeat((n + 63) // 64, 1, 1)[:n]
+    pipe = LipSyncPipeline(lnet, dnet)
+    pipe.run(wav, srcs, coeffs)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    pipe.run(wav, srcs, coeffs)
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b)
+    out["full_path_60s_clip"] = {"frames": n, "ms": round(ms, 2), "frames_per_s": round(n / ms * 1e3, 1),
+                                 "note": "mel -> DNet(B=64) -> glue -> LNet(B=128) on one GPU, configs[3] at N=1"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -115,6 +186,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=32)
     ap.add_argument("--cpu-frames", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the DNet / warp / mel / full-path side measurements")
     ap.add_argument("--breakdown", default="", help="write the per-kernel-class time table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -238,6 +310,9 @@ def main():
                         for k, v in sorted(grouped.items(), key=lambda kv: -kv[1][0])]
                 json.dump({"per_class": table, "sum_ms": total, "ms_per_step_graph": ms_step, "per_op_group": rows}, f, indent=1)
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = measure_extras(dev, net)
     if rank == 0:
         cb = None if args.no_cpu_baseline else cpu_baseline(args.cpu_frames)
         line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -254,7 +329,7 @@ def main():
                         "h2d_bytes_per_step": int(mel.numel() * 4 + face.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
                 "gpu_launches": K * len(ent["plan"]),
                 "launches_per_step": len(ent["plan"]),
-                "roofline": roof, "cpu_baseline": cb, "kernel_classes": table}
+                "roofline": roof, "cpu_baseline": cb, "kernel_classes": table, "other_rows": extras}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,50 @@
+"""-m gpu test of the full per-frame path (mel -> windows -> DNet -> glue -> LNet, BASELINE configs[3] shape
+at reduced length) against the oracle chain, plus shard equivalence: frames computed by "rank r of 2"
+equal the unsharded frames bit-for-bit (frames are independent; no float atomics anywhere)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_path_vs_oracle_and_shard_equivalence():
+    import gpu_util as G
+    from oracle import mel as omel, nets, synth, weights
+    from s2v_b200 import parallel
+    from s2v_b200.models.DNet import DNet
+    from s2v_b200.models.LNet import LNet
+    from s2v_b200.pipeline import LipSyncPipeline, glue_fake_to_face
+    G.lib()
+    sd_l, sd_d = weights.make_state_dict("lnet", 0), weights.make_state_dict("dnet", 0)
+    lnet, dnet = LNet().cuda().eval(), DNet().cuda().eval()
+    lnet.load_state_dict(sd_l, strict=True)
+    dnet.load_state_dict(sd_d, strict=True)
+    wav = synth.wav(0.5, seed=0)                      # 8000 samples -> T = 41 -> 9 windows/frames
+    n = len(omel.mel_window_starts(1 + len(wav) // 200))
+    src, coeff = synth.dnet_inputs(n, seed=2)
+    src, coeff = src.cuda(), coeff.cuda()
+    pipe = LipSyncPipeline(lnet, dnet, lnet_batch=4, dnet_batch=4)
+    assert pipe.n_frames(len(wav)) == n
+    frames = pipe.run(torch.from_numpy(wav).cuda(), src, coeff)
+    assert frames.shape == (n, 3, 96, 96)
+    # oracle chain (fp64 mel restatement, fp32 torch nets on the GPU)
+    mel = omel.melspectrogram(wav)
+    win = torch.from_numpy(omel.mel_windows(mel)).cuda()
+    fake = nets.dnet_forward({k: v.cuda() for k, v in sd_d.items()}, src, coeff)["fake_image"]
+    face = nets.glue_dnet_to_lnet(fake)
+    ref = nets.lnet_forward({k: v.cuda() for k, v in sd_l.items()}, win, face)
+    m, _ = G.report("full path frames vs oracle", frames, ref)
+    p = G.psnr(frames, ref, 1.0)
+    print("full path PSNR %.2f dB" % p)
+    with open("gpurun_out/parity_report.txt", "a") as f:
+        f.write("full path (mel->DNet->glue->LNet) PSNR %.2f dB max_abs %.5f\n" % (p, m))
+    assert p >= 45.0
+    # glue kernel alone vs the oracle's glue
+    g = glue_fake_to_face(fake)
+    assert (g - face).abs().max().item() < 1e-5
+    # shard equivalence, world = 2 emulated on one GPU
+    parts = []
+    for r in range(2):
+        lo, hi = parallel.shard_range(n, r, 2)
+        parts.append(pipe.run(torch.from_numpy(wav).cuda(), src[lo:hi], coeff[lo:hi], rank=r, world=2))
+    assert torch.equal(torch.cat(parts, 0), frames)
