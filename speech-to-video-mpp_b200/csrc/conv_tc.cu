@@ -229,22 +229,40 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int cpr = p.bn >> 3;                     // 16-byte chunks per tile row
       const int total = kTileM * cpr;
-      for (int idx = et; idx < total; idx += 128) {
-        const int row = idx / cpr, ch = idx - row * cpr;
-        const int c = ntile * p.bn + ch * 8;
-        const int rw = row % p.box_w, rh = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
-        const int pn = n0 + rn, py = y0 + rh, px = x0 + rw;
-        if (pn >= p.N || py >= p.OH || px >= p.OW || c >= p.cout) continue;
-        H8 hv = ld_h8(stage + (size_t)row * pitch + ch * 8);
-        if (p.r2.p) {
-          float a[8], f[8];
-          h8_to_f(hv, a);
-          h8_to_f(ld_h8(p.r2.p + pn * p.r2.sn + py * p.r2.sh + px * p.r2.sw + c), f);
+      // 4 independent (row, 16 B chunk) items per iteration: the residual loads are issued together so
+      // their L2 latency overlaps (y and res2 may be the same buffer, so the compiler cannot hoist them)
+      for (int base = et; base < total; base += 4 * 128) {
+        H8 hv[4], rv[4];
+        __half* dst[4];
+        bool ok[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] += f[i];
-          hv = f_to_h8(a);
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 128;
+          ok[u] = idx < total;
+          const int row = ok[u] ? idx / cpr : 0, ch = ok[u] ? idx - row * cpr : 0;
+          const int c = ntile * p.bn + ch * 8;
+          const int rw = row % p.box_w, rh = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
+          const int pn = n0 + rn, py = y0 + rh, px = x0 + rw;
+          ok[u] = ok[u] && pn < p.N && py < p.OH && px < p.OW && c < p.cout;
+          dst[u] = p.y.p + pn * p.y.sn + py * p.y.sh + px * p.y.sw + c;
+          if (ok[u]) {
+            hv[u] = ld_h8(stage + (size_t)row * pitch + ch * 8);
+            if (p.r2.p) rv[u] = ld_h8(p.r2.p + pn * p.r2.sn + py * p.r2.sh + px * p.r2.sw + c);
+          }
         }
-        st_h8(p.y.p + pn * p.y.sn + py * p.y.sh + px * p.y.sw + c, hv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          if (p.r2.p) {
+            float a[8], f[8];
+            h8_to_f(hv[u], a);
+            h8_to_f(rv[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += f[i];
+            hv[u] = f_to_h8(a);
+          }
+          st_h8(dst[u], hv[u]);
+        }
       }
     }
 }

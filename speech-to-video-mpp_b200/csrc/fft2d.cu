@@ -123,10 +123,21 @@ __global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View 
     if (add.p) {
       const __half* a0 = add.p + n * add.sn + (2 * t) * add.sh + ch;
       const __half* a1 = a0 + add.sh;
+      // residual loads in groups of 8 ahead of the stores (add and y may alias as far as the compiler knows)
 #pragma unroll
-      for (int w = 0; w < S; ++w) {
-        o0[w * y.sw] = __float2half_rn(fmaf(z[w].x, nrm, __half2float(a0[w * add.sw])));
-        o1[w * y.sw] = __float2half_rn(fmaf(z[w].y, nrm, __half2float(a1[w * add.sw])));
+      for (int w0 = 0; w0 < S; w0 += 8) {
+        __half r0[8], r1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (w0 + j < S) { r0[j] = a0[(w0 + j) * add.sw]; r1[j] = a1[(w0 + j) * add.sw]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (w0 + j < S) {
+            o0[(w0 + j) * y.sw] = __float2half_rn(fmaf(z[w0 + j].x, nrm, __half2float(r0[j])));
+            o1[(w0 + j) * y.sw] = __float2half_rn(fmaf(z[w0 + j].y, nrm, __half2float(r1[j])));
+          }
+        }
       }
     } else {
 #pragma unroll

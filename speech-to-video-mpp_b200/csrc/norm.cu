@@ -23,6 +23,7 @@ __global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pg < PG) {
+#pragma unroll 4
     for (int p = p0 + pg; p < p1; p += PG) {
       const int yy = p / x.w, xx = p - yy * x.w;
       float f[8];
@@ -97,64 +98,93 @@ __global__ void __launch_bounds__(256) adain_finalize_kernel(const float* __rest
   b[idx] = be - (float)mean * av;
 }
 
-// one thread per output vector (n, oy, ox, c8)
-__global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
-                                                         const float* __restrict__ b, int act, float ap, int pool2,
-                                                         View res, View y, int reflect1) {
-  const int C8 = x.c >> 3;
-  const long long total = (long long)y.n * y.h * y.w * C8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  long long r = idx / C8;
-  const int ox = (int)(r % y.w); r /= y.w;
-  const int oy = (int)(r % y.h);
-  const int n = (int)(r / y.h);
-  float av[8], bv[8], o[8];
-  {
-    const float4* pa = reinterpret_cast<const float4*>(a + (size_t)n * x.c + c8 * 8);
-    const float4* pb = reinterpret_cast<const float4*>(b + (size_t)n * x.c + c8 * 8);
-    float4 t0 = pa[0], t1 = pa[1], u0 = pb[0], u1 = pb[1];
-    av[0] = t0.x; av[1] = t0.y; av[2] = t0.z; av[3] = t0.w; av[4] = t1.x; av[5] = t1.y; av[6] = t1.z; av[7] = t1.w;
-    bv[0] = u0.x; bv[1] = u0.y; bv[2] = u0.z; bv[3] = u0.w; bv[4] = u1.x; bv[5] = u1.y; bv[6] = u1.z; bv[7] = u1.w;
-  }
-  if (pool2) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        float f[8];
-        h8_to_f(ld_h8(x.p + n * x.sn + (2 * oy + dy) * x.sh + (2 * ox + dx) * x.sw + c8 * 8), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
-      }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] *= 0.25f;
-  } else {
-    float f[8];
-    h8_to_f(ld_h8(x.p + n * x.sn + oy * x.sh + ox * x.sw + c8 * 8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
-  }
-  if (res.p) {
-    float f[8];
-    h8_to_f(ld_h8(res.p + n * res.sn + oy * res.sh + ox * res.sw + c8 * 8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] += f[i];
-  }
+// one thread per TWO output vectors (n, oy, ox, c8): items idx and idx + half are loaded together so two
+// independent 16-byte loads (four with a residual) are in flight per thread
+__device__ __forceinline__ void affine_store(const View& y, int n, int oy, int ox, int c8, const float* o, int reflect1) {
   const H8 hv = f_to_h8(o);
   __half* yp = y.p + n * y.sn + c8 * 8;
   st_h8(yp + oy * y.sh + ox * y.sw, hv);
   if (reflect1) {
-    // padded(-1) = in(1), padded(H) = in(H-2)
+    // padded(-1) = in(1), padded(H) = in(H-2); h,w >= 4 is enforced on the host
     const int my = (oy == 1) ? -1 : (oy == y.h - 2 ? y.h : -2);
     const int mx = (ox == 1) ? -1 : (ox == y.w - 2 ? y.w : -2);
     if (my != -2) st_h8(yp + my * y.sh + ox * y.sw, hv);
     if (mx != -2) st_h8(yp + oy * y.sh + mx * y.sw, hv);
     if (my != -2 && mx != -2) st_h8(yp + my * y.sh + mx * y.sw, hv);
-    // a 2-wide dimension maps both borders from different pixels; h,w >= 3 is enforced on the host
+  }
+}
+
+__device__ __forceinline__ void load_ab(const float* __restrict__ a, const float* __restrict__ b, int n, int C, int c8,
+                                        float* av, float* bv) {
+  const float4* pa = reinterpret_cast<const float4*>(a + (size_t)n * C + c8 * 8);
+  const float4* pb = reinterpret_cast<const float4*>(b + (size_t)n * C + c8 * 8);
+  const float4 t0 = pa[0], t1 = pa[1], u0 = pb[0], u1 = pb[1];
+  av[0] = t0.x; av[1] = t0.y; av[2] = t0.z; av[3] = t0.w; av[4] = t1.x; av[5] = t1.y; av[6] = t1.z; av[7] = t1.w;
+  bv[0] = u0.x; bv[1] = u0.y; bv[2] = u0.z; bv[3] = u0.w; bv[4] = u1.x; bv[5] = u1.y; bv[6] = u1.z; bv[7] = u1.w;
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
+                                                         const float* __restrict__ b, int act, float ap, View res,
+                                                         View y, int reflect1) {
+  constexpr int U = 2;
+  const int C8 = x.c >> 3;
+  const long long total = (long long)y.n * y.h * y.w * C8;
+  const long long half = (total + U - 1) / U;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= half) return;
+  int n[U], oy[U], ox[U], c8[U];
+  bool ok[U];
+  H8 xin[U][POOL ? 4 : 1], rin[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long idx = i0 + u * half;
+    ok[u] = idx < total;
+    long long r = ok[u] ? idx : 0;
+    c8[u] = (int)(r % C8); r /= C8;
+    ox[u] = (int)(r % y.w); r /= y.w;
+    oy[u] = (int)(r % y.h);
+    n[u] = (int)(r / y.h);
+    if (!ok[u]) continue;
+    if (POOL) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        xin[u][d] = ld_h8(x.p + n[u] * x.sn + (2 * oy[u] + (d >> 1)) * x.sh + (2 * ox[u] + (d & 1)) * x.sw + c8[u] * 8);
+    } else {
+      xin[u][0] = ld_h8(x.p + n[u] * x.sn + oy[u] * x.sh + ox[u] * x.sw + c8[u] * 8);
+    }
+    if (res.p) rin[u] = ld_h8(res.p + n[u] * res.sn + oy[u] * res.sh + ox[u] * res.sw + c8[u] * 8);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!ok[u]) continue;
+    float av[8], bv[8], o[8];
+    load_ab(a, b, n[u], x.c, c8[u], av, bv);
+    if (POOL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        float f[8];
+        h8_to_f(xin[u][d], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= 0.25f;
+    } else {
+      float f[8];
+      h8_to_f(xin[u][0], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+    }
+    if (res.p) {
+      float f[8];
+      h8_to_f(rin[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += f[i];
+    }
+    affine_store(y, n[u], oy[u], ox[u], c8[u], o, reflect1);
   }
 }
 
@@ -305,8 +335,13 @@ extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b,
   if (res && res->ptr && (!view_ok(res) || res->c != y->c || res->h != y->h || res->w != y->w || res->n != y->n)) return S2V_EINVAL;
   if (reflect1 && (y->h < 4 || y->w < 4)) return S2V_EINVAL;
   const long long total = (long long)y->n * y->h * y->w * (y->c >> 3);
-  affine_act_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param, pool2,
-                                                                           mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
+  const int blocks = ceil_div((total + 1) / 2, 256);
+  if (pool2)
+    affine_act_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param,
+                                                                  mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
+  else
+    affine_act_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param,
+                                                                  mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
