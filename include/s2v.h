@@ -151,6 +151,11 @@ typedef struct {
   int32_t act;  float act_param;
   int32_t out_mode;            /* S2V_OUT_*                                            */
   float*  y_f32;               /* destination for S2V_OUT_F32_NCHW                     */
+  /* optional second K segment (tc only): y += conv_{k2}(x2), stride 1, dilation 1, accumulated in the
+   * same TMEM tile before the epilogue; w = [Cout][segment 1 K | segment 2 K].  x2.ptr NULL => absent.
+   * (FFC: out_g = convl2g(x_l) + conv2(x + fu(x)), models/ffc.py:231,172 - one GEMM, no partial sum in HBM) */
+  s2v_view x2;
+  int32_t k2h, k2w, pad2_h, pad2_w;
 } s2v_conv;
 
 /* SIMT direct convolution (small / awkward layers: Cin=3 7x7, Cout=3, audio

@@ -26,7 +26,8 @@ class Conv(C.Structure):
                 ("kh", c_i32), ("kw", c_i32), ("stride_h", c_i32), ("stride_w", c_i32),
                 ("pad_h", c_i32), ("pad_w", c_i32), ("dil_h", c_i32), ("dil_w", c_i32),
                 ("pad_mode", c_i32), ("up2", c_i32), ("act", c_i32), ("act_param", c_f32),
-                ("out_mode", c_i32), ("y_f32", c_vp)]
+                ("out_mode", c_i32), ("y_f32", c_vp),
+                ("x2", View), ("k2h", c_i32), ("k2w", c_i32), ("pad2_h", c_i32), ("pad2_w", c_i32)]
 
 
 class LinGroup(C.Structure):

@@ -36,6 +36,7 @@ struct TcParams {
   int tiles_w, tiles_h;
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
+  int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   View y, r1, r2;
   const float* scale;
   const float* bias;
@@ -268,7 +269,8 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A 16 KB | B bn*128 B] ... then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -284,11 +286,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
   const int x0 = tw * p.box_w, y0 = th * p.box_h, n0 = tn * p.box_n;
   const int ntile = blockIdx.y;
-  const int KI = p.kh * p.kw * p.cin_chunks;
+  const int KI = p.ki_total;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.ki_total > p.ki0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -309,12 +312,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(empty0 + 8u * s, ph ^ 1u);
-        const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
-        const int ky = tap / p.kw, kx = tap - ky * p.kw;
         const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
         mbar_expect_tx(full0 + 8u * s, stage_bytes);
-        tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
-                    y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
+        if (it < p.ki0) {
+          const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
+                      y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
+        } else {                                   // second K segment: same output box, its own input view
+          const int j = it - p.ki0;
+          const int tap = j / p.cin2_chunks, cc = j - tap * p.cin2_chunks;
+          const int ky = tap / p.k2w, kx = tap - ky * p.k2w;
+          tma_load_4d(a_dst, &tmA2, full0 + 8u * s, cc * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+        }
         tma_load_2d(a_dst + kABytes, &tmB, full0 + 8u * s, it * kChunkK, ntile * p.bn);
       }
     }
@@ -420,7 +430,13 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   const int budget = (bn <= 128 ? 100 : 200) * 1024;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
-  const int ki = d->kh * d->kw * p.cin_chunks;
+  const bool seg2 = d->x2.ptr != nullptr;
+  if (seg2 && (!view_ok(&d->x2) || d->x2.n != N || d->k2h <= 0 || d->k2w <= 0 || d->stride_h != 1 || d->stride_w != 1)) return S2V_EINVAL;
+  p.ki0 = d->kh * d->kw * p.cin_chunks;
+  p.cin2_chunks = seg2 ? ceil_div(d->x2.c, kChunkK) : 1;
+  p.k2w = seg2 ? d->k2w : 1; p.pad2_h = d->pad2_h; p.pad2_w = d->pad2_w;
+  p.ki_total = p.ki0 + (seg2 ? d->k2h * d->k2w * p.cin2_chunks : 0);
+  const int ki = p.ki_total;
   if (stages > ki) stages = ki;          // short K loops: less smem per CTA -> more CTAs resident per SM
   if (stages < 1) stages = 1;
   p.stages = stages;
@@ -430,7 +446,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.scale = d->scale; p.bias = d->bias; p.act = d->act; p.ap = d->act_param;
   p.out_mode = d->out_mode; p.yf = d->y_f32;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)d->x.c, (cuuint64_t)d->x.w, (cuuint64_t)d->x.h, (cuuint64_t)d->x.n};
     cuuint64_t gstr[3] = {(cuuint64_t)d->x.sw * 2, (cuuint64_t)d->x.sh * 2, (cuuint64_t)d->x.sn * 2};
@@ -442,7 +458,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
       return S2V_ECUDA;
   }
   {
-    const cuuint64_t ktot = (cuuint64_t)d->kh * d->kw * p.cin_chunks * kChunkK;
+    const cuuint64_t ktot = (cuuint64_t)p.ki_total * kChunkK;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)((cout + 7) / 8 * 8)};   // weight rows are padded to 8 by the packer
     cuuint64_t gstr[1] = {ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)bn};
@@ -450,6 +466,16 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return S2V_ECUDA;
+  }
+  tmA2 = tmA;
+  if (seg2) {
+    cuuint64_t gdim[4] = {(cuuint64_t)d->x2.c, (cuuint64_t)d->x2.w, (cuuint64_t)d->x2.h, (cuuint64_t)d->x2.n};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->x2.sw * 2, (cuuint64_t)d->x2.sh * 2, (cuuint64_t)d->x2.sn * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x2.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
   size_t ring = (size_t)stages * stage_bytes;
@@ -464,7 +490,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     attr = true;
   }
   dim3 grid(p.tiles_w * p.tiles_h * tiles_n, ceil_div(cout, bn));
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, p);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

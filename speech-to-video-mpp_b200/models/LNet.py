@@ -70,7 +70,11 @@ class LNetEngine(EngineBase):
                     p = f"decoder.res{i}.res{b}.{cv}"
                     q = p + ".ffc"
                     self.pack_conv(q + ".to_l", torch.cat([sd[q + ".convl2l.weight"], sd[q + ".convg2l.weight"]], 1).float())
-                    self.pack_conv(q + ".l2g", sd[q + ".convl2g.weight"].float())
+                    if self.impl == "tc":      # l2g (3x3 on x_l) and conv2 (1x1 on x+fu(x)) accumulate in one TMEM tile
+                        e = self.pack_conv(q + ".l2g", sd[q + ".convl2g.weight"].float())
+                        e["w"] = torch.cat([e["w"], ops.pack_w_tc(sd[q + ".convg2g.conv2.weight"].float())], 1).contiguous()
+                    else:
+                        self.pack_conv(q + ".l2g", sd[q + ".convl2g.weight"].float())
                     s1, b1 = bn_fold(sd, q + ".convg2g.conv1.1")
                     self.pack_conv(q + ".st1", sd[q + ".convg2g.conv1.0.weight"].float(), b1, s1)
                     s2, b2 = bn_fold(sd, q + ".convg2g.fu.bn")
@@ -197,12 +201,16 @@ class LNetEngine(EngineBase):
                         q = p + ".ffc"
                         inter = src[:, 1:-1, 1:-1, :]
                         self.conv(plan, q + ".to_l", src, R[..., :cl])                     # l2l + g2l, 3x3 reflect
-                        self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])            # l2g, 3x3 reflect
+                        if self.impl != "tc":
+                            self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])        # l2g, 3x3 reflect
                         self.conv(plan, q + ".st1", inter[..., cl:], s1, act=L.ACT_RELU)   # 1x1 + BN + ReLU
                         plan.add(ops.op_rfft2(lib, s1, F1))
                         self.conv(plan, q + ".fu", flat(F1), flat(F2), act=L.ACT_RELU)     # spectral 1x1 + BN + ReLU
                         plan.add(ops.op_irfft2(lib, F2, s1, s2))                           # x + fu(x)
-                        self.conv(plan, q + ".st2", s2, R[..., cl:], res2=R[..., cl:])     # + l2g partial sum
+                        if self.impl == "tc":                                              # l2g + conv2 in one GEMM
+                            self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:], x2=s2)
+                        else:
+                            self.conv(plan, q + ".st2", s2, R[..., cl:], res2=R[..., cl:])  # + l2g partial sum
                         off = self.gb_off[p]
                         self.adain(plan, ws, p, R, gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0),
                                    dst[:, 1:-1, 1:-1, :], slope=0.01,

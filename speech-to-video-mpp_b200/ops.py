@@ -88,7 +88,8 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
-            out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0) -> Op:
+            out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0,
+            x2=None, k2=(1, 1), pad2=(0, 0)) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
@@ -111,7 +112,10 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     d.pad_h, d.pad_w = pad
     d.dil_h, d.dil_w = dil
     d.pad_mode, d.up2, d.act, d.act_param = pad_mode, up2, act, float(act_param)
-    keep = (d, x, w, y, scale, bias, res1, res2, y_f32)
+    d.x2 = view(x2) if x2 is not None else null_view()
+    d.k2h, d.k2w = k2
+    d.pad2_h, d.pad2_w = pad2
+    keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2)
     cout, taps = d.y.c, k[0] * k[1]
     for t in (scale, bias):
         assert t is None or (t.dtype == torch.float32 and t.numel() == cout), (name, cout)
@@ -121,7 +125,9 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
         co_pad = -(-cout // 16) * 16 if cout >= 16 else -(-cout // 4) * 4
         assert w.dtype == torch.float32 and tuple(w.shape) == (taps, x.shape[3], co_pad), (name, w.shape, x.shape, cout)
     else:
-        assert w.dtype == torch.float16 and tuple(w.shape) == (-(-cout // 8) * 8, taps * (-(-x.shape[3] // 64) * 64)), (name, w.shape, x.shape, cout)
+        kcols = taps * (-(-x.shape[3] // 64) * 64) + (k2[0] * k2[1] * (-(-x2.shape[3] // 64) * 64) if x2 is not None else 0)
+        assert w.dtype == torch.float16 and tuple(w.shape) == (-(-cout // 8) * 8, kcols), (name, w.shape, x.shape, cout)
+        assert x2 is None or impl == "tc"
     if impl == "simt":
         op = Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
     else:
@@ -131,6 +137,8 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     # algorithmic FLOPs of the reference op this launch replaces (2*MACs on true channel counts);
     # alg_scale lets the sub-pixel phases of nearest-x2 + conv3x3 report the reference's 3x3 work
     op.alg_flops = 2.0 * d.y.n * d.y.h * d.y.w * cout * taps * cin_true * alg_scale
+    if x2 is not None:
+        op.alg_flops += 2.0 * d.y.n * d.y.h * d.y.w * cout * k2[0] * k2[1] * x2.shape[3]
     return op
 
 
