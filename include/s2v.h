@@ -156,6 +156,17 @@ typedef struct {
    * (FFC: out_g = convl2g(x_l) + conv2(x + fu(x)), models/ffc.py:231,172 - one GEMM, no partial sum in HBM) */
   s2v_view x2;
   int32_t k2h, k2w, pad2_h, pad2_w;
+  /* optional fused statistics (tc, fp16 NHWC output only): the epilogue also writes, per image and per
+   * spatial tile of the launch, the sum and sum of squares of every output channel it produced:
+   *   stats_partial[((n*stats_chunks_total + chunk)*stats_c_total + stats_c_off + c)*2 + {0,1}],
+   *   chunk = stats_chunk_off + tile*stats_gmax + g
+   * i.e. the [N][chunks][C][2] layout s2v_ln2d_finalize / s2v_adain_finalize consume (replaces a
+   * s2v_chan_stats pass over the output).  tile = tile_y*tiles_x + tile_x of the launch's pixel boxes;
+   * the rows of a tile are split over stats_groups (power of two, <= stats_gmax, groups*ceil(BN/2) <= 128)
+   * interleaved row groups g so that all 128 epilogue threads take part; entries never written must be
+   * zero (allocate the buffer zeroed once).                                                           */
+  float*  stats_partial;
+  int32_t stats_c_off, stats_c_total, stats_chunk_off, stats_chunks_total, stats_groups, stats_gmax;
 } s2v_conv;
 
 /* SIMT direct convolution (small / awkward layers: Cin=3 7x7, Cout=3, audio
@@ -173,6 +184,8 @@ int s2v_conv_simt(const s2v_conv* d, void* stream);
  * symmetric-padding formula (asymmetric padding of the sub-pixel phases of
  * nearest-x2 + conv3x3 and of ConvTranspose2d).                                 */
 int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, void* stream);
+/* N tile (BN) s2v_conv_tc picks for a given Cout (host-side sizing of the statistics groups) */
+int s2v_conv_tc_tile_n(int cout);
 
 /* grouped small linears (all AdaIN gamma/beta heads of a net in one launch,
  * models/base_blocks.py:136-141,149-151):

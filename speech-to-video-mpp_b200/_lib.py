@@ -27,7 +27,9 @@ class Conv(C.Structure):
                 ("pad_h", c_i32), ("pad_w", c_i32), ("dil_h", c_i32), ("dil_w", c_i32),
                 ("pad_mode", c_i32), ("up2", c_i32), ("act", c_i32), ("act_param", c_f32),
                 ("out_mode", c_i32), ("y_f32", c_vp),
-                ("x2", View), ("k2h", c_i32), ("k2w", c_i32), ("pad2_h", c_i32), ("pad2_w", c_i32)]
+                ("x2", View), ("k2h", c_i32), ("k2w", c_i32), ("pad2_h", c_i32), ("pad2_w", c_i32),
+                ("stats_partial", c_vp), ("stats_c_off", c_i32), ("stats_c_total", c_i32),
+                ("stats_chunk_off", c_i32), ("stats_chunks_total", c_i32), ("stats_groups", c_i32), ("stats_gmax", c_i32)]
 
 
 class LinGroup(C.Structure):
@@ -59,6 +61,7 @@ _SIGNATURES = {
     "s2v_glue_fake_to_face_f32": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "s2v_conv_simt": (C.c_int, [C.POINTER(Conv), c_vp]),
     "s2v_conv_tc": (C.c_int, [C.POINTER(Conv), C.c_int, C.c_int, C.c_int, c_vp]),
+    "s2v_conv_tc_tile_n": (C.c_int, [C.c_int]),
     "s2v_grouped_linear": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_i64, c_vp]),
     "s2v_chan_stats": (C.c_int, [VP, C.c_int, c_vp, c_vp]),
     "s2v_ln2d_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),

@@ -37,6 +37,8 @@ struct TcParams {
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
+  float* stats;                                           // fused per-(image, tile, channel) sum / sumsq
+  int st_c_off, st_c_total, st_chunk_off, st_chunks_total, st_groups, st_gmax;
   View y, r1, r2;
   const float* scale;
   const float* bias;
@@ -227,7 +229,38 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (!direct) {
+      uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_bias + 256);
+      if (p.stats) s_valid[m] = valid ? 1 : 0;
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.stats) {
+        // column sums of the staged fp16 tile: thread (column pair cp, row group g) walks rows g, g+G, ... of
+        // one image of the box at a time, in fixed order (deterministic); every group is its own chunk.
+        const int rows_per_img = p.box_w * p.box_h;
+        const int pairs = (p.bn + 1) >> 1;
+        const int cp = et % pairs, g = et / pairs;
+        const int col = 2 * cp;
+        const int c = ntile * p.bn + col;
+        if (g < p.st_groups && c < p.cout) {
+          const int tile_sp = (blockIdx.x % (p.tiles_w * p.tiles_h));
+          const int chunk = p.st_chunk_off + tile_sp * p.st_gmax + g;
+          for (int im = 0; im < p.box_n; ++im) {
+            if (n0 + im >= p.N) break;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const __half* sp = stage + (size_t)(im * rows_per_img) * pitch + col;
+            const uint8_t* vp = s_valid + im * rows_per_img;
+#pragma unroll 4
+            for (int r = g; r < rows_per_img; r += p.st_groups) {
+              if (!vp[r]) continue;
+              const float2 v = __half22float2(*reinterpret_cast<const __half2*>(sp + (size_t)r * pitch));
+              s0 += v.x; q0 = fmaf(v.x, v.x, q0);
+              s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+            }
+            float* o = p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2;
+            if (c + 1 < p.cout) *reinterpret_cast<float4*>(o) = make_float4(s0, q0, s1, q1);
+            else { o[0] = s0; o[1] = q0; }
+          }
+        }
+      }
       const int cpr = p.bn >> 3;                     // 16-byte chunks per tile row
       const int total = kTileM * cpr;
       // 4 independent (row, 16 B chunk) items per iteration: the residual loads are issued together so
@@ -388,6 +421,18 @@ static EncodeTiledFn get_encode() {
 
 using namespace s2v;
 
+extern "C" int s2v_conv_tc_tile_n(int cout) {
+  if (cout <= 256) return ((cout + 15) / 16) * 16;
+  // pick the N tile that wastes the least: 256, 192 or 128
+  const int cands[3] = {256, 192, 128};
+  int best = 256, best_waste = 1 << 30;
+  for (int i = 0; i < 3; ++i) {
+    const int w = ceil_div(cout, cands[i]) * cands[i] - cout;
+    if (w < best_waste) { best_waste = w; best = cands[i]; }
+  }
+  return best;
+}
+
 extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, void* stream) {
   if (!d || !view_ok(&d->x) || !d->w) return S2V_EINVAL;
   if (d->out_mode == S2V_OUT_F16_NHWC && !view_ok(&d->y)) return S2V_EINVAL;
@@ -413,17 +458,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.str_h = d->stride_h; p.str_w = d->stride_w;
   p.cin_chunks = ceil_div(d->x.c, kChunkK);
   p.cout = cout;
-  int bn = cout <= 256 ? ((cout + 15) / 16) * 16 : 256;
-  if (cout > 256) {
-    // pick the N tile that wastes the least: 256, 192 or 128
-    const int cands[3] = {256, 192, 128};
-    int best = 256, best_waste = 1 << 30;
-    for (int i = 0; i < 3; ++i) {
-      const int w = ceil_div(cout, cands[i]) * cands[i] - cout;
-      if (w < best_waste) { best_waste = w; best = cands[i]; }
-    }
-    bn = best;
-  }
+  const int bn = s2v_conv_tc_tile_n(cout);
   p.bn = bn;
   p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
   const int stage_bytes = kABytes + bn * 128;
@@ -445,6 +480,15 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.r2 = mk(d->res2.ptr ? &d->res2 : nullptr);
   p.scale = d->scale; p.bias = d->bias; p.act = d->act; p.ap = d->act_param;
   p.out_mode = d->out_mode; p.yf = d->y_f32;
+  p.stats = d->stats_partial;
+  p.st_c_off = d->stats_c_off; p.st_c_total = d->stats_c_total;
+  p.st_chunk_off = d->stats_chunk_off; p.st_chunks_total = d->stats_chunks_total;
+  p.st_groups = d->stats_groups; p.st_gmax = d->stats_gmax;
+  if (p.stats && (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_c_total <= 0 || p.st_chunks_total <= 0 ||
+                  p.st_groups <= 0 || p.st_groups > p.st_gmax || p.st_groups * ((bn + 1) / 2) > kTileM ||
+                  (p.st_c_off & 1) || (p.st_c_total & 1) ||
+                  p.st_chunk_off + p.tiles_w * p.tiles_h * p.st_gmax > p.st_chunks_total || p.st_c_off + cout > p.st_c_total))
+    return S2V_EINVAL;
 
   CUtensorMap tmA, tmB, tmA2;
   {
@@ -483,7 +527,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (staging > ring) ring = staging;       // the ring doubles as the epilogue's output staging tile
   p.ring_bytes = (int)ring;
   // barriers + tmem ptr + scale/bias tables sit behind the ring
-  const size_t smem = ring + 16 * stages + 16 + 2 * 256 * sizeof(float) + 64 + 1024;
+  const size_t smem = ring + 16 * stages + 16 + 2 * 256 * sizeof(float) + 128 + 64 + 1024;
   static bool attr = false;   // idempotent
   if (!attr) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;

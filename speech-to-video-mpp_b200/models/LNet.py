@@ -144,9 +144,9 @@ class LNetEngine(EngineBase):
             for t, c_lo in (("inp", 0), ("ref", 3)):       # masked face = planes 0-2, reference = planes 3-5
                 p = f"encoder.first_{t}.model"
                 raw = buf("enc.raw0", (B, 96, 96, 64))
-                self.stem_conv(plan, ws, p, face_in[:, c_lo:c_lo + 3], raw)
+                st = self.stem_conv(plan, ws, p, face_in[:, c_lo:c_lo + 3], raw, stats=True)
                 a0 = buf(f"enc.{t}.a0", (B, 96, 96, 64))
-                self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0)
+                self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0, stats=st)
                 x = a0
                 if t == "inp":
                     skips.append(a0)
@@ -154,14 +154,14 @@ class LNetEngine(EngineBase):
                     p = f"encoder.{t}_down{i}.model"
                     s, co = 96 >> i, 128 << i
                     raw = buf(f"enc.raw{i + 1}", (B, s, s, co))
-                    self.conv(plan, p, x, raw, pad=(1, 1))
+                    st = self.conv_stats(plan, ws, p, x, raw, pad=(1, 1))
                     if i < 2:
                         y = buf(f"enc.{t}.a{i + 1}", (B, s // 2, s // 2, co))
                         if t == "inp":
                             skips.append(y)
                     else:
                         y = cat[..., :512] if t == "inp" else cat[..., 512:]
-                    self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], y, pool2=1)
+                    self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], y, pool2=1, stats=st)
                     x = y
             # ---- cross attention at 12x12 (tokens = pixels) ----------------------------------
             X, Y = cat[..., :512], cat[..., 512:]
@@ -200,7 +200,8 @@ class LNetEngine(EngineBase):
                         p = f"decoder.res{i}.res{b}.{cv}"
                         q = p + ".ffc"
                         inter = src[:, 1:-1, 1:-1, :]
-                        self.conv(plan, q + ".to_l", src, R[..., :cl])                     # l2l + g2l, 3x3 reflect
+                        gm = max(ops.stats_groups(lib, cl, S, S), ops.stats_groups(lib, cg, S, S)) if self.impl == "tc" else 1
+                        st = self.conv_stats(plan, ws, q + ".to_l", src, R[..., :cl], tag=p, c_total=c, gmax=gm)   # l2l + g2l, 3x3 reflect
                         if self.impl != "tc":
                             self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])        # l2g, 3x3 reflect
                         self.conv(plan, q + ".st1", inter[..., cl:], s1, act=L.ACT_RELU)   # 1x1 + BN + ReLU
@@ -208,13 +209,13 @@ class LNetEngine(EngineBase):
                         self.conv(plan, q + ".fu", flat(F1), flat(F2), act=L.ACT_RELU)     # spectral 1x1 + BN + ReLU
                         plan.add(ops.op_irfft2(lib, F2, s1, s2))                           # x + fu(x)
                         if self.impl == "tc":                                              # l2g + conv2 in one GEMM
-                            self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:], x2=s2)
+                            self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], R[..., cl:], tag=p, c_total=c, c_off=cl, gmax=gm, x2=s2)
                         else:
                             self.conv(plan, q + ".st2", s2, R[..., cl:], res2=R[..., cl:])  # + l2g partial sum
                         off = self.gb_off[p]
                         self.adain(plan, ws, p, R, gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0),
                                    dst[:, 1:-1, 1:-1, :], slope=0.01,
-                                   res=None if res is None else res[:, 1:-1, 1:-1, :], reflect1=1)
+                                   res=None if res is None else res[:, 1:-1, 1:-1, :], reflect1=1, stats=st)
                     cur = (cur + 2) % 3
                 dec_out = xps[cur][:, 1:-1, 1:-1, :]
                 co = c // 4 if i == 2 else c // 2
@@ -224,21 +225,23 @@ class LNetEngine(EngineBase):
                 if self.impl == "tc":
                     for ph in (0, 1):
                         for qh in (0, 1):
-                            self.conv(plan, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0)
+                            st = self.conv_stats(plan, ws, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], tag=p,
+                                                 phase=2 * ph + qh, phases=4, pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0)
                 else:
                     self.conv(plan, p, dec_out, uraw, pad=(1, 1), up2=1)
+                    st = None
                 uact = buf(f"dec{i}.uact", (B, S2, S2, co))
-                self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact)
+                self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact, stats=st)
                 p = f"decoder.jump{i}.model"
                 jraw = buf(f"dec{i}.jraw", (B, S2, S2, co))
-                self.conv(plan, p, skips[i], jraw, pad=(1, 1))
+                st = self.conv_stats(plan, ws, p, skips[i], jraw, pad=(1, 1))
                 if i > 0:
                     xps = [buf(f"dec{i - 1}.xp{j}", (B, S2 + 2, S2 + 2, co), zero=True) for j in range(3)]
                     self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], xps[0][:, 1:-1, 1:-1, :],
-                                     res=uact, reflect1=1)
+                                     res=uact, reflect1=1, stats=st)
                 else:
                     last = buf("dec.last", (B, 96, 96, 64))
-                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uact)
+                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uact, stats=st)
             self.conv(plan, "decoder.final.model.0", last, None, pad=(3, 3), act=L.ACT_SIGMOID, y_f32=out,
                       out_shape=(B, 3, 96, 96))
             return dict(mel=mel_in, face=face_in, out=out)

@@ -4,6 +4,7 @@ path happens in libs2v's kernels."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -91,7 +92,7 @@ class EngineBase:
         kw.setdefault("scale", e["scale"])
         return plan.add(ops.op_conv(self.lib, x, e["w"], y, impl=e["impl"], name=name, **kw))
 
-    def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3):
+    def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3, stats=False):
         """k x k zero-padded stem conv on a tiny-Cin NCHW float input (FirstBlock2d / input_layer,
         models/base_blocks.py:79-92,312).  tc path: the input is packed to 8 channels into a buffer
         padded by k//2; one row tap's k x 8 = 56 (+8 zero-weight) consecutive values are exactly one
@@ -101,12 +102,34 @@ class EngineBase:
         if self.W[name]["impl"] != "tc":
             x8 = self.buf(ws, name + ".in8", (n, h, w, 8))
             plan.add(ops.op_pack(self.lib, src_nchw, x8, 0, 8))
-            return self.conv(plan, name, x8, y, pad=(pad, pad), cin_true=cin_true)
+            self.conv(plan, name, x8, y, pad=(pad, pad), cin_true=cin_true)
+            return None
         wp = w + 2 * pad + 2                        # +2: the 8th (zero-weight) pixel of the last window stays in the row
         xp = self.buf(ws, name + ".in8p", (n, h + 2 * pad, wp, 8), zero=True)
         plan.add(ops.op_pack(self.lib, src_nchw, xp[:, pad:pad + h, pad:pad + w, :], 0, 8))
         win = torch.as_strided(xp, (n, h + 2 * pad, w, 64), (xp.stride(0), xp.stride(1), 8, 1))
-        return self.conv(plan, name, win, y, pad=(0, 0), cin_true=cin_true * k)
+        if stats:
+            return self.conv_stats(plan, ws, name, win, y, pad=(0, 0), cin_true=cin_true * k)
+        self.conv(plan, name, win, y, pad=(0, 0), cin_true=cin_true * k)
+        return None
+
+    def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, gmax=None, **kw):
+        """conv whose epilogue also emits the per-(image, tile, channel) sums of its output (tc path).
+        Returns (partial, chunks) for layernorm2d/adain(stats=...), or None on the simt path (the caller
+        then falls back to a chan_stats pass).  Measured on B200 (round 1): with the current non-overlapped
+        epilogue the fused statistics cost more inside the GEMM (+3.2 ms/step) than the separate
+        full-chip chan_stats pass they remove (2.7 ms/step), so this is opt-in (S2V_FUSED_STATS=1) until the
+        epilogue is overlapped with the next tile's main loop."""
+        if self.W[name]["impl"] != "tc" or os.environ.get("S2V_FUSED_STATS", "0") != "1":
+            self.conv(plan, name, x, y, **kw)
+            return None
+        n, h, w, c = y.shape
+        tiles = ops.box_tiles(h, w, n)
+        g = ops.stats_groups(self.lib, c, h, w)
+        gmax = max(g, gmax or 1)
+        partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * gmax * phases, c_total or c, 2), torch.float32, zero=True)
+        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles * gmax, g, gmax), **kw)
+        return partial, tiles * gmax * phases
 
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):
@@ -118,10 +141,16 @@ class EngineBase:
         plan.add(ops.op_chan_stats(self.lib, x, chunks, partial))
         return partial, chunks, a, b
 
-    def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0):
-        """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124)."""
+    def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0, stats=None):
+        """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124).
+        ``stats``: (partial, chunks) already produced by the conv epilogue."""
         n, h, w, c = x.shape
-        partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        if stats is None:
+            partial, chunks, a, b = self._stats(plan, ws, tag, x)
+        else:
+            partial, chunks = stats
+            a = self.buf(ws, tag + ".a", (n, c), torch.float32)
+            b = self.buf(ws, tag + ".b", (n, c), torch.float32)
         plan.add(ops.op_ln2d_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, a, b))
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=L.ACT_LRELU, act_param=slope, pool2=pool2, res=res,
                                    reflect1=reflect1))

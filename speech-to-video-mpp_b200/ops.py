@@ -71,7 +71,10 @@ class Plan:
 
 
 def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
-    """Box of 128 output pixels (box_w, box_h, box_n) with the least padding waste."""
+    """Box of 128 output pixels (box_w, box_h, box_n) with the least padding waste.  The choice is a
+    function of the image size ONLY (evaluated for a large batch): the spatial tiling also defines the
+    reduction tree of the fused statistics, which must not change with the batch a frame is computed in."""
+    n = 4096
     best, best_key = None, None
     for bw in (128, 64, 32, 16, 8, 4, 2, 1):
         for bh in (128, 64, 32, 16, 8, 4, 2, 1):
@@ -89,7 +92,7 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
             out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0,
-            x2=None, k2=(1, 1), pad2=(0, 0)) -> Op:
+            x2=None, k2=(1, 1), pad2=(0, 0), stats=None) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
@@ -115,7 +118,13 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     d.x2 = view(x2) if x2 is not None else null_view()
     d.k2h, d.k2w = k2
     d.pad2_h, d.pad2_w = pad2
-    keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2)
+    if stats is not None:       # (partial [N,chunks,C,2] float32, c_off, chunk_off, groups, gmax): fused output statistics
+        partial, c_off, chunk_off, d.stats_groups, d.stats_gmax = stats
+        assert impl == "tc" and partial.dtype == torch.float32 and partial.dim() == 4 and partial.shape[0] == d.y.n
+        d.stats_partial = partial.data_ptr()
+        d.stats_c_off, d.stats_c_total = c_off, partial.shape[2]
+        d.stats_chunk_off, d.stats_chunks_total = chunk_off, partial.shape[1]
+    keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2, stats)
     cout, taps = d.y.c, k[0] * k[1]
     for t in (scale, bias):
         assert t is None or (t.dtype == torch.float32 and t.numel() == cout), (name, cout)
@@ -140,6 +149,22 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     if x2 is not None:
         op.alg_flops += 2.0 * d.y.n * d.y.h * d.y.w * cout * k2[0] * k2[1] * x2.shape[3]
     return op
+
+
+def box_tiles(h: int, w: int, n: int) -> int:
+    """Spatial tiles per image of a conv_tc launch with the default box (= statistics chunks it emits)."""
+    bw, bh, _ = choose_box(h, w, n)
+    return -(-w // bw) * -(-h // bh)
+
+
+def stats_groups(lib, cout: int, h: int, w: int) -> int:
+    """Row groups the conv_tc epilogue splits a tile into for the fused statistics (see include/s2v.h)."""
+    bn = lib.s2v_conv_tc_tile_n(cout)
+    bw, bh, _ = choose_box(h, w, 1)
+    g = 1
+    while g * 2 <= 8 and g * 2 * ((bn + 1) // 2) <= 128 and g * 2 <= bw * bh:
+        g *= 2
+    return g
 
 
 def stats_chunks(n: int, hw: int) -> int:

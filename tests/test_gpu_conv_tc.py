@@ -189,3 +189,22 @@ def test_two_segment_gemm(G):
     ref = F.conv2d(F.pad(xl, (1, 1, 1, 1), mode="reflect"), w3.half().float()) + F.conv2d(s2.permute(0, 3, 1, 2).float(), w1.half().float())
     m, rel = G.report("conv_tc two-segment (3x3 + 1x1)", G.nchw(R[..., cl:]), ref)
     assert rel < 3e-3 and (R[..., :cl] == 5).all()
+
+
+def test_fused_epilogue_statistics(G):
+    """conv_tc's optional fused per-(image, tile, channel) sums feed the same finalize kernels as chan_stats."""
+    lib, L, ops = G.lib(), G.L, G.ops
+    torch.manual_seed(12)
+    for (n, s, cin, cout) in ((9, 12, 128, 256), (3, 48, 64, 32), (2, 24, 64, 96)):
+        x = torch.randn(n, s, s, cin, device="cuda").half()
+        wt = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
+        y = torch.zeros(n, s, s, cout, dtype=torch.float16, device="cuda")
+        tiles, g = ops.box_tiles(s, s, n), ops.stats_groups(lib, cout, s, s)
+        partial = torch.zeros(n, tiles * g, cout, 2, device="cuda")
+        ops.op_conv(lib, x, ops.pack_w_tc(wt), y, k=(3, 3), pad=(1, 1), stats=(partial, 0, 0, g, g)).run()
+        torch.cuda.synchronize()
+        yf = y.float()
+        ref_s, ref_q = yf.sum((1, 2)), (yf * yf).sum((1, 2))
+        got = partial.sum(1)
+        assert (got[..., 0] - ref_s).abs().max().item() < 2e-2 * max(1.0, ref_s.abs().max().item())
+        assert (got[..., 1] - ref_q).abs().max().item() < 1e-3 * ref_q.abs().max().item()
