@@ -36,6 +36,7 @@ struct TcParams {
   int tiles_w, tiles_h;
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
+  int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store;
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   float* stats;                                           // fused per-(image, tile, channel) sum / sumsq
   int st_c_off, st_c_total, st_chunk_off, st_chunks_total, st_groups, st_gmax;
@@ -129,12 +130,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-struct EpiCtx {
-  uint8_t* smem_raw;
-  uint32_t smem_base, tptr_addr, tfull, tmem;
-  int n0, y0, x0, ntile, warp, lane;
-};
-
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, float ap) {
   if (ACT == S2V_ACT_RELU) return fmaxf(v, 0.f);
@@ -148,110 +143,156 @@ __device__ __forceinline__ float act_t(float v, float ap) {
   return v;
 }
 
-// TMEM -> registers -> scale/bias/activation -> (staged, coalesced | direct) stores.  TMEM lane quarter = warp % 4.
+struct Smem {            // offsets (shared-space addresses) of the carved regions
+  uint32_t ring, stage_out, full0, empty0, tfull0, tempty0, tptr;
+  float* s_scale;
+  float* s_bias;
+  uint8_t* s_valid;
+  __half* stage;
+};
+
+__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& ntile, int& n0, int& y0, int& x0, int& tile_sp) {
+  const int m_tiles = p.m_tiles;
+  ntile = tile / m_tiles;
+  const int mt = tile - ntile * m_tiles;
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int tn = mt / per_img;
+  tile_sp = mt - tn * per_img;
+  const int th = tile_sp / p.tiles_w, tw = tile_sp - th * p.tiles_w;
+  x0 = tw * p.box_w; y0 = th * p.box_h; n0 = tn * p.box_n;
+}
+
+// Epilogue warps (4): for every tile of this CTA, TMEM -> registers -> scale/bias/activation ->
+// (fp16 tile staged in smem -> optional column statistics -> coalesced 16-byte stores [+ residual]) or direct
+// stores (fp32 NCHW heads, pre-activation residual).  Runs concurrently with the producer / MMA warps
+// working on the NEXT tile (the accumulator is double-buffered in TMEM).
 template <int ACT>
-__device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
-  uint8_t* smem_raw = cx.smem_raw;
-  const uint32_t smem_base = cx.smem_base, tptr_addr = cx.tptr_addr, tfull = cx.tfull, tmem = cx.tmem;
-  const int n0 = cx.n0, y0 = cx.y0, x0 = cx.x0, ntile = cx.ntile, warp = cx.warp, lane = cx.lane;
-    const int q = warp & 3;
-    const int et = threadIdx.x - 64;                 // 0..127 within the epilogue warps
-    const int m = q * 32 + lane;
-    const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm, const CUtensorMap* tmY, uint32_t tmem, int warp,
+                                              int lane) {
+  const int q = warp & 3;                          // TMEM lane quarter this warp may access
+  const int et = threadIdx.x - 64;                 // 0..127
+  const int m = q * 32 + lane;                     // tile row owned in phase 1
+  const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
+  const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
+  const int half_n = p.bn > 128 ? 128 : p.bn;      // columns staged per pass (<= 2 panels of 64 channels)
+  // staging layout = what a SWIZZLE_128B TMA store expects: panels of 64 channels, [128 rows][128 B] each,
+  // 16-byte chunk j of row r stored at chunk position j ^ (r & 7)  (also makes the smem stores conflict-free)
+  const bool tma_store = !direct && (p.r2.p == nullptr) && p.use_tma_store;
+  auto stage_ptr = [&](int row, int col) -> __half* {      // col multiple of 8 within the pass
+    const int panel = col >> 6, chunk = (col >> 3) & 7;
+    return sm.stage + (size_t)panel * (kTileM * 64) + (size_t)row * 64 + ((chunk ^ (row & 7)) << 3);
+  };
+  int j = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+    int ntile, n0, y0, x0, tile_sp;
+    tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
     const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
     const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
-    // per-channel scale / bias of this N tile -> shared memory (overlaps the main loop)
-    float* s_scale = reinterpret_cast<float*>(smem_raw + (tptr_addr + 8u - smem_u32(smem_raw)));
-    float* s_bias = s_scale + 256;
+    const uint32_t buf = (uint32_t)j & 1u;
+    // previous tile's stores are done with the staging tile / tables before they are overwritten
+    if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int i = et; i < p.bn; i += 128) {
       const int c = ntile * p.bn + i;
-      s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
-      s_bias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+      sm.s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
+      sm.s_bias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
     }
+    if (!direct && p.stats) sm.s_valid[m] = valid ? 1 : 0;
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    mbar_wait(tfull, 0);
+    mbar_wait(sm.tfull0 + 8u * buf, ((uint32_t)j >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
-    // staged path: the smem ring is idle once the accumulator is complete (every MMA has retired, so
-    // every TMA load has landed and been consumed) -> reuse it as a [128][bn + 8] fp16 tile, then
-    // write it out with coalesced 16-byte stores (+ residual) instead of one pixel row per thread.
-    const int pitch = p.bn + 8;                      // +16 B per row: conflict-free 16-byte smem stores
-    __half* stage = reinterpret_cast<__half*>(smem_raw + (smem_base - smem_u32(smem_raw)));
-    for (int cb = 0; cb < p.bn; cb += 32) {
-      float v[32];
-      tmem_ld16_nowait(trow + (uint32_t)cb, v);
-      if (cb + 16 < p.bn) tmem_ld16_nowait(trow + (uint32_t)(cb + 16), v + 16);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.tmem_buf_cols;
+    for (int pass0 = 0; pass0 < p.bn; pass0 += half_n) {
+      const int pass_n = min(half_n, p.bn - pass0);
+      for (int cb = 0; cb < pass_n; cb += 32) {
+        float v[32];
+        tmem_ld16_nowait(trow + (uint32_t)(pass0 + cb), v);
+        if (cb + 16 < pass_n) tmem_ld16_nowait(trow + (uint32_t)(pass0 + cb + 16), v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int cl = cb + 8 * g;                  // column within the N tile
-        if (cl >= p.bn) break;
-        const int c = ntile * p.bn + cl;
-        float* o = v + 8 * g;
-        const float4 s0 = *reinterpret_cast<const float4*>(s_scale + cl), s1 = *reinterpret_cast<const float4*>(s_scale + cl + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl), b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
-        o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
-        o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
-        if (!direct) {
+        for (int g = 0; g < 4; ++g) {
+          const int cl = cb + 8 * g;                // column within the pass
+          if (cl >= pass_n) break;
+          const int ct = pass0 + cl;                // column within the N tile
+          const int c = ntile * p.bn + ct;
+          float* o = v + 8 * g;
+          const float4 s0 = *reinterpret_cast<const float4*>(sm.s_scale + ct), s1 = *reinterpret_cast<const float4*>(sm.s_scale + ct + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sm.s_bias + ct), b1 = *reinterpret_cast<const float4*>(sm.s_bias + ct + 4);
+          o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
+          o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
+          if (!direct) {
+            if (ACT != S2V_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
+            }
+            st_h8(stage_ptr(m, cl), f_to_h8(o));
+            continue;
+          }
+          if (!valid || c >= p.cout) continue;
+          if (p.r1.p) {
+            float f[8];
+            h8_to_f(ld_h8(p.r1.p + n * p.r1.sn + oy * p.r1.sh + ox * p.r1.sw + c), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += f[i];
+          }
           if (ACT != S2V_ACT_NONE) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
           }
-          st_h8(stage + (size_t)m * pitch + cl, f_to_h8(o));
-          continue;
-        }
-        if (!valid || c >= p.cout) continue;
-        if (p.r1.p) {
-          float f[8];
-          h8_to_f(ld_h8(p.r1.p + n * p.r1.sn + oy * p.r1.sh + ox * p.r1.sw + c), f);
+          if (p.r2.p) {
+            float f[8];
+            h8_to_f(ld_h8(p.r2.p + n * p.r2.sn + oy * p.r2.sh + ox * p.r2.sw + c), f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += f[i];
-        }
-        if (ACT != S2V_ACT_NONE) {
+            for (int i = 0; i < 8; ++i) o[i] += f[i];
+          }
+          if (p.out_mode == S2V_OUT_F32_NCHW) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
-        }
-        if (p.r2.p) {
-          float f[8];
-          h8_to_f(ld_h8(p.r2.p + n * p.r2.sn + oy * p.r2.sh + ox * p.r2.sw + c), f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += f[i];
-        }
-        if (p.out_mode == S2V_OUT_F32_NCHW) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (c + i < p.cout) p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
-        } else {
-          st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
+            for (int i = 0; i < 8; ++i)
+              if (c + i < p.cout) p.yf[(((size_t)n * p.cout + c + i) * p.OH + oy) * p.OW + ox] = o[i];
+          } else {
+            st_h8(p.y.p + n * p.y.sn + oy * p.y.sh + ox * p.y.sw + c, f_to_h8(o));
+          }
         }
       }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (!direct) {
-      uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_bias + 256);
-      if (p.stats) s_valid[m] = valid ? 1 : 0;
+      const bool last_pass = pass0 + half_n >= p.bn;
+      if (last_pass) {
+        // all TMEM reads of this accumulator buffer are complete: hand it back to the MMA warp
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.tempty0 + 8u * buf) : "memory");
+      }
+      if (direct) continue;
+      if (tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tma_store && et == 0) {
+        // one bulk tensor store per 64-channel panel; TMA clips rows/channels outside the output view
+        for (int pc = 0; pc < pass_n; pc += 64) {
+          const uint32_t src = sm.stage_out + (uint32_t)(pc >> 6) * (kTileM * 128);
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(tmY), "r"(src), "r"(ntile * p.bn + pass0 + pc), "r"(x0), "r"(y0), "r"(n0)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if (p.stats) {
         // column sums of the staged fp16 tile: thread (column pair cp, row group g) walks rows g, g+G, ... of
         // one image of the box at a time, in fixed order (deterministic); every group is its own chunk.
         const int rows_per_img = p.box_w * p.box_h;
-        const int pairs = (p.bn + 1) >> 1;
+        const int pairs = (pass_n + 1) >> 1;
         const int cp = et % pairs, g = et / pairs;
         const int col = 2 * cp;
-        const int c = ntile * p.bn + col;
+        const int c = ntile * p.bn + pass0 + col;
         if (g < p.st_groups && c < p.cout) {
-          const int tile_sp = (blockIdx.x % (p.tiles_w * p.tiles_h));
           const int chunk = p.st_chunk_off + tile_sp * p.st_gmax + g;
           for (int im = 0; im < p.box_n; ++im) {
             if (n0 + im >= p.N) break;
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const __half* sp = stage + (size_t)(im * rows_per_img) * pitch + col;
-            const uint8_t* vp = s_valid + im * rows_per_img;
+            const uint8_t* vp = sm.s_valid + im * rows_per_img;
 #pragma unroll 4
             for (int r = g; r < rows_per_img; r += p.st_groups) {
               if (!vp[r]) continue;
-              const float2 v = __half22float2(*reinterpret_cast<const __half2*>(sp + (size_t)r * pitch));
+              const int row = im * rows_per_img + r;
+              const float2 v = __half22float2(*reinterpret_cast<const __half2*>(stage_ptr(row, col & ~7) + (col & 7)));
               s0 += v.x; q0 = fmaf(v.x, v.x, q0);
               s1 += v.y; q1 = fmaf(v.y, v.y, q1);
             }
@@ -261,8 +302,8 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
           }
         }
       }
-      const int cpr = p.bn >> 3;                     // 16-byte chunks per tile row
-      const int total = kTileM * cpr;
+      const int cpr = pass_n >> 3;                  // 16-byte chunks per staged row
+      const int total = tma_store ? 0 : kTileM * cpr;
       // 4 independent (row, 16 B chunk) items per iteration: the residual loads are issued together so
       // their L2 latency overlaps (y and res2 may be the same buffer, so the compiler cannot hoist them)
       for (int base = et; base < total; base += 4 * 128) {
@@ -274,13 +315,13 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
           const int idx = base + u * 128;
           ok[u] = idx < total;
           const int row = ok[u] ? idx / cpr : 0, ch = ok[u] ? idx - row * cpr : 0;
-          const int c = ntile * p.bn + ch * 8;
+          const int c = ntile * p.bn + pass0 + ch * 8;
           const int rw = row % p.box_w, rh = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
           const int pn = n0 + rn, py = y0 + rh, px = x0 + rw;
           ok[u] = ok[u] && pn < p.N && py < p.OH && px < p.OW && c < p.cout;
           dst[u] = p.y.p + pn * p.y.sn + py * p.y.sh + px * p.y.sw + c;
           if (ok[u]) {
-            hv[u] = ld_h8(stage + (size_t)row * pitch + ch * 8);
+            hv[u] = ld_h8(stage_ptr(row, ch * 8));
             if (p.r2.p) rv[u] = ld_h8(p.r2.p + pn * p.r2.sn + py * p.r2.sh + px * p.r2.sw + c);
           }
         }
@@ -298,39 +339,54 @@ __device__ __forceinline__ void epilogue(const TcParams& p, const EpiCtx& cx) {
           st_h8(dst[u], hv[u]);
         }
       }
+      if (!last_pass) {                               // staging tile is reused by the next pass
+        if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
+  }
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem ring and its
+// mbarrier phases run continuously across tiles; the fp32 accumulator is double-buffered in TMEM so the
+// epilogue of tile j overlaps the TMA/MMA main loop of tile j+1.
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stage][A 16 KB | B bn*128 B] ... then barriers
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t bar_base = smem_base + (uint32_t)p.ring_bytes;   // full[s], empty[s], tmem_full, tmem_ptr, scale/bias
-  const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages, tfull = bar_base + 16u * p.stages;
-  const uint32_t tptr_addr = tfull + 8u;
-  volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
+  Smem sm;
+  sm.ring = smem_base;
+  sm.stage_out = smem_base + (uint32_t)p.ring_bytes;
+  const uint32_t bar_base = sm.stage_out + (uint32_t)p.stage_out_bytes;
+  sm.full0 = bar_base;
+  sm.empty0 = bar_base + 8u * p.stages;
+  sm.tfull0 = bar_base + 16u * p.stages;
+  sm.tempty0 = sm.tfull0 + 16u;
+  sm.tptr = sm.tempty0 + 16u;
+  sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
+  sm.s_bias = sm.s_scale + 256;
+  sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_bias + 256);
+  sm.stage = reinterpret_cast<__half*>(smem_raw + (sm.stage_out - raw_u32));
+  volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (sm.tptr - raw_u32));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
-  const int x0 = tw * p.box_w, y0 = th * p.box_h, n0 = tn * p.box_n;
-  const int ntile = blockIdx.y;
   const int KI = p.ki_total;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.ki_total > p.ki0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
-    mbar_init(tfull, 1);
+    if (p.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(sm.full0 + 8u * s, 1); mbar_init(sm.empty0 + 8u * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull0 + 8u * b, 1); mbar_init(sm.tempty0 + 8u * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr_addr), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm.tptr), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -341,24 +397,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < KI; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(empty0 + 8u * s, ph ^ 1u);
-        const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-        mbar_expect_tx(full0 + 8u * s, stage_bytes);
-        if (it < p.ki0) {
-          const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
-          tma_load_4d(a_dst, &tmA, full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
-                      y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
-        } else {                                   // second K segment: same output box, its own input view
-          const int j = it - p.ki0;
-          const int tap = j / p.cin2_chunks, cc = j - tap * p.cin2_chunks;
-          const int ky = tap / p.k2w, kx = tap - ky * p.k2w;
-          tma_load_4d(a_dst, &tmA2, full0 + 8u * s, cc * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+      uint32_t it_g = 0;                            // global k-iteration counter (ring position across tiles)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int ntile, n0, y0, x0, tile_sp;
+        tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+        for (int it = 0; it < KI; ++it, ++it_g) {
+          const uint32_t s = it_g % (uint32_t)p.stages;
+          const uint32_t ph = (it_g / (uint32_t)p.stages) & 1u;
+          mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
+          const uint32_t a_dst = sm.ring + s * stage_bytes;
+          mbar_expect_tx(sm.full0 + 8u * s, stage_bytes);
+          if (it < p.ki0) {
+            const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            tma_load_4d(a_dst, &tmA, sm.full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
+                        y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
+          } else {                                   // second K segment: same output box, its own input view
+            const int jj = it - p.ki0;
+            const int tap = jj / p.cin2_chunks, cc = jj - tap * p.cin2_chunks;
+            const int ky = tap / p.k2w, kx = tap - ky * p.k2w;
+            tma_load_4d(a_dst, &tmA2, sm.full0 + 8u * s, cc * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+          }
+          tma_load_2d(a_dst + kABytes, &tmB, sm.full0 + 8u * s, it * kChunkK, ntile * p.bn);
         }
-        tma_load_2d(a_dst + kABytes, &tmB, full0 + 8u * s, it * kChunkK, ntile * p.bn);
       }
     }
   } else if (warp == 1) {
@@ -366,33 +427,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== MMA issuer (one thread) =====
       // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      for (int it = 0; it < KI; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(full0 + 8u * s, ph);
+      uint32_t it_g = 0;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = (uint32_t)j & 1u;
+        mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + kABytes);
+        const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
+        for (int it = 0; it < KI; ++it, ++it_g) {
+          const uint32_t s = it_g % (uint32_t)p.stages;
+          const uint32_t ph = (it_g / (uint32_t)p.stages) & 1u;
+          mbar_wait(sm.full0 + 8u * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = sm.ring + s * stage_bytes;
+          const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + kABytes);
 #pragma unroll
-        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
-          // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
-          umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(sm.empty0 + 8u * s);          // frees the smem slot when these MMAs retire
         }
-        umma_commit(empty0 + 8u * s);          // frees the smem slot when these MMAs retire
+        umma_commit(sm.tfull0 + 8u * buf);          // accumulator of this tile complete
       }
-      umma_commit(tfull);                      // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5 (activation resolved once, outside the per-element loops) =====
-    const EpiCtx cx{smem_raw, smem_base, tptr_addr, tfull, tmem, n0, y0, x0, ntile, warp, lane};
     switch (p.act) {
-      case S2V_ACT_RELU: epilogue<S2V_ACT_RELU>(p, cx); break;
-      case S2V_ACT_LRELU: epilogue<S2V_ACT_LRELU>(p, cx); break;
-      case S2V_ACT_SIGMOID: epilogue<S2V_ACT_SIGMOID>(p, cx); break;
-      case S2V_ACT_TANH: epilogue<S2V_ACT_TANH>(p, cx); break;
-      case S2V_ACT_GELU: epilogue<S2V_ACT_GELU>(p, cx); break;
-      default: epilogue<S2V_ACT_NONE>(p, cx); break;
+      case S2V_ACT_RELU: epilogue_loop<S2V_ACT_RELU>(p, sm, &tmY, tmem, warp, lane); break;
+      case S2V_ACT_LRELU: epilogue_loop<S2V_ACT_LRELU>(p, sm, &tmY, tmem, warp, lane); break;
+      case S2V_ACT_SIGMOID: epilogue_loop<S2V_ACT_SIGMOID>(p, sm, &tmY, tmem, warp, lane); break;
+      case S2V_ACT_TANH: epilogue_loop<S2V_ACT_TANH>(p, sm, &tmY, tmem, warp, lane); break;
+      case S2V_ACT_GELU: epilogue_loop<S2V_ACT_GELU>(p, sm, &tmY, tmem, warp, lane); break;
+      default: epilogue_loop<S2V_ACT_NONE>(p, sm, &tmY, tmem, warp, lane); break;
     }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores landed
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -460,9 +529,13 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.cout = cout;
   const int bn = s2v_conv_tc_tile_n(cout);
   p.bn = bn;
-  p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+  // two accumulator buffers (epilogue of tile j overlaps the main loop of tile j+1)
+  p.tmem_buf_cols = bn <= 16 ? 16 : bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * p.tmem_buf_cols < 32 ? 32 : 2 * p.tmem_buf_cols;
   const int stage_bytes = kABytes + bn * 128;
-  const int budget = (bn <= 128 ? 100 : 200) * 1024;
+  const int half_n = bn > 128 ? 128 : bn;
+  p.stage_out_bytes = ((half_n + 63) / 64) * kTileM * 128;                 // fp16 output staging: 64-channel swizzled panels
+  const int budget = 224 * 1024 - p.stage_out_bytes - 4096;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   const bool seg2 = d->x2.ptr != nullptr;
@@ -471,9 +544,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.cin2_chunks = seg2 ? ceil_div(d->x2.c, kChunkK) : 1;
   p.k2w = seg2 ? d->k2w : 1; p.pad2_h = d->pad2_h; p.pad2_w = d->pad2_w;
   p.ki_total = p.ki0 + (seg2 ? d->k2h * d->k2w * p.cin2_chunks : 0);
-  const int ki = p.ki_total;
-  if (stages > ki) stages = ki;          // short K loops: less smem per CTA -> more CTAs resident per SM
-  if (stages < 1) stages = 1;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   p.y = mk(d->y);
   p.r1 = mk(d->res1.ptr ? &d->res1 : nullptr);
@@ -522,19 +593,36 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
-  size_t ring = (size_t)stages * stage_bytes;
-  const size_t staging = (((size_t)kTileM * (bn + 8) * 2) + 1023) / 1024 * 1024;
-  if (staging > ring) ring = staging;       // the ring doubles as the epilogue's output staging tile
-  p.ring_bytes = (int)ring;
-  // barriers + tmem ptr + scale/bias tables sit behind the ring
-  const size_t smem = ring + 16 * stages + 16 + 2 * 256 * sizeof(float) + 128 + 64 + 1024;
+  CUtensorMap tmY = tmA;
+  p.use_tma_store = (d->out_mode == S2V_OUT_F16_NHWC && !d->res1.ptr && !d->res2.ptr) ? 1 : 0;
+  if (p.use_tma_store) {
+    cuuint64_t gdim[4] = {(cuuint64_t)d->y.c, (cuuint64_t)d->y.w, (cuuint64_t)d->y.h, (cuuint64_t)d->y.n};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->y.sw * 2, (cuuint64_t)d->y.sh * 2, (cuuint64_t)d->y.sn * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->y.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      p.use_tma_store = 0;                  // e.g. a stride the encoder rejects: fall back to the manual coalesced stores
+  }
+  p.ring_bytes = stages * stage_bytes;
+  // ring | output staging tile | barriers + tmem ptr | scale/bias tables | row-valid mask
+  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 64 + 2 * 256 * sizeof(float) + 128 + 1024;
+  if (smem > 227 * 1024) return S2V_EINVAL;
+  p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  p.total_tiles = p.m_tiles * ceil_div(cout, bn);
   static bool attr = false;   // idempotent
   if (!attr) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
     attr = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * tiles_n, ceil_div(cout, bn));
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, p);
+  static int n_sm = 0;        // immutable after the first call
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+      return S2V_ECUDA;
+  }
+  const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
