@@ -36,8 +36,10 @@ struct TcParams {
   int tiles_w, tiles_h;
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
-  int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store;
+  int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols;
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
+  // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
+  int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident;
   float* stats;                                           // fused per-(image, tile, channel) sum / sumsq
   int st_c_off, st_c_total, st_chunk_off, st_chunks_total, st_groups, st_gmax;
   View y, r1, r2;
@@ -91,8 +93,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
 // start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(8 rows * 128 B = 1024 B)>>4 <<32 | version 1 <<46 | SW128 (2) <<61
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes = 1024) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
@@ -103,6 +105,21 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// same instruction with the 64-bit descriptors assembled from (lo, hi) words inside the asm block: the issue loop
+// only does 32-bit adds on the address field (the single issuing thread is latency-bound, every instruction counts)
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -144,7 +161,7 @@ __device__ __forceinline__ float act_t(float v, float ap) {
 }
 
 struct Smem {            // offsets (shared-space addresses) of the carved regions
-  uint32_t ring, stage_out, full0, empty0, tfull0, tempty0, tptr;
+  uint32_t ring, stage_out, full0, empty0, tfull0, tempty0, tptr, afull0, aempty0, ball, bring;
   float* s_scale;
   float* s_bias;
   uint8_t* s_valid;
@@ -174,7 +191,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   const int m = q * 32 + lane;                     // tile row owned in phase 1
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
   const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
-  const int half_n = p.bn > 128 ? 128 : p.bn;      // columns staged per pass (<= 2 panels of 64 channels)
+  const int half_n = p.bn > p.pass_cols ? p.pass_cols : p.bn;      // columns staged per pass (1 or 2 panels of 64 channels)
   // staging layout = what a SWIZZLE_128B TMA store expects: panels of 64 channels, [128 rows][128 B] each,
   // 16-byte chunk j of row r stored at chunk position j ^ (r & 7)  (also makes the smem stores conflict-free)
   const bool tma_store = !direct && (p.r2.p == nullptr) && p.use_tma_store;
@@ -366,7 +383,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   sm.empty0 = bar_base + 8u * p.stages;
   sm.tfull0 = bar_base + 16u * p.stages;
   sm.tempty0 = sm.tfull0 + 16u;
-  sm.tptr = sm.tempty0 + 16u;
+  sm.afull0 = sm.tempty0 + 16u;             // up to 4 A-patch slots (halo mode)
+  sm.aempty0 = sm.afull0 + 32u;
+  sm.ball = sm.aempty0 + 32u;               // resident-weights barrier (halo mode)
+  sm.tptr = sm.ball + 16u;
+  sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
   sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
   sm.s_bias = sm.s_scale + 256;
   sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_bias + 256);
@@ -383,6 +404,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(sm.full0 + 8u * s, 1); mbar_init(sm.empty0 + 8u * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull0 + 8u * b, 1); mbar_init(sm.tempty0 + 8u * b, 4); }
+    for (int a = 0; a < 4; ++a) { mbar_init(sm.afull0 + 8u * a, 1); mbar_init(sm.aempty0 + 8u * a, 1); }
+    mbar_init(sm.ball, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -396,29 +419,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it_g = 0;                            // global k-iteration counter (ring position across tiles)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int ntile, n0, y0, x0, tile_sp;
-        tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
-        for (int it = 0; it < KI; ++it, ++it_g) {
-          const uint32_t s = it_g % (uint32_t)p.stages;
-          const uint32_t ph = (it_g / (uint32_t)p.stages) & 1u;
-          mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
-          const uint32_t a_dst = sm.ring + s * stage_bytes;
-          mbar_expect_tx(sm.full0 + 8u * s, stage_bytes);
-          if (it < p.ki0) {
-            const int tap = it / p.cin_chunks, cc = it - tap * p.cin_chunks;
-            const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            tma_load_4d(a_dst, &tmA, sm.full0 + 8u * s, cc * kChunkK, x0 * p.str_w - p.pad_w + kx * p.dil_w,
-                        y0 * p.str_h - p.pad_h + ky * p.dil_h, n0);
-          } else {                                   // second K segment: same output box, its own input view
-            const int jj = it - p.ki0;
-            const int tap = jj / p.cin2_chunks, cc = jj - tap * p.cin2_chunks;
-            const int ky = tap / p.k2w, kx = tap - ky * p.k2w;
-            tma_load_4d(a_dst, &tmA2, sm.full0 + 8u * s, cc * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+      // ===== TMA producer =====  (ring state is kept incrementally: no divisions in the single-thread loops)
+      uint32_t s = 0, ph = 0;                       // B (or A+B) ring slot / phase
+      if (p.halo) {
+        if (p.b_resident) {                         // the whole weight matrix of this (single) N tile stays in smem
+          mbar_expect_tx(sm.ball, (uint32_t)KI * b_bytes);
+          for (int it = 0; it < KI; ++it) tma_load_2d(sm.bring + (uint32_t)it * b_bytes, &tmB, sm.ball, it * kChunkK, 0);
+        }
+        uint32_t a = 0, aph = 0;
+        const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          int ntile, n0, y0, x0, tile_sp;
+          tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+          int kcol = 0;
+          for (int seg = 0; seg < 2; ++seg) {
+            const int chunks = seg == 0 ? p.cin_chunks : chunks2;
+            const int taps = seg == 0 ? p.taps0 : p.taps2;
+            const uint32_t abytes = (uint32_t)(seg == 0 ? p.prows0 : p.prows2) * 128u;
+            const CUtensorMap* tm = seg == 0 ? &tmA : &tmA2;
+            const int ax = x0 - (seg == 0 ? p.pad_w : p.pad2_w), ay = y0 - (seg == 0 ? p.pad_h : p.pad2_h);
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(sm.aempty0 + 8u * a, aph ^ 1u);
+              mbar_expect_tx(sm.afull0 + 8u * a, abytes);
+              tma_load_4d(sm.ring + a * (uint32_t)p.a_slot_bytes, tm, sm.afull0 + 8u * a, c * kChunkK, ax, ay, n0);
+              if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
+              if (p.b_resident) continue;
+              for (int t = 0; t < taps; ++t, kcol += kChunkK) {
+                mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
+                mbar_expect_tx(sm.full0 + 8u * s, b_bytes);
+                tma_load_2d(sm.bring + s * b_bytes, &tmB, sm.full0 + 8u * s, kcol, ntile * p.bn);
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+              }
+            }
           }
-          tma_load_2d(a_dst + kABytes, &tmB, sm.full0 + 8u * s, it * kChunkK, ntile * p.bn);
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          int ntile, n0, y0, x0, tile_sp;
+          tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+          const int bx = x0 * p.str_w - p.pad_w, by = y0 * p.str_h - p.pad_h;
+          int kcol = 0;
+          for (int seg = 0; seg < 2; ++seg) {
+            const int chunks = seg == 0 ? p.cin_chunks : (p.ki_total > p.ki0 ? p.cin2_chunks : 0);
+            const int kh = seg == 0 ? p.kh : p.taps2 / p.k2w, kw = seg == 0 ? p.kw : p.k2w;
+            for (int c = 0; c < chunks; ++c) {
+              for (int ky = 0; ky < kh; ++ky) {
+                for (int kx = 0; kx < kw; ++kx, kcol += kChunkK) {     // K order is chunk-major: (chunk, tap)
+                  mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
+                  const uint32_t a_dst = sm.ring + s * stage_bytes;
+                  mbar_expect_tx(sm.full0 + 8u * s, stage_bytes);
+                  if (seg == 0) tma_load_4d(a_dst, &tmA, sm.full0 + 8u * s, c * kChunkK, bx + kx * p.dil_w, by + ky * p.dil_h, n0);
+                  else tma_load_4d(a_dst, &tmA2, sm.full0 + 8u * s, c * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+                  tma_load_2d(a_dst + kABytes, &tmB, sm.full0 + 8u * s, kcol, ntile * p.bn);
+                  if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                }
+              }
+            }
+          }
         }
       }
     }
@@ -427,26 +484,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== MMA issuer (one thread) =====
       // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      uint32_t it_g = 0;
+      const uint32_t hi1024 = desc_hi(1024);
+      uint32_t s = 0, ph = 0, a = 0, aph = 0;
+      const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
       int j = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
         const uint32_t buf = (uint32_t)j & 1u;
         mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
-        for (int it = 0; it < KI; ++it, ++it_g) {
-          const uint32_t s = it_g % (uint32_t)p.stages;
-          const uint32_t ph = (it_g / (uint32_t)p.stages) & 1u;
-          mbar_wait(sm.full0 + 8u * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_addr = sm.ring + s * stage_bytes;
-          const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + kABytes);
-#pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k) {
-            // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+        uint32_t accum = 0;
+        if (p.halo) {
+          if (p.b_resident && j == 0) { mbar_wait(sm.ball, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+          uint32_t b_res_lo = desc_lo(sm.bring);                       // resident weights: walks the whole matrix per tile
+          for (int seg = 0; seg < 2; ++seg) {
+            const int chunks = seg == 0 ? p.cin_chunks : chunks2;
+            const int taps = seg == 0 ? p.taps0 : p.taps2;
+            const int kw = seg == 0 ? p.kw : p.k2w;
+            const int kh = taps / kw;
+            const int pw = seg == 0 ? p.pw0 : p.pw2;
+            // 8-row core groups of the M tile: contiguous rows for 1x1 (SBO 1024 B); for k > 1 the box is 8 pixels
+            // wide, one group per image row of the patch -> SBO = patch width * 128 B
+            const uint32_t a_hi = desc_hi(taps > 1 ? (uint32_t)pw * 128u : 1024u);
+            const uint32_t row_step = (uint32_t)(pw - kw) * 8u;       // (addr >> 4) units: next patch row after kw taps
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(sm.afull0 + 8u * a, aph);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              uint32_t a_lo = desc_lo(sm.ring + a * (uint32_t)p.a_slot_bytes);
+              for (int ky = 0; ky < kh; ++ky, a_lo += row_step) {
+                for (int kx = 0; kx < kw; ++kx, a_lo += 8u) {          // +128 B = next pixel of the patch row
+                  uint32_t b_lo;
+                  if (p.b_resident) {
+                    b_lo = b_res_lo;
+                    b_res_lo += b_bytes >> 4;
+                  } else {
+                    mbar_wait(sm.full0 + 8u * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    b_lo = desc_lo(sm.bring + s * b_bytes);
+                  }
+                  umma_f16_lh(d_tmem, a_lo, a_hi, b_lo, hi1024, idesc, accum);
+                  umma_f16_lh(d_tmem, a_lo + 2u, a_hi, b_lo + 2u, hi1024, idesc, 1u);
+                  umma_f16_lh(d_tmem, a_lo + 4u, a_hi, b_lo + 4u, hi1024, idesc, 1u);
+                  umma_f16_lh(d_tmem, a_lo + 6u, a_hi, b_lo + 6u, hi1024, idesc, 1u);
+                  accum = 1u;
+                  if (!p.b_resident) {
+                    umma_commit(sm.empty0 + 8u * s);
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                  }
+                }
+              }
+              umma_commit(sm.aempty0 + 8u * a);     // patch slot free once these MMAs retire
+              if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
+            }
           }
-          umma_commit(sm.empty0 + 8u * s);          // frees the smem slot when these MMAs retire
+        } else {
+          for (int it = 0; it < KI; ++it) {
+            mbar_wait(sm.full0 + 8u * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = sm.ring + s * stage_bytes;
+            const uint32_t a_lo = desc_lo(a_addr), b_lo = desc_lo(a_addr + kABytes);
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
+            umma_f16_lh(d_tmem, a_lo, hi1024, b_lo, hi1024, idesc, accum);
+            umma_f16_lh(d_tmem, a_lo + 2u, hi1024, b_lo + 2u, hi1024, idesc, 1u);
+            umma_f16_lh(d_tmem, a_lo + 4u, hi1024, b_lo + 4u, hi1024, idesc, 1u);
+            umma_f16_lh(d_tmem, a_lo + 6u, hi1024, b_lo + 6u, hi1024, idesc, 1u);
+            accum = 1u;
+            umma_commit(sm.empty0 + 8u * s);        // frees the smem slot when these MMAs retire
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+          }
         }
         umma_commit(sm.tfull0 + 8u * buf);          // accumulator of this tile complete
       }
@@ -532,19 +637,71 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   // two accumulator buffers (epilogue of tile j overlaps the main loop of tile j+1)
   p.tmem_buf_cols = bn <= 16 ? 16 : bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.tmem_buf_cols < 32 ? 32 : 2 * p.tmem_buf_cols;
-  const int stage_bytes = kABytes + bn * 128;
-  const int half_n = bn > 128 ? 128 : bn;
-  p.stage_out_bytes = ((half_n + 63) / 64) * kTileM * 128;                 // fp16 output staging: 64-channel swizzled panels
-  const int budget = 224 * 1024 - p.stage_out_bytes - 4096;
-  int stages = budget / stage_bytes;
-  if (stages > 8) stages = 8;
+  const int b_bytes = bn * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  p.pass_cols = 128;                                                       // fp16 output staging: 64-channel swizzled panels
+  p.stage_out_bytes = (((bn > 128 ? 128 : bn) + 63) / 64) * kTileM * 128;
+  int budget = 224 * 1024 - p.stage_out_bytes - 4096;
   const bool seg2 = d->x2.ptr != nullptr;
   if (seg2 && (!view_ok(&d->x2) || d->x2.n != N || d->k2h <= 0 || d->k2w <= 0 || d->stride_h != 1 || d->stride_w != 1)) return S2V_EINVAL;
-  p.ki0 = d->kh * d->kw * p.cin_chunks;
+  p.taps0 = d->kh * d->kw;
+  p.taps2 = seg2 ? d->k2h * d->k2w : 1;
+  p.ki0 = p.taps0 * p.cin_chunks;
   p.cin2_chunks = seg2 ? ceil_div(d->x2.c, kChunkK) : 1;
   p.k2w = seg2 ? d->k2w : 1; p.pad2_h = d->pad2_h; p.pad2_w = d->pad2_w;
-  p.ki_total = p.ki0 + (seg2 ? d->k2h * d->k2w * p.cin2_chunks : 0);
-  if (stages < 2) stages = 2;
+  p.ki_total = p.ki0 + (seg2 ? p.taps2 * p.cin2_chunks : 0);
+  // halo mode: stride 1, no dilation, and (1x1, any box) or (k > 1 with an 8-pixel-wide single-image box)
+  const bool unit = d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1;
+  const bool box816 = box_w == 8 && box_n == 1;
+  const bool halo_ok = unit && (p.taps0 == 1 || box816) && (!seg2 || p.taps2 == 1 || box816);
+  p.pw0 = box_w + (p.taps0 > 1 ? d->kw - 1 : 0);
+  const int ph0 = box_h + (p.taps0 > 1 ? d->kh - 1 : 0);
+  p.prows0 = p.pw0 * ph0 * box_n;
+  p.pw2 = box_w + (seg2 && p.taps2 > 1 ? d->k2w - 1 : 0);
+  const int ph2 = box_h + (seg2 && p.taps2 > 1 ? d->k2h - 1 : 0);
+  p.prows2 = seg2 ? p.pw2 * ph2 * box_n : 0;
+  const int prmax = p.prows0 > p.prows2 ? p.prows0 : p.prows2;
+  const int a_slot_bytes = (prmax * 128 + 1023) / 1024 * 1024;
+  const long long w_bytes = (long long)p.ki_total * b_bytes;
+  // weights of a single-N-tile layer stay resident in smem when they fit next to two A patches; a one-panel
+  // (64-column) staging pass is used if that is what makes them fit
+  bool resident = false;
+  if (halo_ok && ceil_div(cout, bn) == 1) {
+    if (w_bytes <= budget - 2 * a_slot_bytes) resident = true;
+    else if (bn > 64 && w_bytes <= budget + (p.stage_out_bytes - kTileM * 128) - 2 * a_slot_bytes) {
+      resident = true;
+      p.pass_cols = 64;
+      budget += p.stage_out_bytes - kTileM * 128;
+      p.stage_out_bytes = kTileM * 128;
+    }
+  }
+  // halo mode pays off when taps share a patch (k > 1) or when the weights are resident; a plain streaming
+  // 1x1 GEMM keeps the leaner one-barrier-per-iteration tap loop
+  p.halo = (halo_ok && (p.taps0 > 1 || p.taps2 > 1 || resident) && p.pw0 <= 256 && ph0 <= 256 && p.pw2 <= 256 && ph2 <= 256) ? 1 : 0;
+  int stages;
+  p.a_slots = 0; p.a_slot_bytes = 0; p.b_resident = 0;
+  if (p.halo) {
+    p.a_slot_bytes = a_slot_bytes;
+    if (resident) {
+      p.b_resident = 1;
+      p.a_slots = (int)((budget - w_bytes) / p.a_slot_bytes);
+      if (p.a_slots > 4) p.a_slots = 4;
+      stages = 1;
+      p.ring_bytes = p.a_slots * p.a_slot_bytes + (int)w_bytes;
+    } else {
+      p.a_slots = p.taps0 > 1 ? 2 : 3;
+      if (p.a_slots * p.a_slot_bytes + 2 * b_bytes > budget) p.a_slots = 2;
+      stages = (budget - p.a_slots * p.a_slot_bytes) / b_bytes;
+      if (stages > 8) stages = 8;
+      if (stages < 2) return S2V_EINVAL;
+      p.ring_bytes = p.a_slots * p.a_slot_bytes + stages * b_bytes;
+    }
+  } else {
+    stages = budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.ring_bytes = stages * stage_bytes;
+  }
   p.stages = stages;
   p.y = mk(d->y);
   p.r1 = mk(d->res1.ptr ? &d->res1 : nullptr);
@@ -567,6 +724,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     cuuint64_t gstr[3] = {(cuuint64_t)d->x.sw * 2, (cuuint64_t)d->x.sh * 2, (cuuint64_t)d->x.sn * 2};
     // strided convs: the box spans box*stride input pixels and TMA's element stride picks every stride-th one
     cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(box_w * d->stride_w), (cuuint32_t)(box_h * d->stride_h), (cuuint32_t)box_n};
+    if (p.halo) { box[1] = (cuuint32_t)p.pw0; box[2] = (cuuint32_t)ph0; }     // the patch: box + (k-1) halo
     cuuint32_t es[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
     if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -587,7 +745,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (seg2) {
     cuuint64_t gdim[4] = {(cuuint64_t)d->x2.c, (cuuint64_t)d->x2.w, (cuuint64_t)d->x2.h, (cuuint64_t)d->x2.n};
     cuuint64_t gstr[3] = {(cuuint64_t)d->x2.sw * 2, (cuuint64_t)d->x2.sh * 2, (cuuint64_t)d->x2.sn * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(p.halo ? p.pw2 : box_w), (cuuint32_t)(p.halo ? ph2 : box_h), (cuuint32_t)box_n};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x2.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -604,9 +762,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       p.use_tma_store = 0;                  // e.g. a stride the encoder rejects: fall back to the manual coalesced stores
   }
-  p.ring_bytes = stages * stage_bytes;
   // ring | output staging tile | barriers + tmem ptr | scale/bias tables | row-valid mask
-  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 64 + 2 * 256 * sizeof(float) + 128 + 1024;
+  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 2 * 256 * sizeof(float) + 128 + 1024;
   if (smem > 227 * 1024) return S2V_EINVAL;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);

@@ -200,7 +200,7 @@ class LNetEngine(EngineBase):
                         p = f"decoder.res{i}.res{b}.{cv}"
                         q = p + ".ffc"
                         inter = src[:, 1:-1, 1:-1, :]
-                        gm = max(ops.stats_groups(lib, cl, S, S), ops.stats_groups(lib, cg, S, S)) if self.impl == "tc" else 1
+                        gm = max(ops.stats_groups(lib, cl, S, S, (3, 3)), ops.stats_groups(lib, cg, S, S, (3, 3))) if self.impl == "tc" else 1
                         st = self.conv_stats(plan, ws, q + ".to_l", src, R[..., :cl], tag=p, c_total=c, gmax=gm)   # l2l + g2l, 3x3 reflect
                         if self.impl != "tc":
                             self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])        # l2g, 3x3 reflect

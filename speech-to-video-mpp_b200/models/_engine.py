@@ -124,8 +124,9 @@ class EngineBase:
             self.conv(plan, name, x, y, **kw)
             return None
         n, h, w, c = y.shape
-        tiles = ops.box_tiles(h, w, n)
-        g = ops.stats_groups(self.lib, c, h, w)
+        k = kw.get("k", self.W[name]["k"])
+        tiles = ops.box_tiles(h, w, n, k)
+        g = ops.stats_groups(self.lib, c, h, w, k)
         gmax = max(g, gmax or 1)
         partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * gmax * phases, c_total or c, 2), torch.float32, zero=True)
         self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles * gmax, g, gmax), **kw)

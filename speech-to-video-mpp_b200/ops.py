@@ -70,6 +70,16 @@ class Plan:
         return len(self.ops)
 
 
+def conv_box(h: int, w: int, k=(1, 1), stride=(1, 1), dil=(1, 1)) -> tuple[int, int, int]:
+    """Box for a conv_tc launch.  k > 1 unit-stride convs prefer the 8 x 16 single-image box: it enables the
+    kernel's halo mode (one A patch per channel chunk serves every tap) unless it wastes > 34 % of the tile."""
+    if k[0] * k[1] > 1 and tuple(stride) == (1, 1) and tuple(dil) == (1, 1):
+        tiles = -(-w // 8) * -(-h // 16)
+        if tiles * 128 / float(h * w) <= 1.34:
+            return (8, 16, 1)
+    return choose_box(h, w, 1)
+
+
 def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
     """Box of 128 output pixels (box_w, box_h, box_n) with the least padding waste.  The choice is a
     function of the image size ONLY (evaluated for a large batch): the spatial tiling also defines the
@@ -141,7 +151,7 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
         op = Op(name + "[simt]", lib.s2v_conv_simt, (C.byref(d),), keep)
     else:
         if box is None:
-            box = choose_box(d.y.h, d.y.w, d.y.n)
+            box = conv_box(d.y.h, d.y.w, k, stride, dil)
         op = Op(name + "[tc]", lib.s2v_conv_tc, (C.byref(d), box[0], box[1], box[2]), keep)
     # algorithmic FLOPs of the reference op this launch replaces (2*MACs on true channel counts);
     # alg_scale lets the sub-pixel phases of nearest-x2 + conv3x3 report the reference's 3x3 work
@@ -151,16 +161,16 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     return op
 
 
-def box_tiles(h: int, w: int, n: int) -> int:
+def box_tiles(h: int, w: int, n: int, k=(1, 1)) -> int:
     """Spatial tiles per image of a conv_tc launch with the default box (= statistics chunks it emits)."""
-    bw, bh, _ = choose_box(h, w, n)
+    bw, bh, _ = conv_box(h, w, k)
     return -(-w // bw) * -(-h // bh)
 
 
-def stats_groups(lib, cout: int, h: int, w: int) -> int:
+def stats_groups(lib, cout: int, h: int, w: int, k=(1, 1)) -> int:
     """Row groups the conv_tc epilogue splits a tile into for the fused statistics (see include/s2v.h)."""
     bn = lib.s2v_conv_tc_tile_n(cout)
-    bw, bh, _ = choose_box(h, w, 1)
+    bw, bh, _ = conv_box(h, w, k)
     g = 1
     while g * 2 <= 8 and g * 2 * ((bn + 1) // 2) <= 128 and g * 2 <= bw * bh:
         g *= 2
@@ -275,12 +285,14 @@ def op_flow_warp(lib, src, flow, out, out16=None, c_off=0) -> Op:
 
 
 def pack_w_tc(w: torch.Tensor) -> torch.Tensor:
-    """[Cout,Cin,kh,kw] float -> fp16 [Cout][kh*kw][Cin64] (K-major, zero-filled channel pad)."""
+    """[Cout,Cin,kh,kw] float -> fp16 [Cout][Cin64/64][kh*kw][64]: K-major, CHUNK-major (all taps of a
+    64-channel chunk are adjacent, so one A patch serves them), zero-filled channel pad."""
     co, ci, kh, kw = w.shape
     ci64 = -(-ci // 64) * 64
     co8 = -(-co // 8) * 8                       # rows padded to 8 (Cout = 3 heads)
     out = torch.zeros(co8, kh * kw, ci64, dtype=torch.float16, device=w.device)
     out[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16)
+    out = out.reshape(co8, kh * kw, ci64 // 64, 64).permute(0, 2, 1, 3)
     return out.reshape(co8, kh * kw * ci64).contiguous()
 
 

@@ -199,7 +199,7 @@ def test_fused_epilogue_statistics(G):
         x = torch.randn(n, s, s, cin, device="cuda").half()
         wt = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
         y = torch.zeros(n, s, s, cout, dtype=torch.float16, device="cuda")
-        tiles, g = ops.box_tiles(s, s, n), ops.stats_groups(lib, cout, s, s)
+        tiles, g = ops.box_tiles(s, s, n, (3, 3)), ops.stats_groups(lib, cout, s, s, (3, 3))
         partial = torch.zeros(n, tiles * g, cout, 2, device="cuda")
         ops.op_conv(lib, x, ops.pack_w_tc(wt), y, k=(3, 3), pad=(1, 1), stats=(partial, 0, 0, g, g)).run()
         torch.cuda.synchronize()

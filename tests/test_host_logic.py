@@ -71,7 +71,10 @@ def test_weight_packing_layouts():
     w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
     p = ops.pack_w_tc(w)
     assert p.shape == (8, 9 * 64) and p.dtype == torch.float16 and (p[2:] == 0).all()
-    assert p[1, 4 * 64 + 2].item() == w[1, 2, 1, 1].item() and p[1, 4 * 64 + 3].item() == 0
+    assert p[1, 4 * 64 + 2].item() == w[1, 2, 1, 1].item() and p[1, 4 * 64 + 3].item() == 0     # one chunk: [tap][64]
+    w2 = torch.randn(8, 128, 3, 3)
+    p2 = ops.pack_w_tc(w2)                          # chunk-major: [cout][chunk][tap][64]
+    assert p2.shape == (8, 2 * 9 * 64) and p2[3, (1 * 9 + 5) * 64 + 7].item() == w2[3, 64 + 7, 1, 2].half().item()
     s = ops.pack_w_simt(w, 8)
     assert s.shape == (9, 8, 4) and s[5, 1, 1].item() == w[1, 1, 1, 2].item()
 
