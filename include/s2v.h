@@ -220,6 +220,12 @@ int s2v_adain_finalize(const float* partial, int N, int chunks, int C, int64_t c
  * y (y must be the interior view of a buffer padded by 1).                      */
 int s2v_affine_act(const s2v_view* x, const float* a, const float* b, int act, float act_param,
                    int pool2, const s2v_view* res, const s2v_view* y, int reflect1, void* stream);
+/* Single-pass InstanceNorm2d + AdaIN + activation [+res] [reflect border] for maps whose (image, channel group)
+ * slab fits in shared memory (s2v_adain_fused_fits > 0): one read of x instead of chan_stats + adain_finalize
+ * + affine_act.  Same arithmetic and the same fixed reduction order for every batch size.                     */
+int s2v_adain_fused_fits(int h, int w, int c);
+int s2v_adain_fused(const s2v_view* x, const float* gamma, const float* beta, int64_t gb_stride, float eps,
+                    int act, float act_param, const s2v_view* res, const s2v_view* y, int reflect1, void* stream);
 /* nn.LayerNorm(C) over the channel dim of every pixel/token (transformer.py:27,35) */
 int s2v_token_layernorm(const s2v_view* x, const float* gamma, const float* beta, float eps,
                         const s2v_view* y, void* stream);

@@ -23,13 +23,26 @@ __global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pg < PG) {
-#pragma unroll 4
-    for (int p = p0 + pg; p < p1; p += PG) {
-      const int yy = p / x.w, xx = p - yy * x.w;
-      float f[8];
-      h8_to_f(ld_h8(x.p + n * x.sn + yy * x.sh + xx * x.sw + c8 * 8), f);
+    // 4 independent 16-byte loads in flight per thread (addresses computed first, then loads, then math)
+    for (int p = p0 + pg; p < p1; p += 4 * PG) {
+      H8 v[4];
+      bool ok[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      for (int u = 0; u < 4; ++u) {
+        const int pu = p + u * PG;
+        ok[u] = pu < p1;
+        const int pc = ok[u] ? pu : p;
+        const int yy = pc / x.w, xx = pc - yy * x.w;
+        v[u] = ld_h8(x.p + n * x.sn + yy * x.sh + xx * x.sw + c8 * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float f[8];
+        h8_to_f(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
     }
     float* o = sm + ((size_t)pg * x.c + c8 * 8) * 2;
 #pragma unroll
@@ -123,43 +136,50 @@ __device__ __forceinline__ void load_ab(const float* __restrict__ a, const float
   bv[0] = u0.x; bv[1] = u0.y; bv[2] = u0.z; bv[3] = u0.w; bv[4] = u1.x; bv[5] = u1.y; bv[6] = u1.z; bv[7] = u1.w;
 }
 
-template <int POOL>
+template <int ACT>
+__device__ __forceinline__ float act_c(float v, float ap) {
+  if (ACT == S2V_ACT_LRELU) return v > 0.f ? v : v * ap;
+  if (ACT == S2V_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == S2V_ACT_NONE) return v;
+  return v;
+}
+
+// grid (ceil(W*C8/256), ceil(H/2), N): thread = (ox, c8) of output rows oy and oy + ceil(H/2) of image n.
+// Both rows share the per-(n,c) affine; all loads of both rows are issued before any math.
+template <int POOL, int ACT>
 __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
-                                                         const float* __restrict__ b, int act, float ap, View res,
-                                                         View y, int reflect1) {
+                                                         const float* __restrict__ b, float ap, View res, View y,
+                                                         int reflect1) {
   constexpr int U = 2;
   const int C8 = x.c >> 3;
-  const long long total = (long long)y.n * y.h * y.w * C8;
-  const long long half = (total + U - 1) / U;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= half) return;
-  int n[U], oy[U], ox[U], c8[U];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= y.w * C8) return;
+  const int ox = idx / C8, c8 = idx - ox * C8;
+  const int n = blockIdx.z;
+  const int hh = (y.h + 1) >> 1;
+  int oy[U];
   bool ok[U];
+  oy[0] = blockIdx.y; oy[1] = blockIdx.y + hh;
+  ok[0] = true; ok[1] = oy[1] < y.h;
   H8 xin[U][POOL ? 4 : 1], rin[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const long long idx = i0 + u * half;
-    ok[u] = idx < total;
-    long long r = ok[u] ? idx : 0;
-    c8[u] = (int)(r % C8); r /= C8;
-    ox[u] = (int)(r % y.w); r /= y.w;
-    oy[u] = (int)(r % y.h);
-    n[u] = (int)(r / y.h);
     if (!ok[u]) continue;
     if (POOL) {
 #pragma unroll
       for (int d = 0; d < 4; ++d)
-        xin[u][d] = ld_h8(x.p + n[u] * x.sn + (2 * oy[u] + (d >> 1)) * x.sh + (2 * ox[u] + (d & 1)) * x.sw + c8[u] * 8);
+        xin[u][d] = ld_h8(x.p + n * x.sn + (2 * oy[u] + (d >> 1)) * x.sh + (2 * ox + (d & 1)) * x.sw + c8 * 8);
     } else {
-      xin[u][0] = ld_h8(x.p + n[u] * x.sn + oy[u] * x.sh + ox[u] * x.sw + c8[u] * 8);
+      xin[u][0] = ld_h8(x.p + n * x.sn + oy[u] * x.sh + ox * x.sw + c8 * 8);
     }
-    if (res.p) rin[u] = ld_h8(res.p + n[u] * res.sn + oy[u] * res.sh + ox[u] * res.sw + c8[u] * 8);
+    if (res.p) rin[u] = ld_h8(res.p + n * res.sn + oy[u] * res.sh + ox * res.sw + c8 * 8);
   }
+  float av[8], bv[8];
+  load_ab(a, b, n, x.c, c8, av, bv);
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (!ok[u]) continue;
-    float av[8], bv[8], o[8];
-    load_ab(a, b, n[u], x.c, c8[u], av, bv);
+    float o[8];
     if (POOL) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -168,7 +188,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
         float f[8];
         h8_to_f(xin[u][d], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+        for (int i = 0; i < 8; ++i) o[i] += act_c<ACT>(fmaf(f[i], av[i], bv[i]), ap);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] *= 0.25f;
@@ -176,7 +196,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
       float f[8];
       h8_to_f(xin[u][0], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = act_apply(fmaf(f[i], av[i], bv[i]), act, ap);
+      for (int i = 0; i < 8; ++i) o[i] = act_c<ACT>(fmaf(f[i], av[i], bv[i]), ap);
     }
     if (res.p) {
       float f[8];
@@ -184,7 +204,118 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += f[i];
     }
-    affine_store(y, n[u], oy[u], ox[u], c8[u], o, reflect1);
+    affine_store(y, n, oy[u], ox, c8, o, reflect1);
+  }
+}
+
+// Single-pass InstanceNorm + AdaIN + activation (+res, +reflect border) for feature maps whose (image, channel
+// group) slab fits in shared memory: one block = image n x CG channels.  The slab is read ONCE from HBM/L2 into
+// smem while per-thread partial sums are accumulated; the per-channel reduction runs in a fixed order
+// (deterministic); the normalised result is written straight from smem.  Replaces chan_stats + adain_finalize +
+// affine_act (three launches, two reads of x) for the FFC levels of LNet.
+constexpr int kFusedThreads = 256;
+
+template <int CG, int ACT>
+__global__ void __launch_bounds__(kFusedThreads) adain_fused_kernel(View x, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, long long gb_stride,
+                                                                    float eps, float ap, View res, View y, int reflect1) {
+  constexpr int G8 = CG / 8;              // 16-byte vectors per pixel in this channel group
+  constexpr int PL = kFusedThreads / G8;  // pixel lanes
+  constexpr int NW = kFusedThreads / 32;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int HW = x.h * x.w;
+  H8* slab = reinterpret_cast<H8*>(smraw);                          // [HW][G8]
+  float* red = reinterpret_cast<float*>(smraw + (size_t)HW * G8 * 16);   // [NW][CG][2]
+  float* ab = red + NW * CG * 2;                                    // [CG][2]
+  const int n = blockIdx.y, c0 = blockIdx.x * CG;
+  const int v = threadIdx.x % G8, pl = threadIdx.x / G8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const __half* xb = x.p + n * x.sn + c0 + v * 8;
+  for (int p = pl; p < HW; p += 2 * PL) {
+    H8 t[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int pu = p + u * PL;
+      ok[u] = pu < HW;
+      const int pc = ok[u] ? pu : p;
+      const int yy = pc / x.w, xx = pc - yy * x.w;
+      t[u] = ld_h8(xb + yy * x.sh + xx * x.sw);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      slab[(size_t)(p + u * PL) * G8 + v] = t[u];
+      float f[8];
+      h8_to_f(t[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+  }
+  // fixed-order reduction: across the pixel lanes of a warp (xor shuffles), then across warps through smem
+#pragma unroll
+  for (int off = G8; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+      q[i] += __shfl_xor_sync(0xffffffffu, q[i], off);
+    }
+  }
+  if (lane < G8) {
+    float* o = red + ((size_t)warp * CG + v * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[2 * i] = s[i]; o[2 * i + 1] = q[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < CG) {
+    const int c = threadIdx.x;
+    double sd = 0.0, qd = 0.0;
+    for (int g = 0; g < NW; ++g) { sd += (double)red[((size_t)g * CG + c) * 2]; qd += (double)red[((size_t)g * CG + c) * 2 + 1]; }
+    const double mean = sd / (double)HW;
+    double var = qd / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[(size_t)n * gb_stride + c0 + c] : 0.f;
+    const float be = beta ? beta[(size_t)n * gb_stride + c0 + c] : 0.f;
+    const float av = rstd * (1.f + g);
+    ab[2 * c] = av;
+    ab[2 * c + 1] = be - (float)mean * av;
+  }
+  __syncthreads();
+  float av[8], bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { av[i] = ab[2 * (v * 8 + i)]; bv[i] = ab[2 * (v * 8 + i) + 1]; }
+  const int c8g = (c0 >> 3) + v;           // vector index within the full channel dim
+  for (int p = pl; p < HW; p += 2 * PL) {
+    H8 r[2];
+    bool ok[2];
+    int yy[2], xx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int pu = p + u * PL;
+      ok[u] = pu < HW;
+      const int pc = ok[u] ? pu : p;
+      yy[u] = pc / x.w; xx[u] = pc - yy[u] * x.w;
+      if (res.p && ok[u]) r[u] = ld_h8(res.p + n * res.sn + yy[u] * res.sh + xx[u] * res.sw + c0 + v * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      float f[8], o[8];
+      h8_to_f(slab[(size_t)(p + u * PL) * G8 + v], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = act_c<ACT>(fmaf(f[i], av[i], bv[i]), ap);
+      if (res.p) {
+        float g[8];
+        h8_to_f(r[u], g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += g[i];
+      }
+      affine_store(y, n, yy[u], xx[u], c8g, o, reflect1);
+    }
   }
 }
 
@@ -334,14 +465,65 @@ extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b,
   if (pool2 ? (x->h != 2 * y->h || x->w != 2 * y->w) : (x->h != y->h || x->w != y->w)) return S2V_EINVAL;
   if (res && res->ptr && (!view_ok(res) || res->c != y->c || res->h != y->h || res->w != y->w || res->n != y->n)) return S2V_EINVAL;
   if (reflect1 && (y->h < 4 || y->w < 4)) return S2V_EINVAL;
-  const long long total = (long long)y->n * y->h * y->w * (y->c >> 3);
-  const int blocks = ceil_div((total + 1) / 2, 256);
-  if (pool2)
-    affine_act_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param,
-                                                                  mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
-  else
-    affine_act_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(mk(x), a, b, act, act_param,
-                                                                  mk(res && res->ptr ? res : nullptr), mk(y), reflect1);
+  if (act != S2V_ACT_NONE && act != S2V_ACT_LRELU && act != S2V_ACT_RELU) return S2V_EINVAL;
+  if (y->n > 65535 || (y->h + 1) / 2 > 65535) return S2V_EINVAL;
+  const dim3 grid(ceil_div((long long)y->w * (y->c >> 3), 256), (y->h + 1) / 2, y->n);
+  const View vx = mk(x), vr = mk(res && res->ptr ? res : nullptr), vy = mk(y);
+  cudaStream_t st = (cudaStream_t)stream;
+#define S2V_AFFINE(P, A) affine_act_kernel<P, A><<<grid, 256, 0, st>>>(vx, a, b, act_param, vr, vy, reflect1)
+  if (pool2) {
+    if (act == S2V_ACT_LRELU) S2V_AFFINE(1, S2V_ACT_LRELU);
+    else if (act == S2V_ACT_RELU) S2V_AFFINE(1, S2V_ACT_RELU);
+    else S2V_AFFINE(1, S2V_ACT_NONE);
+  } else {
+    if (act == S2V_ACT_LRELU) S2V_AFFINE(0, S2V_ACT_LRELU);
+    else if (act == S2V_ACT_RELU) S2V_AFFINE(0, S2V_ACT_RELU);
+    else S2V_AFFINE(0, S2V_ACT_NONE);
+  }
+#undef S2V_AFFINE
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+static size_t adain_fused_smem(int hw, int cg) { return (size_t)hw * (cg / 8) * 16 + (size_t)(kFusedThreads / 32) * cg * 2 * sizeof(float) + cg * 2 * sizeof(float); }
+
+extern "C" int s2v_adain_fused_fits(int h, int w, int c) {
+  const int hw = h * w;
+  if (c % 64 == 0 && adain_fused_smem(hw, 64) <= 100 * 1024) return 64;
+  if (c % 16 == 0 && adain_fused_smem(hw, 16) <= 100 * 1024) return 16;
+  return 0;
+}
+
+extern "C" int s2v_adain_fused(const s2v_view* x, const float* gamma, const float* beta, int64_t gb_stride, float eps,
+                               int act, float act_param, const s2v_view* res, const s2v_view* y, int reflect1,
+                               void* stream) {
+  if (!view_ok(x) || !view_ok(y)) return S2V_EINVAL;
+  if (y->c != x->c || y->n != x->n || y->h != x->h || y->w != x->w || x->n > 65535) return S2V_EINVAL;
+  if (res && res->ptr && (!view_ok(res) || res->c != y->c || res->h != y->h || res->w != y->w || res->n != y->n)) return S2V_EINVAL;
+  if (reflect1 && (y->h < 4 || y->w < 4)) return S2V_EINVAL;
+  if (act != S2V_ACT_NONE && act != S2V_ACT_LRELU && act != S2V_ACT_RELU) return S2V_EINVAL;
+  const int cg = s2v_adain_fused_fits(x->h, x->w, x->c);
+  if (!cg) return S2V_EINVAL;
+  const size_t smem = adain_fused_smem(x->h * x->w, cg);
+  const View vx = mk(x), vr = mk(res && res->ptr ? res : nullptr), vy = mk(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(x->c / cg, x->n);
+#define S2V_FUSED(CGV, A)                                                                                          \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) { cudaFuncSetAttribute(adain_fused_kernel<CGV, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    adain_fused_kernel<CGV, A><<<grid, kFusedThreads, smem, st>>>(vx, gamma, beta, gb_stride, eps, act_param, vr, vy, reflect1); \
+  } while (0)
+  if (cg == 64) {
+    if (act == S2V_ACT_LRELU) S2V_FUSED(64, S2V_ACT_LRELU);
+    else if (act == S2V_ACT_RELU) S2V_FUSED(64, S2V_ACT_RELU);
+    else S2V_FUSED(64, S2V_ACT_NONE);
+  } else {
+    if (act == S2V_ACT_LRELU) S2V_FUSED(16, S2V_ACT_LRELU);
+    else if (act == S2V_ACT_RELU) S2V_FUSED(16, S2V_ACT_RELU);
+    else S2V_FUSED(16, S2V_ACT_NONE);
+  }
+#undef S2V_FUSED
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

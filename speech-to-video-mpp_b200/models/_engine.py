@@ -161,6 +161,11 @@ class EngineBase:
         """InstanceNorm2d*(1+gamma)+beta + activation [+ res] (base_blocks.py:127-157).
         ``stats``: reuse the (partial, chunks) of an earlier call on the same x (two AdaINs of one tensor)."""
         n, h, w, c = x.shape
+        if stats is None and act in (L.ACT_NONE, L.ACT_LRELU, L.ACT_RELU) and self.lib.s2v_adain_fused_fits(h, w, c) > 0 \
+                and os.environ.get("S2V_ADAIN_FUSED", "0") == "1":
+            plan.add(ops.op_adain_fused(self.lib, x, gamma, beta, gb_stride, y, act=act, act_param=slope, res=res,
+                                        reflect1=reflect1))
+            return None
         if stats is None:
             partial, chunks, a, b = self._stats(plan, ws, tag, x)
         else:

@@ -181,7 +181,7 @@ def stats_chunks(n: int, hw: int) -> int:
     """Pixel chunks per image for chan_stats.  A function of the image size ONLY: the reduction
     tree must not depend on the batch size, so that a frame's result is bit-identical whichever
     batch / GPU shard it is computed in."""
-    return max(1, min(hw // 36, 64))
+    return max(1, min(hw // 24, 64))
 
 
 def op_chan_stats(lib, x, chunks, partial) -> Op:
@@ -207,6 +207,14 @@ def op_affine_act(lib, x, a, b, y, *, act=L.ACT_NONE, act_param=0.0, pool2=0, re
     return Op("affine_act", lib.s2v_affine_act,
               (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), pool2, C.byref(vr), C.byref(vy), reflect1),
               (vx, vy, vr, x, y, res, a, b))
+
+
+def op_adain_fused(lib, x, gamma, beta, gb_stride, y, *, act=L.ACT_NONE, act_param=0.0, res=None, reflect1=0, eps=1e-5) -> Op:
+    vx, vy = view(x), view(y)
+    vr = view(res) if res is not None else null_view()
+    return Op("adain_fused", lib.s2v_adain_fused,
+              (C.byref(vx), _ptr(gamma), _ptr(beta), gb_stride, eps, act, float(act_param), C.byref(vr), C.byref(vy), reflect1),
+              (vx, vy, vr, x, y, res, gamma, beta))
 
 
 def op_token_ln(lib, x, gamma, beta, y, eps=1e-5) -> Op:

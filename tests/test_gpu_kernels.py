@@ -224,6 +224,26 @@ def test_adain_reflect(G, n, c, h, w):
     assert torch.equal(yp2, yp)
 
 
+@pytest.mark.parametrize("n,c,h,w,res", [(3, 1024, 12, 12, True), (2, 256, 24, 24, False), (2, 128, 48, 48, True), (2, 64, 20, 20, True)])
+def test_adain_fused_single_pass(G, n, c, h, w, res):
+    lib, L = G.lib(), G.L
+    x, xh = _norm_inputs(n, c, h, w)
+    xf = xh.permute(0, 3, 1, 2).float()
+    gb = torch.randn(n, 2 * c + 3, device="cuda") * 0.3
+    gamma, beta = gb[:, :c], gb[:, c:2 * c]
+    ref = F.leaky_relu(F.instance_norm(xf, eps=1e-5) * (1 + gamma[:, :, None, None]) + beta[:, :, None, None], 0.01)
+    r = torch.randn(n, h, w, c, device="cuda").half() if res else None
+    if res:
+        ref = ref + r.permute(0, 3, 1, 2).float()
+    refp = F.pad(ref, (1, 1, 1, 1), mode="reflect")
+    assert lib.s2v_adain_fused_fits(h, w, c) > 0
+    yp = torch.zeros(n, h + 2, w + 2, c, dtype=torch.float16, device="cuda")
+    G.ops.op_adain_fused(lib, xh, gamma, beta, gb.stride(0), yp[:, 1:-1, 1:-1, :], act=L.ACT_LRELU, act_param=0.01, res=r, reflect1=1).run()
+    m, rel = G.report("adain fused n%d c%d %dx%d" % (n, c, h, w), G.nchw(yp), refp)
+    assert rel < 2e-3
+    assert lib.s2v_adain_fused_fits(256, 256, 32) == 0
+
+
 def test_token_layernorm_add_mean(G):
     lib = G.lib()
     torch.manual_seed(3)
