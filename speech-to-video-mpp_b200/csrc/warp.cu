@@ -20,65 +20,124 @@ __device__ __forceinline__ float2 deform_at(const float* __restrict__ fx, const 
   return make_float2(dx, dy);
 }
 
+// grid_sample, bilinear, zeros padding, align_corners=False.  Branch-free: neighbour coordinates are clamped and
+// the weights of out-of-range neighbours zeroed, so the 4*C gathers are issued back to back (ILP) before any FMA.
+template <int CMAX>
 __device__ __forceinline__ void sample_store(const float* __restrict__ src, float* __restrict__ out, int C, int H,
                                              int W, int Y, int X, float gx, float gy, __half* out16) {
-  // grid_sample, bilinear, zeros padding, align_corners=False
   float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), -1.f), 0.5f);
   float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), -1.f), 0.5f);
-  float fx0 = floorf(ix), fy0 = floorf(iy);
-  float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-  // guard against huge/NaN coordinates before the int conversion
-  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
-  int x0 = finite ? (int)fx0 : -10, y0 = finite ? (int)fy0 : -10;
-  int x1 = x0 + 1, y1 = y0 + 1;
-  bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
-  bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
-  float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+  // keep the float -> int conversion defined for huge / NaN coordinates (they sample nothing)
+  ix = (fabsf(ix) < 1e9f) ? ix : -10.f;
+  iy = (fabsf(iy) < 1e9f) ? iy : -10.f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+  const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+  const float w00 = (vy0 & vx0) ? wx0 * wy0 : 0.f, w01 = (vy0 & vx1) ? wx1 * wy0 : 0.f;
+  const float w10 = (vy1 & vx0) ? wx0 * wy1 : 0.f, w11 = (vy1 & vx1) ? wx1 * wy1 : 0.f;
+  const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+  const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  const int o00 = cy0 * W + cx0, o01 = cy0 * W + cx1, o10 = cy1 * W + cx0, o11 = cy1 * W + cx1;
   const size_t plane = (size_t)H * W;
-  for (int c = 0; c < C; ++c) {
-    const float* s = src + c * plane;
-    float v = 0.f;
-    if (vy0 && vx0) v += s[y0 * W + x0] * w00;
-    if (vy0 && vx1) v += s[y0 * W + x1] * w01;
-    if (vy1 && vx0) v += s[y1 * W + x0] * w10;
-    if (vy1 && vx1) v += s[y1 * W + x1] * w11;
-    out[c * plane + (size_t)Y * W + X] = v;
-    if (out16) out16[c] = __float2half_rn(v);
+  const size_t po = (size_t)Y * W + X;
+  if (C <= CMAX) {
+    float v[CMAX][4];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        const float* sp = src + c * plane;
+        v[c][0] = __ldg(sp + o00); v[c][1] = __ldg(sp + o01); v[c][2] = __ldg(sp + o10); v[c][3] = __ldg(sp + o11);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        // same accumulation order as the reference kernel: nw, ne, sw, se
+        float r = v[c][0] * w00;
+        r += v[c][1] * w01;
+        r += v[c][2] * w10;
+        r += v[c][3] * w11;
+        out[c * plane + po] = r;
+        if (out16) out16[c] = __float2half_rn(r);
+      }
+    }
+  } else {
+    for (int c = 0; c < C; ++c) {
+      const float* sp = src + c * plane;
+      float r = __ldg(sp + o00) * w00;
+      r += __ldg(sp + o01) * w01;
+      r += __ldg(sp + o10) * w10;
+      r += __ldg(sp + o11) * w11;
+      out[c * plane + po] = r;
+      if (out16) out16[c] = __float2half_rn(r);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) flow_warp_kernel(const float* __restrict__ src, const float* __restrict__ flow,
-                                                        float* __restrict__ out, int C, int H, int W, int h, int w,
-                                                        View o16, int c_off) {
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Y = blockIdx.y;
+constexpr int kWarpBX = 32, kWarpBY = 8;
+
+// block = 32 x 8 output pixels; the deformation values of the flow cells under the tile are computed once into
+// shared memory (every 4x4 pixels share their 4 corner cells when the flow is 4x coarser than the image).
+__global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) flow_warp_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                                       float* __restrict__ out, int C, int H, int W, int h, int w,
+                                                                       View o16, int c_off) {
+  constexpr int kMaxCells = 36 * 12;            // smem cell tile capacity (falls back to direct loads beyond it)
+  __shared__ float2 s_def[kMaxCells];
+  const int X = blockIdx.x * kWarpBX + threadIdx.x;
+  const int Y = blockIdx.y * kWarpBY + threadIdx.y;
   const int b = blockIdx.z;
-  if (X >= W) return;
   const float* fx = flow + (size_t)b * 2 * h * w;
   const float* fy = fx + (size_t)h * w;
   const float inv_wm1 = 1.f / (float)(w - 1), inv_hm1 = 1.f / (float)(h - 1);
+  const bool same = (h == H && w == W);
+  // flow-cell rectangle touched by this tile (bilinear resize of the grid reads cells floor(s) and floor(s)+1)
+  const float sch = (float)h / (float)H, scw = (float)w / (float)W;
+  int cy_lo = 0, cx_lo = 0, ncx = 0, ncy = 0;
+  bool tiled = false;
+  if (!same) {
+    const int ty0 = blockIdx.y * kWarpBY, tx0 = blockIdx.x * kWarpBX;
+    cy_lo = min((int)fmaxf(sch * ((float)ty0 + 0.5f) - 0.5f, 0.f), h - 1);
+    cx_lo = min((int)fmaxf(scw * ((float)tx0 + 0.5f) - 0.5f, 0.f), w - 1);
+    const int cy_hi = min((int)fmaxf(sch * ((float)min(ty0 + kWarpBY, H) - 0.5f) - 0.5f, 0.f) + 1, h - 1);
+    const int cx_hi = min((int)fmaxf(scw * ((float)min(tx0 + kWarpBX, W) - 0.5f) - 0.5f, 0.f) + 1, w - 1);
+    ncx = cx_hi - cx_lo + 1; ncy = cy_hi - cy_lo + 1;
+    tiled = ncx * ncy <= kMaxCells;
+    if (tiled) {
+      for (int i = threadIdx.y * kWarpBX + threadIdx.x; i < ncx * ncy; i += kWarpBX * kWarpBY) {
+        const int ci = i / ncx, cj = i - ci * ncx;
+        s_def[i] = deform_at(fx, fy, cy_lo + ci, cx_lo + cj, w, inv_wm1, inv_hm1);
+      }
+    }
+    __syncthreads();
+  }
+  if (X >= W || Y >= H) return;
   float gx, gy;
-  if (h == H && w == W) {
+  if (same) {
     float2 d = deform_at(fx, fy, Y, X, w, inv_wm1, inv_hm1);
     gx = d.x; gy = d.y;
   } else {
     // F.interpolate(mode='bilinear', align_corners=False) of the deformation grid
-    const float sch = (float)h / (float)H, scw = (float)w / (float)W;
     float sy = fmaxf(sch * ((float)Y + 0.5f) - 0.5f, 0.f);
     float sx = fmaxf(scw * ((float)X + 0.5f) - 0.5f, 0.f);
     int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
     int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
     float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f);
     float hy = 1.f - ly, hx = 1.f - lx;
-    float2 d00 = deform_at(fx, fy, y0, x0, w, inv_wm1, inv_hm1);
-    float2 d01 = deform_at(fx, fy, y0, x1, w, inv_wm1, inv_hm1);
-    float2 d10 = deform_at(fx, fy, y1, x0, w, inv_wm1, inv_hm1);
-    float2 d11 = deform_at(fx, fy, y1, x1, w, inv_wm1, inv_hm1);
+    float2 d00, d01, d10, d11;
+    if (tiled) {
+      d00 = s_def[(y0 - cy_lo) * ncx + (x0 - cx_lo)]; d01 = s_def[(y0 - cy_lo) * ncx + (x1 - cx_lo)];
+      d10 = s_def[(y1 - cy_lo) * ncx + (x0 - cx_lo)]; d11 = s_def[(y1 - cy_lo) * ncx + (x1 - cx_lo)];
+    } else {
+      d00 = deform_at(fx, fy, y0, x0, w, inv_wm1, inv_hm1); d01 = deform_at(fx, fy, y0, x1, w, inv_wm1, inv_hm1);
+      d10 = deform_at(fx, fy, y1, x0, w, inv_wm1, inv_hm1); d11 = deform_at(fx, fy, y1, x1, w, inv_wm1, inv_hm1);
+    }
     gx = hy * (hx * d00.x + lx * d01.x) + ly * (hx * d10.x + lx * d11.x);
     gy = hy * (hx * d00.y + lx * d01.y) + ly * (hx * d10.y + lx * d11.y);
   }
   __half* p16 = o16.p ? o16.p + (size_t)b * o16.sn + (size_t)Y * o16.sh + (size_t)X * o16.sw + c_off : nullptr;
-  sample_store(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, p16);
+  sample_store<4>(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, p16);
 }
 
 __global__ void flow_to_deformation_kernel(const float* __restrict__ flow, float* __restrict__ def, int h, int w) {
@@ -111,7 +170,7 @@ __global__ void __launch_bounds__(256) warp_deformation_kernel(const float* __re
     gx = hy * (hx * d00.x + lx * d01.x) + ly * (hx * d10.x + lx * d11.x);
     gy = hy * (hx * d00.y + lx * d01.y) + ly * (hx * d10.y + lx * d11.y);
   }
-  sample_store(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, nullptr);
+  sample_store<4>(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, nullptr);
 }
 
 }  // namespace s2v
@@ -125,8 +184,8 @@ extern "C" int s2v_flow_warp_f32(const float* src, const float* flow, float* out
   if (B > 65535 || H > 65535) return S2V_EINVAL;
   View o16 = mk(out16);
   if (out16 && out16->ptr && (out16->n < B || out16->h != H || out16->w != W || c_off + C > out16->c)) return S2V_EINVAL;
-  dim3 grid(ceil_div(W, 256), H, B);
-  flow_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, flow, out, C, H, W, h, w, o16, c_off);
+  dim3 grid(ceil_div(W, kWarpBX), ceil_div(H, kWarpBY), B);
+  flow_warp_kernel<<<grid, dim3(kWarpBX, kWarpBY), 0, (cudaStream_t)stream>>>(src, flow, out, C, H, W, h, w, o16, c_off);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
