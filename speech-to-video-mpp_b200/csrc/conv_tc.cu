@@ -27,7 +27,7 @@ namespace s2v {
 
 constexpr int kTileM = 128, kChunkK = 64, kUmmaK = 16;
 constexpr int kABytes = kTileM * kChunkK * 2;        // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                        // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr unsigned kSpinLimit = 1u << 26;            // bounded waits: trap instead of hanging the GPU
 
 struct TcParams {
@@ -36,7 +36,7 @@ struct TcParams {
   int tiles_w, tiles_h;
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
-  int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols;
+  int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols, stage_bufs, n_tiles_n, epi_groups;
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
   int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident;
@@ -187,7 +187,15 @@ template <int ACT>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm, const CUtensorMap* tmY, uint32_t tmem, int warp,
                                               int lane) {
   const int q = warp & 3;                          // TMEM lane quarter this warp may access
-  const int et = threadIdx.x - 64;                 // 0..127
+  // two epilogue groups of 4 warps: group g drains accumulator buffer g, i.e. the tiles j = g, g+2, ... of this CTA,
+  // with its own staging buffer, tables and named barrier - two tiles' epilogues are in flight at once
+  const int grp = (warp - 2) >> 2;
+  if (grp >= p.epi_groups) return;
+  const int et = threadIdx.x - 64 - 128 * grp;     // 0..127 within the group
+  const uint32_t bar_id = 1u + (uint32_t)grp;
+  float* const s_scale = sm.s_scale + 512 * grp;
+  float* const s_bias = s_scale + 256;
+  uint8_t* const s_valid = sm.s_valid + 128 * grp;
   const int m = q * 32 + lane;                     // tile row owned in phase 1
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
   const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
@@ -195,32 +203,46 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   // staging layout = what a SWIZZLE_128B TMA store expects: panels of 64 channels, [128 rows][128 B] each,
   // 16-byte chunk j of row r stored at chunk position j ^ (r & 7)  (also makes the smem stores conflict-free)
   const bool tma_store = !direct && (p.r2.p == nullptr) && p.use_tma_store;
+  uint32_t sb = p.epi_groups == 2 ? (uint32_t)grp : 0u;   // staging buffer: one per group, or alternating per pass
   auto stage_ptr = [&](int row, int col) -> __half* {      // col multiple of 8 within the pass
     const int panel = col >> 6, chunk = (col >> 3) & 7;
-    return sm.stage + (size_t)panel * (kTileM * 64) + (size_t)row * 64 + ((chunk ^ (row & 7)) << 3);
+    return sm.stage + (size_t)sb * (p.stage_out_bytes >> 2) + (size_t)panel * (kTileM * 64) + (size_t)row * 64 + ((chunk ^ (row & 7)) << 3);
   };
-  int j = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+  auto load_tables = [&](int ntile) {
+    for (int i = et; i < p.bn; i += 128) {
+      const int c = ntile * p.bn + i;
+      s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
+      s_bias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    }
+  };
+  if (p.n_tiles_n == 1) { load_tables(0); asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
+  const int jstep = p.epi_groups;
+  int j = grp;
+  for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += jstep * gridDim.x, j += jstep) {
     int ntile, n0, y0, x0, tile_sp;
     tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
     const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
     const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
     const uint32_t buf = (uint32_t)j & 1u;
-    // previous tile's stores are done with the staging tile / tables before they are overwritten
-    if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int i = et; i < p.bn; i += 128) {
-      const int c = ntile * p.bn + i;
-      sm.s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
-      sm.s_bias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    if (p.n_tiles_n > 1) {                          // per-channel tables change with the N tile
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      load_tables(ntile);
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
-    if (!direct && p.stats) sm.s_valid[m] = valid ? 1 : 0;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(sm.tfull0 + 8u * buf, ((uint32_t)j >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.tmem_buf_cols;
     for (int pass0 = 0; pass0 < p.bn; pass0 += half_n) {
       const int pass_n = min(half_n, p.bn - pass0);
+      if (!direct) {
+        // the staging buffer of this pass is free once the bulk store issued stage_bufs passes ago has read it
+        if (tma_store && et == 0) {
+          if (p.stage_bufs == 2 && p.epi_groups == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        if (p.stats && pass0 == 0) s_valid[m] = valid ? 1 : 0;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
       for (int cb = 0; cb < pass_n; cb += 32) {
         float v[32];
         tmem_ld16_nowait(trow + (uint32_t)(pass0 + cb), v);
@@ -233,8 +255,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           const int ct = pass0 + cl;                // column within the N tile
           const int c = ntile * p.bn + ct;
           float* o = v + 8 * g;
-          const float4 s0 = *reinterpret_cast<const float4*>(sm.s_scale + ct), s1 = *reinterpret_cast<const float4*>(sm.s_scale + ct + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(sm.s_bias + ct), b1 = *reinterpret_cast<const float4*>(sm.s_bias + ct + 4);
+          const float4 s0 = *reinterpret_cast<const float4*>(s_scale + ct), s1 = *reinterpret_cast<const float4*>(s_scale + ct + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + ct), b1 = *reinterpret_cast<const float4*>(s_bias + ct + 4);
           o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
           o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
           if (!direct) {
@@ -280,11 +302,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
       }
       if (direct) continue;
       if (tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to the TMA engine
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (tma_store && et == 0) {
         // one bulk tensor store per 64-channel panel; TMA clips rows/channels outside the output view
         for (int pc = 0; pc < pass_n; pc += 64) {
-          const uint32_t src = sm.stage_out + (uint32_t)(pc >> 6) * (kTileM * 128);
+          const uint32_t src = sm.stage_out + sb * (uint32_t)(p.stage_out_bytes >> 1) + (uint32_t)(pc >> 6) * (kTileM * 128);
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                        ::"l"(tmY), "r"(src), "r"(ntile * p.bn + pass0 + pc), "r"(x0), "r"(y0), "r"(n0)
                        : "memory");
@@ -304,7 +326,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           for (int im = 0; im < p.box_n; ++im) {
             if (n0 + im >= p.N) break;
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const uint8_t* vp = sm.s_valid + im * rows_per_img;
+            const uint8_t* vp = s_valid + im * rows_per_img;
 #pragma unroll 4
             for (int r = g; r < rows_per_img; r += p.st_groups) {
               if (!vp[r]) continue;
@@ -356,10 +378,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           st_h8(dst[u], hv[u]);
         }
       }
-      if (!last_pass) {                               // staging tile is reused by the next pass
-        if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      if (p.stage_bufs == 2 && p.epi_groups == 1) sb ^= 1u;
     }
   }
 }
@@ -390,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
   sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
   sm.s_bias = sm.s_scale + 256;
-  sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_bias + 256);
+  sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_scale + 1024);     // two groups x (scale[256] | bias[256])
   sm.stage = reinterpret_cast<__half*>(smem_raw + (sm.stage_out - raw_u32));
   volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (sm.tptr - raw_u32));
 
@@ -565,7 +584,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       case S2V_ACT_GELU: epilogue_loop<S2V_ACT_GELU>(p, sm, &tmY, tmem, warp, lane); break;
       default: epilogue_loop<S2V_ACT_NONE>(p, sm, &tmY, tmem, warp, lane); break;
     }
-    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores landed
+    if (threadIdx.x == 64 || threadIdx.x == 192) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores landed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -762,8 +781,24 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       p.use_tma_store = 0;                  // e.g. a stride the encoder rejects: fall back to the manual coalesced stores
   }
-  // ring | output staging tile | barriers + tmem ptr | scale/bias tables | row-valid mask
-  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 2 * 256 * sizeof(float) + 128 + 1024;
+  // a second output staging buffer lets the epilogue fill tile j+1 while the bulk store of tile j still reads smem
+  p.stage_bufs = 1;
+  p.n_tiles_n = ceil_div(cout, bn);
+  {
+    const size_t fixed = 16 * stages + 176 + 4 * 256 * sizeof(float) + 256 + 1024;
+    if ((size_t)p.ring_bytes + 2 * (size_t)p.stage_out_bytes + fixed <= 227 * 1024) {
+      p.stage_bufs = 2;
+    } else if (!p.halo && stages > 3 && (size_t)p.ring_bytes - stage_bytes + 2 * (size_t)p.stage_out_bytes + fixed <= 227 * 1024) {
+      stages -= 1;                      // trade one ring stage for the second staging buffer
+      p.stages = stages;
+      p.ring_bytes = stages * stage_bytes;
+      p.stage_bufs = 2;
+    }
+    if (p.stage_bufs == 2) p.stage_out_bytes *= 2;
+  }
+  p.epi_groups = p.stage_bufs == 2 ? 2 : 1;
+  // ring | output staging tile(s) | barriers + tmem ptr | scale/bias tables | row-valid mask
+  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 4 * 256 * sizeof(float) + 256 + 1024;
   if (smem > 227 * 1024) return S2V_EINVAL;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);

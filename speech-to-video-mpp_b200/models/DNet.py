@@ -297,8 +297,12 @@ class DNet(nn.Module):
         if dev.type != "cuda":
             raise L.S2VError("DNet runs on CUDA only (sm_100a kernels, no CPU fallback); call .cuda() first")
         if self._engine is None or self._engine_key != dev:
+            from .. import custom_ops
+            if getattr(self, "_handle", None):
+                custom_ops.release_engine(self._handle)
             self._engine = DNetEngine(self.state_dict(), dev, conv_impl=self._conv_impl, use_graph=self._use_graph)
             self._engine_key = dev
+            self._handle = custom_ops.register_engine(self._engine)
         return self._engine
 
     @torch.no_grad()
@@ -307,4 +311,10 @@ class DNet(nn.Module):
             raise L.S2VError("this DNet is an inference engine (eval-mode semantics); call .eval()")
         if driving_source.shape[2] < 25:
             raise RuntimeError("driving_source needs at least 25 frames (MappingNet crops 24, models/DNet.py:48-53)")
-        return self.engine().forward(input_image.float().contiguous(), driving_source.float().contiguous(), stage)
+        self.engine()
+        res = torch.ops.s2v.dnet_forward(input_image.float().contiguous(), driving_source.float().contiguous(),
+                                         stage == "warp", self._handle)
+        out = {"flow_field": res[0], "warp_image": res[1]}
+        if stage != "warp":
+            out["fake_image"] = res[2]
+        return out

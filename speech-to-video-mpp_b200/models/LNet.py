@@ -288,9 +288,13 @@ class LNet(nn.Module):
         if dev.type != "cuda":
             raise L.S2VError("LNet runs on CUDA only (sm_100a kernels, no CPU fallback); call .cuda() first")
         if self._engine is None or self._engine_key != dev:
+            from .. import custom_ops
+            if getattr(self, "_handle", None):
+                custom_ops.release_engine(self._handle)
             self._engine = LNetEngine(self.state_dict(), dev, conv_impl=self._conv_impl, use_graph=self._use_graph,
                                       **self._cfg)
             self._engine_key = dev
+            self._handle = custom_ops.register_engine(self._engine)
         return self._engine
 
     @torch.no_grad()
@@ -302,8 +306,8 @@ class LNet(nn.Module):
         if five_d:            # time-major flatten, models/LNet.py:125-127
             audio_sequences = torch.cat([audio_sequences[:, i] for i in range(audio_sequences.size(1))], dim=0)
             face_sequences = torch.cat([face_sequences[:, :, i] for i in range(face_sequences.size(2))], dim=0)
-        eng = self.engine()
-        out = eng.forward(audio_sequences.float().contiguous(), face_sequences.float().contiguous())
+        self.engine()
+        out = torch.ops.s2v.lnet_forward(audio_sequences.float().contiguous(), face_sequences.float().contiguous(), self._handle)
         if five_d:
             out = torch.stack(torch.split(out, B, dim=0), dim=2)
         return out
