@@ -102,7 +102,7 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
             out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0,
-            x2=None, k2=(1, 1), pad2=(0, 0), stats=None) -> Op:
+            x2=None, k2=(1, 1), pad2=(0, 0), stats=None, alg_flops=None) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
@@ -158,6 +158,8 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     op.alg_flops = 2.0 * d.y.n * d.y.h * d.y.w * cout * taps * cin_true * alg_scale
     if x2 is not None:
         op.alg_flops += 2.0 * d.y.n * d.y.h * d.y.w * cout * k2[0] * k2[1] * x2.shape[3]
+    if alg_flops is not None:           # launches that execute structurally-zero weight blocks report the reference's work
+        op.alg_flops = float(alg_flops)
     return op
 
 
