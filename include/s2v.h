@@ -162,7 +162,7 @@ typedef struct {
    *   chunk = stats_chunk_off + tile*stats_gmax + g
    * i.e. the [N][chunks][C][2] layout s2v_ln2d_finalize / s2v_adain_finalize consume (replaces a
    * s2v_chan_stats pass over the output).  tile = tile_y*tiles_x + tile_x of the launch's pixel boxes;
-   * the rows of a tile are split over stats_groups (power of two, <= stats_gmax, groups*ceil(BN/2) <= 128)
+   * the rows of a tile are split over stats_groups (power of two, <= stats_gmax, groups*min(BN,128)/8 <= 128)
    * interleaved row groups g so that all 128 epilogue threads take part; entries never written must be
    * zero (allocate the buffer zeroed once).                                                           */
   float*  stats_partial;

@@ -314,30 +314,34 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (p.stats) {
-        // column sums of the staged fp16 tile: thread (column pair cp, row group g) walks rows g, g+G, ... of
-        // one image of the box at a time, in fixed order (deterministic); every group is its own chunk.
+        // column sums of the staged fp16 tile: thread (16-byte chunk ck = 8 channels, row group g) walks rows
+        // g, g+G, ... of one image of the box at a time with 128-bit smem loads, in fixed order (deterministic);
+        // every row group is its own chunk of the [N][chunks][C][2] partial buffer.
         const int rows_per_img = p.box_w * p.box_h;
-        const int pairs = (pass_n + 1) >> 1;
-        const int cp = et % pairs, g = et / pairs;
-        const int col = 2 * cp;
-        const int c = ntile * p.bn + pass0 + col;
+        const int cks = pass_n >> 3;
+        const int ck = et % cks, g = et / cks;
+        const int c = ntile * p.bn + pass0 + ck * 8;
         if (g < p.st_groups && c < p.cout) {
           const int chunk = p.st_chunk_off + tile_sp * p.st_gmax + g;
           for (int im = 0; im < p.box_n; ++im) {
             if (n0 + im >= p.N) break;
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            float sa[8], qa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sa[i] = qa[i] = 0.f;
             const uint8_t* vp = s_valid + im * rows_per_img;
-#pragma unroll 4
+#pragma unroll 2
             for (int r = g; r < rows_per_img; r += p.st_groups) {
               if (!vp[r]) continue;
-              const int row = im * rows_per_img + r;
-              const float2 v = __half22float2(*reinterpret_cast<const __half2*>(stage_ptr(row, col & ~7) + (col & 7)));
-              s0 += v.x; q0 = fmaf(v.x, v.x, q0);
-              s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+              float f[8];
+              h8_to_f(ld_h8(stage_ptr(im * rows_per_img + r, ck * 8)), f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
             }
-            float* o = p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2;
-            if (c + 1 < p.cout) *reinterpret_cast<float4*>(o) = make_float4(s0, q0, s1, q1);
-            else { o[0] = s0; o[1] = q0; }
+            float4* o = reinterpret_cast<float4*>(p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2);
+            o[0] = make_float4(sa[0], qa[0], sa[1], qa[1]);
+            o[1] = make_float4(sa[2], qa[2], sa[3], qa[3]);
+            o[2] = make_float4(sa[4], qa[4], sa[5], qa[5]);
+            o[3] = make_float4(sa[6], qa[6], sa[7], qa[7]);
           }
         }
       }
@@ -732,8 +736,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.st_chunk_off = d->stats_chunk_off; p.st_chunks_total = d->stats_chunks_total;
   p.st_groups = d->stats_groups; p.st_gmax = d->stats_gmax;
   if (p.stats && (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_c_total <= 0 || p.st_chunks_total <= 0 ||
-                  p.st_groups <= 0 || p.st_groups > p.st_gmax || p.st_groups * ((bn + 1) / 2) > kTileM ||
-                  (p.st_c_off & 1) || (p.st_c_total & 1) ||
+                  p.st_groups <= 0 || p.st_groups > p.st_gmax || p.st_groups * ((bn > 128 ? 128 : bn) / 8) > kTileM ||
+                  (p.st_c_off & 7) || (p.st_c_total & 7) ||
                   p.st_chunk_off + p.tiles_w * p.tiles_h * p.st_gmax > p.st_chunks_total || p.st_c_off + cout > p.st_c_total))
     return S2V_EINVAL;
 

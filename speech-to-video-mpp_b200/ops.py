@@ -170,11 +170,13 @@ def box_tiles(h: int, w: int, n: int, k=(1, 1)) -> int:
 
 
 def stats_groups(lib, cout: int, h: int, w: int, k=(1, 1)) -> int:
-    """Row groups the conv_tc epilogue splits a tile into for the fused statistics (see include/s2v.h)."""
+    """Row groups the conv_tc epilogue splits a tile into for the fused statistics (see include/s2v.h):
+    (16-byte chunks of a <=128-column pass) x groups <= 128 epilogue threads, at most 8 groups."""
     bn = lib.s2v_conv_tc_tile_n(cout)
     bw, bh, _ = conv_box(h, w, k)
+    cks = min(bn, 128) // 8
     g = 1
-    while g * 2 <= 8 and g * 2 * ((bn + 1) // 2) <= 128 and g * 2 <= bw * bh:
+    while g * 2 <= 8 and g * 2 * cks <= 128 and g * 2 <= bw * bh:
         g *= 2
     return g
 
