@@ -65,11 +65,20 @@ __global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restr
   __shared__ double ss[256], sq[256];
   const int n = blockIdx.x;
   double s = 0.0, q = 0.0;
-  for (int c = threadIdx.x; c < C; c += 256)
-    for (int k = 0; k < chunks; ++k) {
-      const float* p = partial + (((size_t)n * chunks + k) * C + c) * 2;
-      s += (double)p[0]; q += (double)p[1];
+  // thread = (channel c, chunk lane): all 256 threads stream the [chunks][C][2] partials of this image with
+  // 8 independent float2 loads in flight; fixed order per thread + fixed tree below => deterministic
+  const int lanes = C >= 256 ? 1 : 256 / C;                 // chunk lanes when C < 256 (C divides 256 or lanes = 1)
+  const int c_of = threadIdx.x % (lanes > 1 ? C : 256), lane = lanes > 1 ? threadIdx.x / C : 0;
+  if (lane < lanes) {
+    for (int c = c_of; c < C; c += (lanes > 1 ? C : 256)) {
+      const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * C + c;
+#pragma unroll 8
+      for (int k = lane; k < chunks; k += lanes) {
+        const float2 v = pp[(size_t)k * C];
+        s += (double)v.x; q += (double)v.y;
+      }
     }
+  }
   ss[threadIdx.x] = s; sq[threadIdx.x] = q;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -96,9 +105,11 @@ __global__ void __launch_bounds__(256) adain_finalize_kernel(const float* __rest
   if (idx >= N * C) return;
   const int n = idx / C, c = idx - n * C;
   double s = 0.0, q = 0.0;
+  const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * C + c;
+#pragma unroll 8
   for (int k = 0; k < chunks; ++k) {
-    const float* p = partial + (((size_t)n * chunks + k) * C + c) * 2;
-    s += (double)p[0]; q += (double)p[1];
+    const float2 v = pp[(size_t)k * C];
+    s += (double)v.x; q += (double)v.y;
   }
   const double mean = s * (double)inv_count;
   double var = q * (double)inv_count - mean * mean;

@@ -135,7 +135,7 @@ class EngineBase:
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):
         n, h, w, c = x.shape
-        chunks = ops.stats_chunks(n, h * w)
+        chunks = ops.stats_chunks(n, h * w, c)
         partial = self.buf(ws, tag + ".partial", (n, chunks, c, 2), torch.float32)
         a = self.buf(ws, tag + ".a", (n, c), torch.float32)
         b = self.buf(ws, tag + ".b", (n, c), torch.float32)

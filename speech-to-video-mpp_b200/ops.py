@@ -181,11 +181,13 @@ def stats_groups(lib, cout: int, h: int, w: int, k=(1, 1)) -> int:
     return g
 
 
-def stats_chunks(n: int, hw: int) -> int:
-    """Pixel chunks per image for chan_stats.  A function of the image size ONLY: the reduction
+def stats_chunks(n: int, hw: int, c: int = 64) -> int:
+    """Pixel chunks per image for chan_stats.  A function of the image geometry ONLY: the reduction
     tree must not depend on the batch size, so that a frame's result is bit-identical whichever
-    batch / GPU shard it is computed in."""
-    return max(1, min(hw // 24, 64))
+    batch / GPU shard it is computed in.  Sized so that every thread streams ~8 pixels (two batches of
+    four independent 16-byte loads): a block covers min(32, 256/(C/8)) pixel lanes."""
+    pg = min(32, max(1, 256 // max(c // 8, 1)))
+    return max(1, min(hw // (8 * pg), 64))
 
 
 def op_chan_stats(lib, x, chunks, partial) -> Op:

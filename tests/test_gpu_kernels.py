@@ -185,7 +185,7 @@ def test_layernorm2d(G, n, c, h, w, pool):
         ref = F.avg_pool2d(ref, 2)
     res = torch.randn(n, ref.shape[2], ref.shape[3], c, device="cuda").half()
     ref = ref + res.permute(0, 3, 1, 2).float()
-    chunks = G.ops.stats_chunks(n, h * w)
+    chunks = G.ops.stats_chunks(n, h * w, c)
     partial = torch.empty(n, chunks, c, 2, device="cuda")
     a, b = torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda")
     y = torch.empty(n, ref.shape[2], ref.shape[3], c, dtype=torch.float16, device="cuda")
@@ -208,7 +208,7 @@ def test_adain_reflect(G, n, c, h, w):
     res = torch.randn(n, h, w, c, device="cuda").half()
     ref = ref + res.permute(0, 3, 1, 2).float()
     refp = F.pad(ref, (1, 1, 1, 1), mode="reflect")
-    chunks = G.ops.stats_chunks(n, h * w)
+    chunks = G.ops.stats_chunks(n, h * w, c)
     partial = torch.empty(n, chunks, c, 2, device="cuda")
     a, b = torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda")
     yp = torch.zeros(n, h + 2, w + 2, c, dtype=torch.float16, device="cuda")
