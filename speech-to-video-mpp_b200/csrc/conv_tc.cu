@@ -37,6 +37,7 @@ struct TcParams {
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols, stage_bufs, n_tiles_n, epi_groups;
+  int m_pairs, total_pair_tiles;                          // CTA-pair mode: the pair (leader, peer) owns M tiles (2*mp, 2*mp+1)
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
   int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident;
@@ -120,6 +121,54 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 
+// ---- CTA-pair (cta_group::2) variants: one MMA instruction spans two SMs (M = 256), each CTA stages its own 128
+// A rows and HALF of the B tile; TMA completions of both CTAs land on the leader's mbarrier; commits are multicast.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_lh_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {     // arrives on `bar` (same offset) in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+// one elected lane of a fully converged warp (the whole MMA warp runs the loop so that descriptors stay warp-uniform)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -168,10 +217,19 @@ struct Smem {            // offsets (shared-space addresses) of the carved regio
   __half* stage;
 };
 
-__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& ntile, int& n0, int& y0, int& x0, int& tile_sp) {
-  const int m_tiles = p.m_tiles;
-  ntile = tile / m_tiles;
-  const int mt = tile - ntile * m_tiles;
+// work item -> (N tile, box origin).  single-CTA mode: item = tile index; pair mode: item = pair-tile index, the CTA of
+// rank `crank` takes M tile 2*mp + crank (an odd tail gives the peer a tile fully outside the tensor: TMA zero-fills its
+// loads and clips its stores).
+template <bool C2>
+__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int crank, int& ntile, int& n0, int& y0, int& x0, int& tile_sp) {
+  int mt;
+  if (C2) {
+    ntile = tile / p.m_pairs;
+    mt = 2 * (tile - ntile * p.m_pairs) + crank;
+  } else {
+    ntile = tile / p.m_tiles;
+    mt = tile - ntile * p.m_tiles;
+  }
   const int per_img = p.tiles_w * p.tiles_h;
   const int tn = mt / per_img;
   tile_sp = mt - tn * per_img;
@@ -183,9 +241,13 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& nt
 // (fp16 tile staged in smem -> optional column statistics -> coalesced 16-byte stores [+ residual]) or direct
 // stores (fp32 NCHW heads, pre-activation residual).  Runs concurrently with the producer / MMA warps
 // working on the NEXT tile (the accumulator is double-buffered in TMEM).
-template <int ACT>
+template <int ACT, bool C2>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm, const CUtensorMap* tmY, uint32_t tmem, int warp,
-                                              int lane) {
+                                              int lane, int crank) {
+  const int w_first = C2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = C2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = C2 ? p.total_pair_tiles : p.total_tiles;
+  const uint32_t tempty_remote0 = C2 ? mapa_rank0(sm.tempty0) : 0u;
   const int q = warp & 3;                          // TMEM lane quarter this warp may access
   // two epilogue groups of 4 warps: group g drains accumulator buffer g, i.e. the tiles j = g, g+2, ... of this CTA,
   // with its own staging buffer, tables and named barrier - two tiles' epilogues are in flight at once
@@ -218,9 +280,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   if (p.n_tiles_n == 1) { load_tables(0); asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
   const int jstep = p.epi_groups;
   int j = grp;
-  for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += jstep * gridDim.x, j += jstep) {
+  for (int tile = w_first + grp * w_step; tile < w_total; tile += jstep * w_step, j += jstep) {
     int ntile, n0, y0, x0, tile_sp;
-    tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+    tile_coords<C2>(p, tile, crank, ntile, n0, y0, x0, tile_sp);
     const int n = n0 + nn, oy = y0 + hh, ox = x0 + ww;
     const bool valid = (n < p.N) && (oy < p.OH) && (ox < p.OW);
     const uint32_t buf = (uint32_t)j & 1u;
@@ -298,7 +360,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         // all TMEM reads of this accumulator buffer are complete: hand it back to the MMA warp
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.tempty0 + 8u * buf) : "memory");
+        if (lane == 0) {
+          if (C2) mbar_arrive_cluster(tempty_remote0 + 8u * buf);       // the leader's MMA thread owns both accumulators' schedule
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.tempty0 + 8u * buf) : "memory");
+        }
       }
       if (direct) continue;
       if (tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to the TMA engine
@@ -390,14 +455,20 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
 // Persistent kernel: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem ring and its
 // mbarrier phases run continuously across tiles; the fp32 accumulator is double-buffered in TMEM so the
 // epilogue of tile j overlaps the TMA/MMA main loop of tile j+1.
+template <bool C2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.bn * 128u;
+  const int crank = C2 ? (int)cluster_ctarank() : 0;
+  const bool leader = crank == 0;
+  const uint32_t b_bytes = (uint32_t)(C2 ? (p.bn >> 1) : p.bn) * 128u;      // pair mode: each CTA stages half of the B tile
   const uint32_t stage_bytes = kABytes + b_bytes;
+  const int w_first = C2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = C2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = C2 ? p.total_pair_tiles : p.total_tiles;
   Smem sm;
   sm.ring = smem_base;
   sm.stage_out = smem_base + (uint32_t)p.ring_bytes;
@@ -426,34 +497,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.ki_total > p.ki0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     if (p.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(sm.full0 + 8u * s, 1); mbar_init(sm.empty0 + 8u * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull0 + 8u * b, 1); mbar_init(sm.tempty0 + 8u * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull0 + 8u * b, 1); mbar_init(sm.tempty0 + 8u * b, C2 ? 8 : 4); }
     for (int a = 0; a < 4; ++a) { mbar_init(sm.afull0 + 8u * a, 1); mbar_init(sm.aempty0 + 8u * a, 1); }
     mbar_init(sm.ball, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm.tptr), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (C2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm.tptr), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm.tptr), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (C2) cluster_sync_all(); else __syncthreads();     // pair mode: the peer's barriers must be initialised before remote arrivals
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tptr_gen;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tptr_gen, 0);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====  (ring state is kept incrementally: no divisions in the single-thread loops)
+      // pair mode: both CTAs load (own A rows, own half of B); every completion lands on the LEADER's barrier, which the
+      // leader arms with the bytes of both CTAs
       uint32_t s = 0, ph = 0;                       // B (or A+B) ring slot / phase
+      const uint32_t full_r = C2 ? mapa_rank0(sm.full0) : sm.full0;
+      const uint32_t afull_r = C2 ? mapa_rank0(sm.afull0) : sm.afull0;
+      const uint32_t ball_r = C2 ? mapa_rank0(sm.ball) : sm.ball;
+      const uint32_t txm = C2 ? 2u : 1u;
+      const int brow0 = C2 ? crank * (p.bn >> 1) : 0;
+#define load_a(dst, tm, bar, c0, c1, c2, c3)                        \
+  do {                                                               \
+    if (C2) tma_load_4d_2sm(dst, tm, bar, c0, c1, c2, c3);           \
+    else tma_load_4d(dst, tm, bar, c0, c1, c2, c3);                  \
+  } while (0)
+#define load_b(dst, bar, kcol, row)                                 \
+  do {                                                               \
+    if (C2) tma_load_2d_2sm(dst, &tmB, bar, kcol, row);              \
+    else tma_load_2d(dst, &tmB, bar, kcol, row);                     \
+  } while (0)
       if (p.halo) {
         if (p.b_resident) {                         // the whole weight matrix of this (single) N tile stays in smem
-          mbar_expect_tx(sm.ball, (uint32_t)KI * b_bytes);
-          for (int it = 0; it < KI; ++it) tma_load_2d(sm.bring + (uint32_t)it * b_bytes, &tmB, sm.ball, it * kChunkK, 0);
+          if (leader) mbar_expect_tx(sm.ball, txm * (uint32_t)KI * b_bytes);
+          for (int it = 0; it < KI; ++it) load_b(sm.bring + (uint32_t)it * b_bytes, ball_r, it * kChunkK, brow0);
         }
         uint32_t a = 0, aph = 0;
         const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = w_first; tile < w_total; tile += w_step) {
           int ntile, n0, y0, x0, tile_sp;
-          tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+          tile_coords<C2>(p, tile, crank, ntile, n0, y0, x0, tile_sp);
           int kcol = 0;
           for (int seg = 0; seg < 2; ++seg) {
             const int chunks = seg == 0 ? p.cin_chunks : chunks2;
@@ -463,23 +556,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ax = x0 - (seg == 0 ? p.pad_w : p.pad2_w), ay = y0 - (seg == 0 ? p.pad_h : p.pad2_h);
             for (int c = 0; c < chunks; ++c) {
               mbar_wait(sm.aempty0 + 8u * a, aph ^ 1u);
-              mbar_expect_tx(sm.afull0 + 8u * a, abytes);
-              tma_load_4d(sm.ring + a * (uint32_t)p.a_slot_bytes, tm, sm.afull0 + 8u * a, c * kChunkK, ax, ay, n0);
+              if (leader) mbar_expect_tx(sm.afull0 + 8u * a, txm * abytes);
+              load_a(sm.ring + a * (uint32_t)p.a_slot_bytes, tm, afull_r + 8u * a, c * kChunkK, ax, ay, n0);
               if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
               if (p.b_resident) continue;
               for (int t = 0; t < taps; ++t, kcol += kChunkK) {
                 mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
-                mbar_expect_tx(sm.full0 + 8u * s, b_bytes);
-                tma_load_2d(sm.bring + s * b_bytes, &tmB, sm.full0 + 8u * s, kcol, ntile * p.bn);
+                if (leader) mbar_expect_tx(sm.full0 + 8u * s, txm * b_bytes);
+                load_b(sm.bring + s * b_bytes, full_r + 8u * s, kcol, ntile * p.bn + brow0);
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
               }
             }
           }
         }
       } else {
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = w_first; tile < w_total; tile += w_step) {
           int ntile, n0, y0, x0, tile_sp;
-          tile_coords(p, tile, ntile, n0, y0, x0, tile_sp);
+          tile_coords<C2>(p, tile, crank, ntile, n0, y0, x0, tile_sp);
           const int bx = x0 * p.str_w - p.pad_w, by = y0 * p.str_h - p.pad_h;
           int kcol = 0;
           for (int seg = 0; seg < 2; ++seg) {
@@ -490,10 +583,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kx = 0; kx < kw; ++kx, kcol += kChunkK) {     // K order is chunk-major: (chunk, tap)
                   mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
                   const uint32_t a_dst = sm.ring + s * stage_bytes;
-                  mbar_expect_tx(sm.full0 + 8u * s, stage_bytes);
-                  if (seg == 0) tma_load_4d(a_dst, &tmA, sm.full0 + 8u * s, c * kChunkK, bx + kx * p.dil_w, by + ky * p.dil_h, n0);
-                  else tma_load_4d(a_dst, &tmA2, sm.full0 + 8u * s, c * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
-                  tma_load_2d(a_dst + kABytes, &tmB, sm.full0 + 8u * s, kcol, ntile * p.bn);
+                  if (leader) mbar_expect_tx(sm.full0 + 8u * s, txm * stage_bytes);
+                  if (seg == 0) load_a(a_dst, &tmA, full_r + 8u * s, c * kChunkK, bx + kx * p.dil_w, by + ky * p.dil_h, n0);
+                  else load_a(a_dst, &tmA2, full_r + 8u * s, c * kChunkK, x0 - p.pad2_w + kx, y0 - p.pad2_h + ky, n0);
+                  load_b(a_dst + kABytes, full_r + 8u * s, kcol, ntile * p.bn + brow0);
                   if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
                 }
               }
@@ -502,16 +595,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+#undef load_a
+#undef load_b
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
+    if (leader) {
+      // ===== MMA issuer: the whole warp walks the loop (warp-uniform descriptors live in uniform registers, no
+      // per-instruction uniformisation), ONE elected lane issues; in pair mode the leader drives both SMs =====
       // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((C2 ? 2 * kTileM : kTileM) >> 4) << 24);
       const uint32_t hi1024 = desc_hi(1024);
+#define mma4(d, alo, ahi, blo, bhi, acc)                                        \
+  do {                                                                           \
+    if (elect_one()) {                                                           \
+      if (C2) {                                                                  \
+        umma_f16_lh_2sm(d, alo, ahi, blo, bhi, idesc, acc);                      \
+        umma_f16_lh_2sm(d, (alo) + 2u, ahi, (blo) + 2u, bhi, idesc, 1u);         \
+        umma_f16_lh_2sm(d, (alo) + 4u, ahi, (blo) + 4u, bhi, idesc, 1u);         \
+        umma_f16_lh_2sm(d, (alo) + 6u, ahi, (blo) + 6u, bhi, idesc, 1u);         \
+      } else {                                                                   \
+        umma_f16_lh(d, alo, ahi, blo, bhi, idesc, acc);                          \
+        umma_f16_lh(d, (alo) + 2u, ahi, (blo) + 2u, bhi, idesc, 1u);             \
+        umma_f16_lh(d, (alo) + 4u, ahi, (blo) + 4u, bhi, idesc, 1u);             \
+        umma_f16_lh(d, (alo) + 6u, ahi, (blo) + 6u, bhi, idesc, 1u);             \
+      }                                                                          \
+    }                                                                            \
+    __syncwarp();                                                                \
+  } while (0)
+#define commit(bar)                     \
+  do {                                  \
+    if (elect_one()) {                  \
+      if (C2) umma_commit_2sm(bar);     \
+      else umma_commit(bar);            \
+    }                                   \
+    __syncwarp();                       \
+  } while (0)
       uint32_t s = 0, ph = 0, a = 0, aph = 0;
       const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
       int j = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      for (int tile = w_first; tile < w_total; tile += w_step, ++j) {
         const uint32_t buf = (uint32_t)j & 1u;
         mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -545,18 +666,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     b_lo = desc_lo(sm.bring + s * b_bytes);
                   }
-                  umma_f16_lh(d_tmem, a_lo, a_hi, b_lo, hi1024, idesc, accum);
-                  umma_f16_lh(d_tmem, a_lo + 2u, a_hi, b_lo + 2u, hi1024, idesc, 1u);
-                  umma_f16_lh(d_tmem, a_lo + 4u, a_hi, b_lo + 4u, hi1024, idesc, 1u);
-                  umma_f16_lh(d_tmem, a_lo + 6u, a_hi, b_lo + 6u, hi1024, idesc, 1u);
+                  mma4(d_tmem, a_lo, a_hi, b_lo, hi1024, accum);
                   accum = 1u;
                   if (!p.b_resident) {
-                    umma_commit(sm.empty0 + 8u * s);
+                    commit(sm.empty0 + 8u * s);
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
                   }
                 }
               }
-              umma_commit(sm.aempty0 + 8u * a);     // patch slot free once these MMAs retire
+              commit(sm.aempty0 + 8u * a);          // patch slot free once these MMAs retire
               if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
             }
           }
@@ -567,34 +685,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a_addr = sm.ring + s * stage_bytes;
             const uint32_t a_lo = desc_lo(a_addr), b_lo = desc_lo(a_addr + kABytes);
             // advance 16 fp16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr>>4) field
-            umma_f16_lh(d_tmem, a_lo, hi1024, b_lo, hi1024, idesc, accum);
-            umma_f16_lh(d_tmem, a_lo + 2u, hi1024, b_lo + 2u, hi1024, idesc, 1u);
-            umma_f16_lh(d_tmem, a_lo + 4u, hi1024, b_lo + 4u, hi1024, idesc, 1u);
-            umma_f16_lh(d_tmem, a_lo + 6u, hi1024, b_lo + 6u, hi1024, idesc, 1u);
+            mma4(d_tmem, a_lo, hi1024, b_lo, hi1024, accum);
             accum = 1u;
-            umma_commit(sm.empty0 + 8u * s);        // frees the smem slot when these MMAs retire
+            commit(sm.empty0 + 8u * s);             // frees the smem slot (of both CTAs) when these MMAs retire
             if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
           }
         }
-        umma_commit(sm.tfull0 + 8u * buf);          // accumulator of this tile complete
+        commit(sm.tfull0 + 8u * buf);               // accumulator of this tile complete (signalled to both CTAs)
       }
     }
+#undef mma4
+#undef commit
   } else {
     switch (p.act) {
-      case S2V_ACT_RELU: epilogue_loop<S2V_ACT_RELU>(p, sm, &tmY, tmem, warp, lane); break;
-      case S2V_ACT_LRELU: epilogue_loop<S2V_ACT_LRELU>(p, sm, &tmY, tmem, warp, lane); break;
-      case S2V_ACT_SIGMOID: epilogue_loop<S2V_ACT_SIGMOID>(p, sm, &tmY, tmem, warp, lane); break;
-      case S2V_ACT_TANH: epilogue_loop<S2V_ACT_TANH>(p, sm, &tmY, tmem, warp, lane); break;
-      case S2V_ACT_GELU: epilogue_loop<S2V_ACT_GELU>(p, sm, &tmY, tmem, warp, lane); break;
-      default: epilogue_loop<S2V_ACT_NONE>(p, sm, &tmY, tmem, warp, lane); break;
+      case S2V_ACT_RELU: epilogue_loop<S2V_ACT_RELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
+      case S2V_ACT_LRELU: epilogue_loop<S2V_ACT_LRELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
+      case S2V_ACT_SIGMOID: epilogue_loop<S2V_ACT_SIGMOID, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
+      case S2V_ACT_TANH: epilogue_loop<S2V_ACT_TANH, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
+      case S2V_ACT_GELU: epilogue_loop<S2V_ACT_GELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
+      default: epilogue_loop<S2V_ACT_NONE, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
     }
     if (threadIdx.x == 64 || threadIdx.x == 192) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores landed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+  if (C2) cluster_sync_all(); else __syncthreads();     // pair mode: nobody leaves while the peer may still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (C2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -660,7 +778,18 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   // two accumulator buffers (epilogue of tile j overlaps the main loop of tile j+1)
   p.tmem_buf_cols = bn <= 16 ? 16 : bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.tmem_buf_cols < 32 ? 32 : 2 * p.tmem_buf_cols;
-  const int b_bytes = bn * 128;
+  // CTA-pair mode (cta_group::2): M = 256 per MMA instruction -> half the single-thread issue cost per SM and half
+  // the weight traffic; needs at least one pair of M tiles
+  // Measured on B200: pairs win where the weight stream dominates (long K loops whose weights cannot stay resident:
+  // 24x24 level 82 -> 56 us, 12x12 3x3 63 -> 60 us) and lose on short / resident layers (pair synchronisation costs more
+  // than the halved weight traffic saves; a cta_group::2 MMA does not issue faster than two cta_group::1 MMAs).
+  const int m_tiles_all = p.tiles_w * p.tiles_h * tiles_n;
+  const int ki_est = d->kh * d->kw * p.cin_chunks + (d->x2.ptr ? d->k2h * d->k2w * ceil_div(d->x2.c, kChunkK) : 0);
+  const bool unit_est = d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1;
+  const bool resident_est = unit_est && ceil_div(cout, bn) == 1 && (long long)ki_est * bn * 128 <= 150 * 1024;
+  const char* env2 = getenv("S2V_CTA2");
+  const bool cta2 = (m_tiles_all >= 2) && (env2 ? atoi(env2) != 0 : (!resident_est && ki_est >= 16));
+  const int b_bytes = (cta2 ? bn / 2 : bn) * 128;
   const int stage_bytes = kABytes + b_bytes;
   p.pass_cols = 128;                                                       // fp16 output staging: 64-channel swizzled panels
   p.stage_out_bytes = (((bn > 128 ? 128 : bn) + 63) / 64) * kTileM * 128;
@@ -757,7 +886,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     const cuuint64_t ktot = (cuuint64_t)p.ki_total * kChunkK;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)((cout + 7) / 8 * 8)};   // weight rows are padded to 8 by the packer
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)(cta2 ? bn / 2 : bn)};
     cuuint32_t es[2] = {1, 1};
     if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -808,7 +937,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);
   static bool attr = false;   // idempotent
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
+    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
+    if (cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
     attr = true;
   }
   static int n_sm = 0;        // immutable after the first call
@@ -817,8 +947,26 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
       return S2V_ECUDA;
   }
-  const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
+  if (cta2) {
+    p.m_pairs = (p.m_tiles + 1) / 2;
+    p.total_pair_tiles = p.m_pairs * p.n_tiles_n;
+    int pairs = n_sm / 2;
+    if (pairs > p.total_pair_tiles) pairs = p.total_pair_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, tmB, tmA2, tmY, p) != cudaSuccess) return S2V_ECUDA;
+  } else {
+    p.m_pairs = 0; p.total_pair_tiles = 0;
+    const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
+    conv_tc_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
+  }
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
