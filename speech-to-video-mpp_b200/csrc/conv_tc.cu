@@ -209,6 +209,40 @@ __device__ __forceinline__ float act_t(float v, float ap) {
   return v;
 }
 
+// Straight-line issue of every tap (KH x KW) x 4 K-steps of ONE 64-channel chunk against smem-resident weights, by the
+// single elected lane: the descriptors of all taps are two base registers plus compile-time multiples of the patch row
+// pitch / the per-tap weight pitch, so the instruction stream between two tcgen05.mma is a couple of uniform adds
+// (the generic loop spends ~50 instructions per 4 MMAs, which bounds every N <= 128 layer).
+template <int KH, int KW, bool C2>
+__device__ __forceinline__ void issue_chunk_resident(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t row_units,
+                                                     uint32_t b_lo, uint32_t b_units, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      const uint32_t a = a_lo + (uint32_t)ky * row_units + (uint32_t)kx * 8u;
+      const uint32_t b = b_lo + (uint32_t)(ky * KW + kx) * b_units;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t acc = (ky == 0 && kx == 0 && k == 0) ? accum : 1u;
+        if (C2) umma_f16_lh_2sm(d_tmem, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, acc);
+        else umma_f16_lh(d_tmem, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, acc);
+      }
+    }
+  }
+}
+// shape ids of the specialised instantiations (0 = generic loop)
+__device__ __forceinline__ int issue_shape(int kh, int kw) {
+  if (kh == 1 && kw == 1) return 1;
+  if (kh == 2 && kw == 2) return 2;
+  if (kh == 3 && kw == 3) return 3;
+  if (kh == 7 && kw == 7) return 4;
+  if (kh == 7 && kw == 1) return 5;
+  if (kh == 1 && kw == 2) return 6;
+  if (kh == 2 && kw == 1) return 7;
+  return 0;
+}
+
 struct Smem {            // offsets (shared-space addresses) of the carved regions
   uint32_t ring, stage_out, full0, empty0, tfull0, tempty0, tptr, afull0, aempty0, ball, bring;
   float* s_scale;
@@ -455,7 +489,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
 // Persistent kernel: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem ring and its
 // mbarrier phases run continuously across tiles; the fp32 accumulator is double-buffered in TMEM so the
 // epilogue of tile j overlaps the TMA/MMA main loop of tile j+1.
-template <bool C2>
+template <bool C2, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
@@ -632,53 +666,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t s = 0, ph = 0, a = 0, aph = 0;
       const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
       int j = 0;
-      for (int tile = w_first; tile < w_total; tile += w_step, ++j) {
-        const uint32_t buf = (uint32_t)j & 1u;
-        mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
-        uint32_t accum = 0;
-        if (p.halo) {
-          if (p.b_resident && j == 0) { mbar_wait(sm.ball, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-          uint32_t b_res_lo = desc_lo(sm.bring);                       // resident weights: walks the whole matrix per tile
+      if (p.halo) {
+        // per-segment invariants, hoisted: this single-warp loop is the critical path of every N <= 128 layer
+        int sg_chunks[2], sg_kh[2], sg_kw[2], sg_shape[2];
+        uint32_t sg_ahi[2], sg_rowstep[2], sg_ru[2], sg_bstep[2];
+#pragma unroll
+        for (int seg = 0; seg < 2; ++seg) {
+          const int taps = seg == 0 ? p.taps0 : p.taps2;
+          const int kw = seg == 0 ? p.kw : p.k2w;
+          const int pw = seg == 0 ? p.pw0 : p.pw2;
+          sg_chunks[seg] = seg == 0 ? p.cin_chunks : chunks2;
+          sg_kw[seg] = kw;
+          sg_kh[seg] = taps / kw;
+          // 8-row core groups of the M tile: contiguous rows for 1x1 (SBO 1024 B); for k > 1 the box is 8 pixels
+          // wide, one group per image row of the patch -> SBO = patch width * 128 B
+          sg_ahi[seg] = desc_hi(taps > 1 ? (uint32_t)pw * 128u : 1024u);
+          sg_rowstep[seg] = (uint32_t)(pw - kw) * 8u;        // (addr >> 4) units: next patch row after kw taps
+          sg_ru[seg] = (uint32_t)pw * 8u;
+          sg_bstep[seg] = (uint32_t)taps * (b_bytes >> 4);
+          sg_shape[seg] = p.b_resident ? issue_shape(sg_kh[seg], kw) : 0;
+        }
+        const uint32_t bu = b_bytes >> 4;
+        const uint32_t a_slot_units = (uint32_t)p.a_slot_bytes >> 4, a_slots = (uint32_t)p.a_slots;
+        const uint32_t ring_lo = desc_lo(sm.ring), bring_lo = desc_lo(sm.bring);
+        const bool b_res = p.b_resident != 0;
+        if (b_res) { mbar_wait(sm.ball, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        for (int tile = w_first; tile < w_total; tile += w_step, ++j) {
+          const uint32_t buf = (uint32_t)j & 1u;
+          mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
+          uint32_t accum = 0;
+          uint32_t b_res_lo = bring_lo;                                  // resident weights: walks the whole matrix per tile
+#pragma unroll
           for (int seg = 0; seg < 2; ++seg) {
-            const int chunks = seg == 0 ? p.cin_chunks : chunks2;
-            const int taps = seg == 0 ? p.taps0 : p.taps2;
-            const int kw = seg == 0 ? p.kw : p.k2w;
-            const int kh = taps / kw;
-            const int pw = seg == 0 ? p.pw0 : p.pw2;
-            // 8-row core groups of the M tile: contiguous rows for 1x1 (SBO 1024 B); for k > 1 the box is 8 pixels
-            // wide, one group per image row of the patch -> SBO = patch width * 128 B
-            const uint32_t a_hi = desc_hi(taps > 1 ? (uint32_t)pw * 128u : 1024u);
-            const uint32_t row_step = (uint32_t)(pw - kw) * 8u;       // (addr >> 4) units: next patch row after kw taps
-            for (int c = 0; c < chunks; ++c) {
+            const int kh = sg_kh[seg], kw = sg_kw[seg], shape = sg_shape[seg];
+            const uint32_t a_hi = sg_ahi[seg], row_step = sg_rowstep[seg], ru = sg_ru[seg];
+            for (int c = 0; c < sg_chunks[seg]; ++c) {
               mbar_wait(sm.afull0 + 8u * a, aph);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              uint32_t a_lo = desc_lo(sm.ring + a * (uint32_t)p.a_slot_bytes);
-              for (int ky = 0; ky < kh; ++ky, a_lo += row_step) {
-                for (int kx = 0; kx < kw; ++kx, a_lo += 8u) {          // +128 B = next pixel of the patch row
-                  uint32_t b_lo;
-                  if (p.b_resident) {
-                    b_lo = b_res_lo;
-                    b_res_lo += b_bytes >> 4;
-                  } else {
-                    mbar_wait(sm.full0 + 8u * s, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    b_lo = desc_lo(sm.bring + s * b_bytes);
+              uint32_t a_lo = ring_lo + a * a_slot_units;
+              if (shape) {
+                if (elect_one()) {
+                  switch (shape) {
+                    case 1: issue_chunk_resident<1, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 2: issue_chunk_resident<2, 2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 3: issue_chunk_resident<3, 3, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 4: issue_chunk_resident<7, 7, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 5: issue_chunk_resident<7, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 6: issue_chunk_resident<1, 2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    default: issue_chunk_resident<2, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
                   }
-                  mma4(d_tmem, a_lo, a_hi, b_lo, hi1024, accum);
-                  accum = 1u;
-                  if (!p.b_resident) {
-                    commit(sm.empty0 + 8u * s);
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                }
+                __syncwarp();
+                b_res_lo += sg_bstep[seg];
+                accum = 1u;
+              } else {
+                for (int ky = 0; ky < kh; ++ky, a_lo += row_step) {
+                  for (int kx = 0; kx < kw; ++kx, a_lo += 8u) {          // +128 B = next pixel of the patch row
+                    uint32_t b_lo;
+                    if (b_res) {
+                      b_lo = b_res_lo;
+                      b_res_lo += bu;
+                    } else {
+                      mbar_wait(sm.full0 + 8u * s, ph);
+                      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                      b_lo = bring_lo + s * bu;
+                    }
+                    mma4(d_tmem, a_lo, a_hi, b_lo, hi1024, accum);
+                    accum = 1u;
+                    if (!b_res) {
+                      commit(sm.empty0 + 8u * s);
+                      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                    }
                   }
                 }
               }
               commit(sm.aempty0 + 8u * a);          // patch slot free once these MMAs retire
-              if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
+              if (++a == a_slots) { a = 0; aph ^= 1u; }
             }
           }
-        } else {
+          commit(sm.tfull0 + 8u * buf);               // accumulator of this tile complete (signalled to both CTAs)
+        }
+      } else {
+        const uint32_t stages = (uint32_t)p.stages;
+        for (int tile = w_first; tile < w_total; tile += w_step, ++j) {
+          const uint32_t buf = (uint32_t)j & 1u;
+          mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
+          uint32_t accum = 0;
           for (int it = 0; it < KI; ++it) {
             mbar_wait(sm.full0 + 8u * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -688,23 +765,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mma4(d_tmem, a_lo, hi1024, b_lo, hi1024, accum);
             accum = 1u;
             commit(sm.empty0 + 8u * s);             // frees the smem slot (of both CTAs) when these MMAs retire
-            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+            if (++s == stages) { s = 0; ph ^= 1u; }
           }
+          commit(sm.tfull0 + 8u * buf);               // accumulator of this tile complete (signalled to both CTAs)
         }
-        commit(sm.tfull0 + 8u * buf);               // accumulator of this tile complete (signalled to both CTAs)
       }
     }
 #undef mma4
 #undef commit
   } else {
-    switch (p.act) {
-      case S2V_ACT_RELU: epilogue_loop<S2V_ACT_RELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-      case S2V_ACT_LRELU: epilogue_loop<S2V_ACT_LRELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-      case S2V_ACT_SIGMOID: epilogue_loop<S2V_ACT_SIGMOID, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-      case S2V_ACT_TANH: epilogue_loop<S2V_ACT_TANH, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-      case S2V_ACT_GELU: epilogue_loop<S2V_ACT_GELU, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-      default: epilogue_loop<S2V_ACT_NONE, C2>(p, sm, &tmY, tmem, warp, lane, crank); break;
-    }
+    epilogue_loop<ACT, C2>(p, sm, &tmY, tmem, warp, lane, crank);
     if (threadIdx.x == 64 || threadIdx.x == 192) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores landed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -935,10 +1005,29 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (smem > 227 * 1024) return S2V_EINVAL;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);
+  // one kernel per (pair mode, activation): keeps each launch's instruction footprint small (the MMA warp's issue
+  // loop is instruction-fetch sensitive)
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+  static const KernelFn kernels[2][6] = {
+      {conv_tc_kernel<false, S2V_ACT_NONE>, conv_tc_kernel<false, S2V_ACT_RELU>, conv_tc_kernel<false, S2V_ACT_LRELU>,
+       conv_tc_kernel<false, S2V_ACT_SIGMOID>, conv_tc_kernel<false, S2V_ACT_TANH>, conv_tc_kernel<false, S2V_ACT_GELU>},
+      {conv_tc_kernel<true, S2V_ACT_NONE>, conv_tc_kernel<true, S2V_ACT_RELU>, conv_tc_kernel<true, S2V_ACT_LRELU>,
+       conv_tc_kernel<true, S2V_ACT_SIGMOID>, conv_tc_kernel<true, S2V_ACT_TANH>, conv_tc_kernel<true, S2V_ACT_GELU>}};
+  int act_idx;
+  switch (d->act) {
+    case S2V_ACT_NONE: act_idx = 0; break;
+    case S2V_ACT_RELU: act_idx = 1; break;
+    case S2V_ACT_LRELU: act_idx = 2; break;
+    case S2V_ACT_SIGMOID: act_idx = 3; break;
+    case S2V_ACT_TANH: act_idx = 4; break;
+    case S2V_ACT_GELU: act_idx = 5; break;
+    default: return S2V_EINVAL;
+  }
   static bool attr = false;   // idempotent
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
-    if (cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 6; ++k)
+        if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
     attr = true;
   }
   static int n_sm = 0;        // immutable after the first call
@@ -961,11 +1050,11 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, tmB, tmA2, tmY, p) != cudaSuccess) return S2V_ECUDA;
+    if (cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, p) != cudaSuccess) return S2V_ECUDA;
   } else {
     p.m_pairs = 0; p.total_pair_tiles = 0;
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
-    conv_tc_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
+    kernels[0][act_idx]<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;

@@ -16,6 +16,8 @@ Data flow per forward (B frames):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -32,6 +34,8 @@ class LNetEngine(EngineBase):
         self.layer, self.base_nc, self.max_nc, self.nblk, self.dnc = layer, base_nc, max_nc, num_res_blocks, descriptor_nc
         assert layer == 3 and base_nc == 64 and max_nc == 512, "kernels are specialised for the default LNet geometry"
         sd = {k: v.detach().to(device) for k, v in sd.items()}
+        # decoder levels (by channel count) whose spatial FFC runs as ONE GEMM with N = C (see _pack)
+        self.merge_levels = tuple(int(v) for v in os.environ.get("S2V_MERGE", "128").split(",") if v)
         self._pack(sd)
 
     # ------------------------------------------------------------------ weights
@@ -70,17 +74,18 @@ class LNetEngine(EngineBase):
                     p = f"decoder.res{i}.res{b}.{cv}"
                     q = p + ".ffc"
                     w_l = torch.cat([sd[q + ".convl2l.weight"], sd[q + ".convg2l.weight"]], 1).float()
-                    merge = self.impl == "tc" and c == 256
+                    merge = self.impl == "tc" and c in self.merge_levels
                     if merge:
-                        # the 24x24 level (C=256) is MMA-issue / weight-stream bound, not FLOP bound: run the whole FFC spatial part as
-                        # ONE GEMM with N = C: rows [0,cl) = l2l|g2l, rows [cl,C) = l2g on the x_l channels (zeros on x_g),
-                        # plus conv2 (1x1 on x+fu(x)) as the second K segment feeding only the global rows
+                        # A tcgen05.mma (M=128, K=16, smem operands) costs >= ~63 cycles whatever N <= 128 is (tools/mb_umma.cu), so
+                        # narrow GEMMs are paid at N = 128: run the whole FFC spatial part as ONE GEMM with N = C: rows [0,cl) =
+                        # l2l|g2l, rows [cl,C) = l2g on the x_l channels (zeros on x_g), plus conv2 (1x1 on x+fu(x)) as the second
+                        # K segment feeding only the global rows.  Pays at 48x48 (C=128: N 32+96 -> 128, weights resident in
+                        # CTA-pair mode); at 24x24 the two separate GEMMs keep their weights resident and win; at 12x12 the
+                        # zero-block FLOPs would dominate.
                         w_g = torch.cat([sd[q + ".convl2g.weight"].float(), torch.zeros(cg, cg, 3, 3, device=w_l.device)], 1)
                         e = self.pack_conv(q + ".all", torch.cat([w_l, w_g], 0))
                         w2 = torch.cat([torch.zeros(cl, cg // 2, 1, 1, device=w_l.device), sd[q + ".convg2g.conv2.weight"].float()], 0)
                         e["w"] = torch.cat([e["w"], ops.pack_w_tc(w2)], 1).contiguous()
-                        # (measured: 98.6 us vs 82.0 + 37.4 us separately; at 48x48 the separate GEMMs keep their weights
-                        #  resident in smem and win, at 12x12 the extra zero-block FLOPs would dominate)
                     else:
                         self.pack_conv(q + ".to_l", w_l)
                     if merge:
