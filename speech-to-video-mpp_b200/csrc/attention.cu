@@ -10,6 +10,8 @@ namespace s2v {
 constexpr int kDh = 64, kMaxT = 256, kChunk = 8;
 
 __global__ void __launch_bounds__(kMaxT) attention_kernel(View q, View k, View v, View o, int heads, float scale_log2e) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __half sm[];        // K [T][64], V [T][64]
   const int T = q.w;
   const int n = blockIdx.x / heads, h = blockIdx.x - n * heads;
@@ -102,7 +104,7 @@ extern "C" int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_vie
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxT * kDh * 2); attr = true; }
   }
-  attention_kernel<<<q->n * heads, threads, smem, (cudaStream_t)stream>>>(mk(q), mk(k), mk(v), mk(o), heads,
+  launch_pdl(attention_kernel, q->n * heads, threads, smem, (cudaStream_t)stream, mk(q), mk(k), mk(v), mk(o), heads,
                                                                          scale * 1.4426950408889634f);
   S2V_CHECK_LAUNCH();
   return S2V_OK;

@@ -29,6 +29,8 @@ __device__ __forceinline__ int reflect_idx(int i, int L) {
 
 template <int PX, int CO>
 __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvP p) {
+  pdl_trigger();
+  pdl_wait();
   const int OH = p.y.h, OW = p.y.w;
   const int OWG = (OW + PX - 1) / PX;
   const long long groups = (long long)p.y.n * OH * OWG;
@@ -172,10 +174,10 @@ extern "C" int s2v_conv_simt(const s2v_conv* d, void* stream) {
   const long long groups = (long long)d->y.n * OH * ((OW + 1) / 2);
   if (wide) {
     const long long threads = groups * (p.cout_pad / 16);
-    conv_simt_kernel<2, 16><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(conv_simt_kernel<2, 16>, ceil_div(threads, 128), 128, 0, (cudaStream_t)stream, p);
   } else {
     const long long threads = groups * (p.cout_pad / 4);
-    conv_simt_kernel<2, 4><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(conv_simt_kernel<2, 4>, ceil_div(threads, 128), 128, 0, (cudaStream_t)stream, p);
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;

@@ -20,6 +20,7 @@
 //   A multi-stage smem ring is handed over with mbarriers (TMA complete_tx -> MMA,
 //   tcgen05.commit -> producer); the accumulator (128 lanes x BN fp32 columns) lives in TMEM.
 #include <cuda.h>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -37,6 +38,7 @@ struct TcParams {
   int kh, kw, pad_h, pad_w, dil_h, dil_w, str_h, str_w;
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols, stage_bufs, n_tiles_n, epi_groups;
+  int tab;                                                // per-group scale / bias table length (bn rounded up to 32)
   int m_pairs, total_pair_tiles;                          // CTA-pair mode: the pair (leader, peer) owns M tiles (2*mp, 2*mp+1)
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
@@ -289,8 +291,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   if (grp >= p.epi_groups) return;
   const int et = threadIdx.x - 64 - 128 * grp;     // 0..127 within the group
   const uint32_t bar_id = 1u + (uint32_t)grp;
-  float* const s_scale = sm.s_scale + 512 * grp;
-  float* const s_bias = s_scale + 256;
+  float* const s_scale = sm.s_scale + 2 * p.tab * grp;
+  float* const s_bias = s_scale + p.tab;
   uint8_t* const s_valid = sm.s_valid + 128 * grp;
   const int m = q * 32 + lane;                     // tile row owned in phase 1
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
@@ -413,29 +415,49 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (p.stats) {
-        // column sums of the staged fp16 tile: thread (16-byte chunk ck = 8 channels, row group g) walks rows
-        // g, g+G, ... of one image of the box at a time with 128-bit smem loads, in fixed order (deterministic);
-        // every row group is its own chunk of the [N][chunks][C][2] partial buffer.
+        // Column sums (sum, sum of squares) of the staged fp16 tile, ONE partial per (image, spatial tile, channel):
+        // the G = 128 / (pass_n / 8) consecutive lanes that share a 16-byte chunk (8 channels) each walk rows g, g+G, ...
+        // of one image of the box with conflict-free 128-bit smem loads, then a fixed butterfly over those lanes
+        // (deterministic, independent of the batch) leaves the total in lane g == 0.
         const int rows_per_img = p.box_w * p.box_h;
-        const int cks = pass_n >> 3;
-        const int ck = et % cks, g = et / cks;
+        const int cks = pass_n >> 3;                // 4, 8 or 16 (validated on the host)
+        const int G = 128 / cks;
+        const int ck = et / G, g = et - ck * G;
         const int c = ntile * p.bn + pass0 + ck * 8;
-        if (g < p.st_groups && c < p.cout) {
-          const int chunk = p.st_chunk_off + tile_sp * p.st_gmax + g;
-          for (int im = 0; im < p.box_n; ++im) {
-            if (n0 + im >= p.N) break;
-            float sa[8], qa[8];
+        const int chunk = p.st_chunk_off + tile_sp;
+        const bool full_tile = (n0 + p.box_n <= p.N) && (y0 + p.box_h <= p.OH) && (x0 + p.box_w <= p.OW);
+        for (int im = 0; im < p.box_n; ++im) {
+          if (n0 + im >= p.N) break;
+          float sa[8], qa[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sa[i] = qa[i] = 0.f;
-            const uint8_t* vp = s_valid + im * rows_per_img;
+          for (int i = 0; i < 8; ++i) sa[i] = qa[i] = 0.f;
+          const uint8_t* vp = s_valid + im * rows_per_img;
+          if (full_tile) {                          // common case: no row mask, loads issued back to back
+#pragma unroll 4
+            for (int r = g; r < rows_per_img; r += G) {
+              float f[8];
+              h8_to_f(ld_h8(stage_ptr(im * rows_per_img + r, ck * 8)), f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
+            }
+          } else {
 #pragma unroll 2
-            for (int r = g; r < rows_per_img; r += p.st_groups) {
+            for (int r = g; r < rows_per_img; r += G) {
               if (!vp[r]) continue;
               float f[8];
               h8_to_f(ld_h8(stage_ptr(im * rows_per_img + r, ck * 8)), f);
 #pragma unroll
               for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
             }
+          }
+          for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
+              qa[i] += __shfl_xor_sync(0xffffffffu, qa[i], o);
+            }
+          }
+          if (g == 0 && c < p.cout) {
             float4* o = reinterpret_cast<float4*>(p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2);
             o[0] = make_float4(sa[0], qa[0], sa[1], qa[1]);
             o[1] = make_float4(sa[2], qa[2], sa[3], qa[3]);
@@ -494,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger_conv();     // the next kernel may start its prologue while this one runs (it waits for our completion itself)
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const int crank = C2 ? (int)cluster_ctarank() : 0;
@@ -517,8 +540,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   sm.tptr = sm.ball + 16u;
   sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
   sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
-  sm.s_bias = sm.s_scale + 256;
-  sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_scale + 1024);     // two groups x (scale[256] | bias[256])
+  sm.s_bias = sm.s_scale + p.tab;
+  sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_scale + 4 * p.tab);     // two groups x (scale[tab] | bias[tab])
   sm.stage = reinterpret_cast<__half*>(smem_raw + (sm.stage_out - raw_u32));
   volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (sm.tptr - raw_u32));
 
@@ -549,6 +572,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (C2) cluster_sync_all(); else __syncthreads();     // pair mode: the peer's barriers must be initialised before remote arrivals
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tptr_gen, 0);
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel; nothing
+  // below may touch activations before it has completed.  The producer thread waits later: weights are never written
+  // by a kernel, so a resident weight matrix is fetched first.
+  if (threadIdx.x != 0) pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -576,6 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (leader) mbar_expect_tx(sm.ball, txm * (uint32_t)KI * b_bytes);
           for (int it = 0; it < KI; ++it) load_b(sm.bring + (uint32_t)it * b_bytes, ball_r, it * kChunkK, brow0);
         }
+        pdl_wait();
         uint32_t a = 0, aph = 0;
         const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
         for (int tile = w_first; tile < w_total; tile += w_step) {
@@ -604,6 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
+        pdl_wait();
         for (int tile = w_first; tile < w_total; tile += w_step) {
           int ntile, n0, y0, x0, tile_sp;
           tile_coords<C2>(p, tile, crank, ntile, n0, y0, x0, tile_sp);
@@ -628,6 +657,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+#if S2V_PDL_TRIG_CONV == 2
+      // every load of this CTA is issued: let the next kernel's launch / prologue overlap our last tiles
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     }
 #undef load_a
 #undef load_b
@@ -807,6 +840,9 @@ static EncodeTiledFn get_encode() {
 using namespace s2v;
 
 extern "C" int s2v_conv_tc_tile_n(int cout) {
+  static int bn_max = 0;                   // development knob, resolved once
+  if (!bn_max) { const char* e = getenv("S2V_BN_MAX"); bn_max = e ? atoi(e) : 256; if (bn_max != 128) bn_max = 256; }
+  if (bn_max == 128 && cout > 128 && cout % 128 == 0) return 128;
   if (cout <= 256) return ((cout + 15) / 16) * 16;
   // pick the N tile that wastes the least: 256, 192 or 128
   const int cands[3] = {256, 192, 128};
@@ -848,22 +884,6 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   // two accumulator buffers (epilogue of tile j overlaps the main loop of tile j+1)
   p.tmem_buf_cols = bn <= 16 ? 16 : bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.tmem_buf_cols < 32 ? 32 : 2 * p.tmem_buf_cols;
-  // CTA-pair mode (cta_group::2): M = 256 per MMA instruction -> half the single-thread issue cost per SM and half
-  // the weight traffic; needs at least one pair of M tiles
-  // Measured on B200: pairs win where the weight stream dominates (long K loops whose weights cannot stay resident:
-  // 24x24 level 82 -> 56 us, 12x12 3x3 63 -> 60 us) and lose on short / resident layers (pair synchronisation costs more
-  // than the halved weight traffic saves; a cta_group::2 MMA does not issue faster than two cta_group::1 MMAs).
-  const int m_tiles_all = p.tiles_w * p.tiles_h * tiles_n;
-  const int ki_est = d->kh * d->kw * p.cin_chunks + (d->x2.ptr ? d->k2h * d->k2w * ceil_div(d->x2.c, kChunkK) : 0);
-  const bool unit_est = d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1;
-  const bool resident_est = unit_est && ceil_div(cout, bn) == 1 && (long long)ki_est * bn * 128 <= 150 * 1024;
-  const char* env2 = getenv("S2V_CTA2");
-  const bool cta2 = (m_tiles_all >= 2) && (env2 ? atoi(env2) != 0 : (!resident_est && ki_est >= 16));
-  const int b_bytes = (cta2 ? bn / 2 : bn) * 128;
-  const int stage_bytes = kABytes + b_bytes;
-  p.pass_cols = 128;                                                       // fp16 output staging: 64-channel swizzled panels
-  p.stage_out_bytes = (((bn > 128 ? 128 : bn) + 63) / 64) * kTileM * 128;
-  int budget = 224 * 1024 - p.stage_out_bytes - 4096;
   const bool seg2 = d->x2.ptr != nullptr;
   if (seg2 && (!view_ok(&d->x2) || d->x2.n != N || d->k2h <= 0 || d->k2w <= 0 || d->stride_h != 1 || d->stride_w != 1)) return S2V_EINVAL;
   p.taps0 = d->kh * d->kw;
@@ -872,58 +892,102 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.cin2_chunks = seg2 ? ceil_div(d->x2.c, kChunkK) : 1;
   p.k2w = seg2 ? d->k2w : 1; p.pad2_h = d->pad2_h; p.pad2_w = d->pad2_w;
   p.ki_total = p.ki0 + (seg2 ? p.taps2 * p.cin2_chunks : 0);
+  p.n_tiles_n = ceil_div(cout, bn);
+  p.tab = (bn + 31) / 32 * 32;
   // halo mode: stride 1, no dilation, and (1x1, any box) or (k > 1 with an 8-pixel-wide single-image box)
   const bool unit = d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1;
   const bool box816 = box_w == 8 && box_n == 1;
-  const bool halo_ok = unit && (p.taps0 == 1 || box816) && (!seg2 || p.taps2 == 1 || box816);
   p.pw0 = box_w + (p.taps0 > 1 ? d->kw - 1 : 0);
   const int ph0 = box_h + (p.taps0 > 1 ? d->kh - 1 : 0);
   p.prows0 = p.pw0 * ph0 * box_n;
   p.pw2 = box_w + (seg2 && p.taps2 > 1 ? d->k2w - 1 : 0);
   const int ph2 = box_h + (seg2 && p.taps2 > 1 ? d->k2h - 1 : 0);
   p.prows2 = seg2 ? p.pw2 * ph2 * box_n : 0;
+  const bool halo_ok = unit && (p.taps0 == 1 || box816) && (!seg2 || p.taps2 == 1 || box816) && p.pw0 <= 256 && ph0 <= 256 &&
+                       p.pw2 <= 256 && ph2 <= 256;
   const int prmax = p.prows0 > p.prows2 ? p.prows0 : p.prows2;
   const int a_slot_bytes = (prmax * 128 + 1023) / 1024 * 1024;
-  const long long w_bytes = (long long)p.ki_total * b_bytes;
-  // weights of a single-N-tile layer stay resident in smem when they fit next to two A patches; a one-panel
-  // (64-column) staging pass is used if that is what makes them fit
-  bool resident = false;
-  if (halo_ok && ceil_div(cout, bn) == 1) {
-    if (w_bytes <= budget - 2 * a_slot_bytes) resident = true;
-    else if (bn > 64 && w_bytes <= budget + (p.stage_out_bytes - kTileM * 128) - 2 * a_slot_bytes) {
-      resident = true;
-      p.pass_cols = 64;
-      budget += p.stage_out_bytes - kTileM * 128;
-      p.stage_out_bytes = kTileM * 128;
+
+  // ---- shared-memory plan.  In order of preference:
+  //  * weights RESIDENT (single N tile, halo-capable geometry): loaded once per CTA, every tile only streams its A patches;
+  //  * TWO output staging buffers = two epilogue groups (tiles j and j+1 drain concurrently) - with 64-column passes if
+  //    128-column ones do not fit;  one staging buffer / one group otherwise;
+  //  * streaming weights: halo mode (one A patch per chunk serves all taps) when taps share a patch, else the plain
+  //    (A box + B tile) per tap ring.
+  struct SmemPlan { bool ok, resident, halo; int pass_cols, bufs, a_slots, stages, ring_bytes, stage_out_bytes, b_bytes; };
+  const int cap = 227 * 1024 - (16 * 8 + 176 + 4 * p.tab * (int)sizeof(float) + 256 + 1024);
+  auto plan_smem = [&](bool pair) -> SmemPlan {
+    SmemPlan sp = {};
+    const int bb = (pair ? bn / 2 : bn) * 128;
+    sp.b_bytes = bb;
+    const long long wb = (long long)p.ki_total * bb;
+    auto staging = [&](int pc, int bufs) { return (((bn > pc ? pc : bn) + 63) / 64) * kTileM * 128 * bufs; };
+    if (halo_ok && p.n_tiles_n == 1) {
+      for (int bufs = 2; bufs >= 1; --bufs)
+        for (int pc = 128; pc >= 64; pc -= 64) {
+          if (pc == 64 && bn <= 64) continue;
+          const int so = staging(pc, bufs);
+          if (wb + 2LL * a_slot_bytes + so > cap) continue;
+          sp.ok = sp.resident = sp.halo = true;
+          sp.pass_cols = pc; sp.bufs = bufs; sp.stage_out_bytes = so; sp.stages = 1;
+          sp.a_slots = (int)((cap - so - wb) / a_slot_bytes);
+          if (sp.a_slots > 4) sp.a_slots = 4;
+          sp.ring_bytes = sp.a_slots * a_slot_bytes + (int)wb;
+          return sp;
+        }
     }
-  }
-  // halo mode pays off when taps share a patch (k > 1) or when the weights are resident; a plain streaming
-  // 1x1 GEMM keeps the leaner one-barrier-per-iteration tap loop
-  p.halo = (halo_ok && (p.taps0 > 1 || p.taps2 > 1 || resident) && p.pw0 <= 256 && ph0 <= 256 && p.pw2 <= 256 && ph2 <= 256) ? 1 : 0;
-  int stages;
-  p.a_slots = 0; p.a_slot_bytes = 0; p.b_resident = 0;
-  if (p.halo) {
-    p.a_slot_bytes = a_slot_bytes;
-    if (resident) {
-      p.b_resident = 1;
-      p.a_slots = (int)((budget - w_bytes) / p.a_slot_bytes);
-      if (p.a_slots > 4) p.a_slots = 4;
-      stages = 1;
-      p.ring_bytes = p.a_slots * p.a_slot_bytes + (int)w_bytes;
-    } else {
-      p.a_slots = p.taps0 > 1 ? 2 : 3;
-      if (p.a_slots * p.a_slot_bytes + 2 * b_bytes > budget) p.a_slots = 2;
-      stages = (budget - p.a_slots * p.a_slot_bytes) / b_bytes;
-      if (stages > 8) stages = 8;
-      if (stages < 2) return S2V_EINVAL;
-      p.ring_bytes = p.a_slots * p.a_slot_bytes + stages * b_bytes;
+    sp.halo = halo_ok && (p.taps0 > 1 || p.taps2 > 1);
+    sp.pass_cols = 128;
+    for (int bufs = 2; bufs >= 1; --bufs) {
+      const int so = staging(128, bufs), avail = cap - so;
+      sp.bufs = bufs; sp.stage_out_bytes = so;
+      if (sp.halo) {
+        sp.a_slots = p.taps0 > 1 ? 2 : 3;
+        if (sp.a_slots * a_slot_bytes + 2 * bb > avail) sp.a_slots = 2;
+        sp.stages = (avail - sp.a_slots * a_slot_bytes) / bb;
+        if (sp.stages > 8) sp.stages = 8;
+        if (sp.stages < (bufs == 2 ? 4 : 2)) continue;
+        sp.ring_bytes = sp.a_slots * a_slot_bytes + sp.stages * bb;
+      } else {
+        sp.a_slots = 0;
+        sp.stages = avail / (kABytes + bb);
+        if (sp.stages > 8) sp.stages = 8;
+        if (sp.stages < (bufs == 2 ? 3 : 2)) continue;
+        sp.ring_bytes = sp.stages * (kABytes + bb);
+      }
+      sp.ok = true;
+      return sp;
     }
-  } else {
-    stages = budget / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    p.ring_bytes = stages * stage_bytes;
+    return sp;
+  };
+  // CTA-pair mode (cta_group::2): M = 256 per MMA instruction, each CTA stages half of the B tile -> half the weight
+  // traffic / footprint.  Used when that is what makes the weights resident, or for long streaming K loops (measured on
+  // B200: 24x24 level 82 -> 56 us, 12x12 3x3 63 -> 60 us); short streaming layers lose (pair synchronisation).
+  const int m_tiles_all = p.tiles_w * p.tiles_h * tiles_n;
+  SmemPlan sp = plan_smem(false);
+  bool cta2 = false;
+  if (m_tiles_all >= 2) {
+    const char* env2 = getenv("S2V_CTA2");
+    if (env2) cta2 = atoi(env2) != 0;
+    else if (!sp.resident) {
+      const SmemPlan s2 = plan_smem(true);
+      cta2 = s2.ok && (s2.resident || p.ki_total >= 16);
+    }
+    if (cta2) sp = plan_smem(true);
   }
+  if (!sp.ok) return S2V_EINVAL;
+  const int b_bytes = sp.b_bytes;
+  const int stage_bytes = kABytes + b_bytes;
+  p.pass_cols = sp.pass_cols;
+  p.stage_out_bytes = sp.stage_out_bytes;
+  p.stage_bufs = sp.bufs;
+  p.epi_groups = sp.bufs == 2 ? 2 : 1;
+  p.halo = sp.halo ? 1 : 0;
+  p.b_resident = sp.resident ? 1 : 0;
+  p.a_slots = sp.halo ? sp.a_slots : 0;
+  p.a_slot_bytes = sp.halo ? a_slot_bytes : 0;
+  p.ring_bytes = sp.ring_bytes;
+  int stages = sp.stages;
   p.stages = stages;
   p.y = mk(d->y);
   p.r1 = mk(d->res1.ptr ? &d->res1 : nullptr);
@@ -934,10 +998,12 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.st_c_off = d->stats_c_off; p.st_c_total = d->stats_c_total;
   p.st_chunk_off = d->stats_chunk_off; p.st_chunks_total = d->stats_chunks_total;
   p.st_groups = d->stats_groups; p.st_gmax = d->stats_gmax;
+  // fused statistics: one partial per (image, spatial tile, channel); every <=128-column epilogue pass must be 32, 64 or
+  // 128 columns wide (the lanes sharing a 16-byte chunk form a power-of-two group inside a warp)
+  const bool st_bn_ok = bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256;
   if (p.stats && (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_c_total <= 0 || p.st_chunks_total <= 0 ||
-                  p.st_groups <= 0 || p.st_groups > p.st_gmax || p.st_groups * ((bn > 128 ? 128 : bn) / 8) > kTileM ||
-                  (p.st_c_off & 7) || (p.st_c_total & 7) ||
-                  p.st_chunk_off + p.tiles_w * p.tiles_h * p.st_gmax > p.st_chunks_total || p.st_c_off + cout > p.st_c_total))
+                  p.st_groups != 1 || p.st_gmax != 1 || !st_bn_ok || (p.st_c_off & 7) || (p.st_c_total & 7) ||
+                  p.st_chunk_off + p.tiles_w * p.tiles_h > p.st_chunks_total || p.st_c_off + cout > p.st_c_total))
     return S2V_EINVAL;
 
   CUtensorMap tmA, tmB, tmA2;
@@ -984,24 +1050,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       p.use_tma_store = 0;                  // e.g. a stride the encoder rejects: fall back to the manual coalesced stores
   }
-  // a second output staging buffer lets the epilogue fill tile j+1 while the bulk store of tile j still reads smem
-  p.stage_bufs = 1;
-  p.n_tiles_n = ceil_div(cout, bn);
-  {
-    const size_t fixed = 16 * stages + 176 + 4 * 256 * sizeof(float) + 256 + 1024;
-    if ((size_t)p.ring_bytes + 2 * (size_t)p.stage_out_bytes + fixed <= 227 * 1024) {
-      p.stage_bufs = 2;
-    } else if (!p.halo && stages > 3 && (size_t)p.ring_bytes - stage_bytes + 2 * (size_t)p.stage_out_bytes + fixed <= 227 * 1024) {
-      stages -= 1;                      // trade one ring stage for the second staging buffer
-      p.stages = stages;
-      p.ring_bytes = stages * stage_bytes;
-      p.stage_bufs = 2;
-    }
-    if (p.stage_bufs == 2) p.stage_out_bytes *= 2;
-  }
-  p.epi_groups = p.stage_bufs == 2 ? 2 : 1;
   // ring | output staging tile(s) | barriers + tmem ptr | scale/bias tables | row-valid mask
-  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 4 * 256 * sizeof(float) + 256 + 1024;
+  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 4 * p.tab * sizeof(float) + 256 + 1024;
   if (smem > 227 * 1024) return S2V_EINVAL;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);
@@ -1036,6 +1086,12 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
       return S2V_ECUDA;
   }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("S2V_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (dbg)
+    fprintf(stderr, "conv_tc: N=%d %dx%d cin=%d cout=%d k=%dx%d seg2=%d | bn=%d halo=%d resident=%d a_slots=%d stages=%d pass_cols=%d stage_bufs=%d "
+            "epi_groups=%d cta2=%d m_tiles=%d smem=%zu\n", N, OH, OW, d->x.c, cout, d->kh, d->kw, (int)seg2, bn, p.halo, p.b_resident, p.a_slots,
+            stages, p.pass_cols, p.stage_bufs, p.epi_groups, (int)cta2, p.m_tiles, smem);
   if (cta2) {
     p.m_pairs = (p.m_tiles + 1) / 2;
     p.total_pair_tiles = p.m_pairs * p.n_tiles_n;
@@ -1046,15 +1102,17 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, p) != cudaSuccess) return S2V_ECUDA;
   } else {
     p.m_pairs = 0; p.total_pair_tiles = 0;
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
-    kernels[0][act_idx]<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmA2, tmY, p);
+    launch_pdl(kernels[0][act_idx], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, tmA2, tmY, p);
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;

@@ -51,6 +51,8 @@ __device__ __forceinline__ void fft(float2 (&x)[N]) {
 // x [N,S,S,C] -> spec [N,S,S/2+1,2C]; block (n, CB channels), threads (S/2+1)*CB
 template <int S, int CB>
 __global__ void __launch_bounds__((S / 2 + 1) * CB) rfft2_kernel(View x, View sp) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int K = S / 2 + 1;
   extern __shared__ float2 sm[];      // [S][K][CB]
   const int c = threadIdx.x % CB, t = threadIdx.x / CB;
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__((S / 2 + 1) * CB) rfft2_kernel(View x, View sp
 // spec [N,S,S/2+1,2C] -> y [N,S,S,C] (+ add)
 template <int S, int CB>
 __global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View add, View y) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int K = S / 2 + 1;
   extern __shared__ float2 sm[];      // [S][K][CB]
   const int c = threadIdx.x % CB, t = threadIdx.x / CB;
@@ -155,7 +159,7 @@ static int launch_rfft2(const s2v_view* x, const s2v_view* sp, cudaStream_t st) 
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
   static bool attr = false;   // idempotent attribute set (same value every time)
   if (!attr) { cudaFuncSetAttribute(rfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  rfft2_kernel<S, CB><<<dim3(x->c / CB, x->n), K * CB, smem, st>>>(mk(x), mk(sp));
+  launch_pdl(rfft2_kernel<S, CB>, dim3(x->c / CB, x->n), K * CB, smem, st, mk(x), mk(sp));
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }
 template <int S, int CB>
@@ -164,7 +168,7 @@ static int launch_irfft2(const s2v_view* sp, const s2v_view* add, const s2v_view
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(irfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  irfft2_kernel<S, CB><<<dim3(y->c / CB, y->n), K * CB, smem, st>>>(mk(sp), mk(add && add->ptr ? add : nullptr), mk(y));
+  launch_pdl(irfft2_kernel<S, CB>, dim3(y->c / CB, y->n), K * CB, smem, st, mk(sp), mk(add && add->ptr ? add : nullptr), mk(y));
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }
 

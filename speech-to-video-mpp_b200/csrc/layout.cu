@@ -9,6 +9,8 @@ namespace s2v {
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, int N, int C, int H, int W,
                                                    long long src_sn, View d, int c_off, int c_fill, float scale,
                                                    float shift) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * H * W;
   if (idx >= total) return;
@@ -22,6 +24,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
 }
 
 __global__ void __launch_bounds__(256) unpack_kernel(View s, int c_off, int C, float* __restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)s.n * s.h * s.w;
   if (idx >= total) return;
@@ -39,6 +43,8 @@ __global__ void __launch_bounds__(256) unpack_kernel(View s, int c_off, int C, f
 // align_corners=False), face = cat(ref with rows >= mask_row zeroed, ref).
 __global__ void __launch_bounds__(256) glue_kernel(const float* __restrict__ fake, float* __restrict__ face, int B,
                                                    int C, int H, int W, int oh, int ow, int mask_row) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * C * oh * ow;
   if (idx >= total) return;
@@ -70,7 +76,7 @@ extern "C" int s2v_glue_fake_to_face_f32(const float* fake, float* face, int B, 
   if (B == 0) return S2V_OK;
   if (!fake || !face || B < 0 || C <= 0 || H <= 0 || W <= 0 || oh <= 0 || ow <= 0) return S2V_EINVAL;
   const long long total = (long long)B * C * oh * ow;
-  glue_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(fake, face, B, C, H, W, oh, ow, mask_row);
+  launch_pdl(glue_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, fake, face, B, C, H, W, oh, ow, mask_row);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -81,7 +87,7 @@ extern "C" int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, i
   if (!src || !view_ok(dst) || C <= 0 || c_fill < C || c_off < 0 || c_off + c_fill > dst->c) return S2V_EINVAL;
   if (dst->n < N || dst->h != H || dst->w != W || src_sn < (int64_t)C * H * W) return S2V_EINVAL;
   const long long total = (long long)N * H * W;
-  pack_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(src, N, C, H, W, src_sn, mk(dst), c_off, c_fill, scale, shift);
+  launch_pdl(pack_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, src, N, C, H, W, src_sn, mk(dst), c_off, c_fill, scale, shift);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -89,7 +95,7 @@ extern "C" int s2v_pack_nchw_f32(const float* src, int N, int C, int H, int W, i
 extern "C" int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, float* dst, void* stream) {
   if (!view_ok(src) || !dst || C <= 0 || c_off < 0 || c_off + C > src->c) return S2V_EINVAL;
   const long long total = (long long)src->n * src->h * src->w;
-  unpack_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(src), c_off, C, dst);
+  launch_pdl(unpack_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(src), c_off, C, dst);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(kLinTile) grouped_linear_kernel(const __half* 
                                                                  const s2v_lin_group* __restrict__ groups,
                                                                  const int* __restrict__ tile2group,
                                                                  float* __restrict__ out, long long out_stride) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[kLinRows][kLinMaxK];
   const s2v_lin_group g = groups[tile2group[2 * blockIdx.x]];
   const int j = tile2group[2 * blockIdx.x + 1] + threadIdx.x;
@@ -48,7 +50,7 @@ extern "C" int s2v_grouped_linear(const void* hidden_f16, int64_t hidden_stride,
                                   void* stream) {
   if (B == 0 || n_tiles == 0) return S2V_OK;
   if (!hidden_f16 || !groups_dev || !tile2group_dev || !out || B < 0 || n_tiles < 0) return S2V_EINVAL;
-  grouped_linear_kernel<<<dim3(n_tiles, ceil_div(B, kLinRows)), kLinTile, 0, (cudaStream_t)stream>>>(
+  launch_pdl(grouped_linear_kernel, dim3(n_tiles, ceil_div(B, kLinRows)), kLinTile, 0, (cudaStream_t)stream, 
       (const __half*)hidden_f16, hidden_stride, B, groups_dev, tile2group_dev, out, out_stride);
   S2V_CHECK_LAUNCH();
   return S2V_OK;

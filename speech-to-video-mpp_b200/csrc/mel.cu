@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mel_kernel(const float* _
                                                                  const float* __restrict__ basis,
                                                                  const int* __restrict__ band_range,
                                                                  float* __restrict__ out, int reflect) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_hann[kNfft];
   __shared__ float s_x[kWarpsPerBlock][kNfft];
   __shared__ float s_mag[kWarpsPerBlock][kBins + 15];
@@ -124,6 +126,8 @@ __host__ __device__ inline long long window_start(long long i, double mult, long
 
 __global__ void mel_windows_kernel(const float* __restrict__ mel, long long T, double mult, long long first,
                                    long long count, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count * kMels * 16) return;
   const int col = (int)(idx & 15);
@@ -157,7 +161,7 @@ extern "C" int s2v_melspectrogram_f32(const float* wav, int64_t n_samples, const
   if (n_samples < 0 || !basis || !mel_out || (n_samples > 0 && !wav)) return S2V_EINVAL;
   if (pad_reflect && n_samples <= kNfft / 2) return S2V_EINVAL;
   const int T = 1 + (int)(n_samples / kHop);
-  mel_kernel<<<ceil_div(T, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(mel_kernel, ceil_div(T, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream, 
       wav, n_samples, T, basis, band_range, mel_out, pad_reflect);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
@@ -192,7 +196,7 @@ extern "C" int s2v_mel_windows_f32(const float* mel, int64_t n_cols, double fps,
   if (!mel || !out || n_cols < 16 || !(fps > 0) || first < 0 || count < 0) return S2V_EINVAL;
   if (first + count > s2v_mel_window_count(n_cols, fps)) return S2V_EINVAL;
   const long long total = count * kMels * 16;
-  mel_windows_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mel, n_cols, 80.0 / fps, first, count, out);
+  launch_pdl(mel_windows_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mel, n_cols, 80.0 / fps, first, count, out);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

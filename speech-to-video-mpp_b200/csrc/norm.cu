@@ -12,6 +12,8 @@ namespace s2v {
 
 // grid (chunks, N); block = PG * C8 threads (C8 = C/8); thread (pg, c8) walks pixels pg, pg+PG, ...
 __global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];   // [PG][C][2]
   const int C8 = x.c >> 3;
   const int c8 = threadIdx.x % C8, pg = threadIdx.x / C8;
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restr
                                                             double inv_count, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             float* __restrict__ a, float* __restrict__ b) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double ss[256], sq[256];
   const int n = blockIdx.x;
   double s = 0.0, q = 0.0;
@@ -101,6 +105,8 @@ __global__ void __launch_bounds__(256) adain_finalize_kernel(const float* __rest
                                                              int C, float inv_count, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, long long gb_stride,
                                                              float eps, float* __restrict__ a, float* __restrict__ b) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * C) return;
   const int n = idx / C, c = idx - n * C;
@@ -161,6 +167,8 @@ template <int POOL, int ACT>
 __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
                                                          const float* __restrict__ b, float ap, View res, View y,
                                                          int reflect1) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int U = 2;
   const int C8 = x.c >> 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,6 +238,8 @@ template <int CG, int ACT>
 __global__ void __launch_bounds__(kFusedThreads) adain_fused_kernel(View x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, long long gb_stride,
                                                                     float eps, float ap, View res, View y, int reflect1) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int G8 = CG / 8;              // 16-byte vectors per pixel in this channel group
   constexpr int PL = kFusedThreads / G8;  // pixel lanes
   constexpr int NW = kFusedThreads / 32;
@@ -331,6 +341,8 @@ __global__ void __launch_bounds__(kFusedThreads) adain_fused_kernel(View x, cons
 }
 
 __global__ void __launch_bounds__(256) reflect_border_kernel(View v) {
+  pdl_trigger();
+  pdl_wait();
   // v = interior view; fills rows -1 / H and cols -1 / W (pad 1, reflect)
   const int C8 = v.c >> 3;
   const int PW = v.w + 2, PH = v.h + 2;
@@ -356,6 +368,8 @@ __global__ void __launch_bounds__(256) reflect_border_kernel(View v) {
 // one warp per token; C <= 1024 (C/8 vectors spread over lanes)
 __global__ void __launch_bounds__(256) token_ln_kernel(View x, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, View y) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)x.n * x.h * x.w;
@@ -405,6 +419,8 @@ __global__ void __launch_bounds__(256) token_ln_kernel(View x, const float* __re
 }
 
 __global__ void __launch_bounds__(256) add_kernel(View a, View b, View y) {
+  pdl_trigger();
+  pdl_wait();
   const int C8 = y.c >> 3;
   const long long total = (long long)y.n * y.h * y.w * C8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -423,6 +439,8 @@ __global__ void __launch_bounds__(256) add_kernel(View a, View b, View y) {
 }
 
 __global__ void __launch_bounds__(256) mean_over_w_kernel(View x, View y) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= x.n * x.c) return;
   const int n = idx / x.c, c = idx - n * x.c;
@@ -445,7 +463,7 @@ extern "C" int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, voi
   const int threads = PG * C8;
   const size_t smem = (size_t)PG * x->c * 2 * sizeof(float);
   if (smem > 48 * 1024) return S2V_EINVAL;
-  chan_stats_kernel<<<dim3(chunks, x->n), threads, smem, (cudaStream_t)stream>>>(mk(x), chunks, PG, partial);
+  launch_pdl(chan_stats_kernel, dim3(chunks, x->n), threads, smem, (cudaStream_t)stream, mk(x), chunks, PG, partial);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -453,7 +471,7 @@ extern "C" int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, voi
 extern "C" int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
                                  const float* gamma, const float* beta, float eps, float* a, float* b, void* stream) {
   if (!partial || !gamma || !beta || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
-  ln2d_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(partial, chunks, C, 1.0 / ((double)count_per_channel * C),
+  launch_pdl(ln2d_finalize_kernel, N, 256, 0, (cudaStream_t)stream, partial, chunks, C, 1.0 / ((double)count_per_channel * C),
                                                             gamma, beta, eps, a, b);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
@@ -463,7 +481,7 @@ extern "C" int s2v_adain_finalize(const float* partial, int N, int chunks, int C
                                   const float* gamma, const float* beta, int64_t gb_stride, float eps, float* a,
                                   float* b, void* stream) {
   if (!partial || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
-  adain_finalize_kernel<<<ceil_div((long long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(adain_finalize_kernel, ceil_div((long long)N * C, 256), 256, 0, (cudaStream_t)stream, 
       partial, N, chunks, C, 1.f / (float)count_per_channel, gamma, beta, gb_stride, eps, a, b);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
@@ -481,7 +499,7 @@ extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b,
   const dim3 grid(ceil_div((long long)y->w * (y->c >> 3), 256), (y->h + 1) / 2, y->n);
   const View vx = mk(x), vr = mk(res && res->ptr ? res : nullptr), vy = mk(y);
   cudaStream_t st = (cudaStream_t)stream;
-#define S2V_AFFINE(P, A) affine_act_kernel<P, A><<<grid, 256, 0, st>>>(vx, a, b, act_param, vr, vy, reflect1)
+#define S2V_AFFINE(P, A) launch_pdl(affine_act_kernel<P, A>, grid, 256, 0, st, vx, a, b, act_param, vr, vy, reflect1)
   if (pool2) {
     if (act == S2V_ACT_LRELU) S2V_AFFINE(1, S2V_ACT_LRELU);
     else if (act == S2V_ACT_RELU) S2V_AFFINE(1, S2V_ACT_RELU);
@@ -523,7 +541,7 @@ extern "C" int s2v_adain_fused(const s2v_view* x, const float* gamma, const floa
   do {                                                                                                             \
     static bool attr = false;                                                                                      \
     if (!attr) { cudaFuncSetAttribute(adain_fused_kernel<CGV, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
-    adain_fused_kernel<CGV, A><<<grid, kFusedThreads, smem, st>>>(vx, gamma, beta, gb_stride, eps, act_param, vr, vy, reflect1); \
+    launch_pdl(adain_fused_kernel<CGV, A>, grid, kFusedThreads, smem, st, vx, gamma, beta, gb_stride, eps, act_param, vr, vy, reflect1); \
   } while (0)
   if (cg == 64) {
     if (act == S2V_ACT_LRELU) S2V_FUSED(64, S2V_ACT_LRELU);
@@ -542,7 +560,7 @@ extern "C" int s2v_adain_fused(const s2v_view* x, const float* gamma, const floa
 extern "C" int s2v_reflect_border(const s2v_view* interior, void* stream) {
   if (!view_ok(interior) || interior->h < 2 || interior->w < 2) return S2V_EINVAL;
   const long long total = (long long)interior->n * (2 * (interior->w + 2) + 2 * interior->h) * (interior->c >> 3);
-  reflect_border_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(interior));
+  launch_pdl(reflect_border_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(interior));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -552,7 +570,7 @@ extern "C" int s2v_token_layernorm(const s2v_view* x, const float* gamma, const 
   if (!view_ok(x) || !view_ok(y) || !gamma || !beta || x->c > 1024) return S2V_EINVAL;
   if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return S2V_EINVAL;
   const long long total = (long long)x->n * x->h * x->w;
-  token_ln_kernel<<<ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(mk(x), gamma, beta, eps, mk(y));
+  launch_pdl(token_ln_kernel, ceil_div(total, 8), 256, 0, (cudaStream_t)stream, mk(x), gamma, beta, eps, mk(y));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -562,14 +580,14 @@ extern "C" int s2v_add(const s2v_view* a, const s2v_view* b, const s2v_view* y, 
   if (a->n != y->n || a->h != y->h || a->w != y->w || a->c != y->c) return S2V_EINVAL;
   if (b->n != y->n || b->h != y->h || b->w != y->w || b->c != y->c) return S2V_EINVAL;
   const long long total = (long long)y->n * y->h * y->w * (y->c >> 3);
-  add_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(a), mk(b), mk(y));
+  launch_pdl(add_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(a), mk(b), mk(y));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
 
 extern "C" int s2v_mean_over_w(const s2v_view* x, const s2v_view* y, void* stream) {
   if (!view_ok(x) || !view_ok(y) || x->h != 1 || y->h != 1 || y->w != 1 || x->c != y->c || x->n != y->n) return S2V_EINVAL;
-  mean_over_w_kernel<<<ceil_div((long long)x->n * x->c, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y));
+  launch_pdl(mean_over_w_kernel, ceil_div((long long)x->n * x->c, 256), 256, 0, (cudaStream_t)stream, mk(x), mk(y));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

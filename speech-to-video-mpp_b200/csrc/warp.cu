@@ -83,6 +83,8 @@ constexpr int kWarpBX = 32, kWarpBY = 8;
 __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) flow_warp_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                                        float* __restrict__ out, int C, int H, int W, int h, int w,
                                                                        View o16, int c_off) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int kMaxCells = 36 * 12;            // smem cell tile capacity (falls back to direct loads beyond it)
   __shared__ float2 s_def[kMaxCells];
   const int X = blockIdx.x * kWarpBX + threadIdx.x;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) flow_warp_kernel(const f
 }
 
 __global__ void flow_to_deformation_kernel(const float* __restrict__ flow, float* __restrict__ def, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
   if (j >= w) return;
   const float* fx = flow + (size_t)b * 2 * h * w;
@@ -151,6 +155,8 @@ __global__ void flow_to_deformation_kernel(const float* __restrict__ flow, float
 __global__ void __launch_bounds__(256) warp_deformation_kernel(const float* __restrict__ src,
                                                                const float* __restrict__ def, float* __restrict__ out,
                                                                int C, int H, int W, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, b = blockIdx.z;
   if (X >= W) return;
   const float2* d = reinterpret_cast<const float2*>(def) + (size_t)b * h * w;
@@ -185,7 +191,7 @@ extern "C" int s2v_flow_warp_f32(const float* src, const float* flow, float* out
   View o16 = mk(out16);
   if (out16 && out16->ptr && (out16->n < B || out16->h != H || out16->w != W || c_off + C > out16->c)) return S2V_EINVAL;
   dim3 grid(ceil_div(W, kWarpBX), ceil_div(H, kWarpBY), B);
-  flow_warp_kernel<<<grid, dim3(kWarpBX, kWarpBY), 0, (cudaStream_t)stream>>>(src, flow, out, C, H, W, h, w, o16, c_off);
+  launch_pdl(flow_warp_kernel, grid, dim3(kWarpBX, kWarpBY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16, c_off);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -194,7 +200,7 @@ extern "C" int s2v_flow_to_deformation_f32(const float* flow, float* deformation
   if (B == 0) return S2V_OK;
   if (!flow || !deformation || B < 0 || h < 2 || w < 2 || B > 65535 || h > 65535) return S2V_EINVAL;
   dim3 grid(ceil_div(w, 128), h, B);
-  flow_to_deformation_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(flow, deformation, h, w);
+  launch_pdl(flow_to_deformation_kernel, grid, 128, 0, (cudaStream_t)stream, flow, deformation, h, w);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
@@ -205,7 +211,7 @@ extern "C" int s2v_warp_deformation_f32(const float* src, const float* deformati
   if (!src || !deformation || !out || B < 0 || C <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return S2V_EINVAL;
   if (B > 65535 || H > 65535) return S2V_EINVAL;
   dim3 grid(ceil_div(W, 256), H, B);
-  warp_deformation_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, deformation, out, C, H, W, h, w);
+  launch_pdl(warp_deformation_kernel, grid, 256, 0, (cudaStream_t)stream, src, deformation, out, C, H, W, h, w);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

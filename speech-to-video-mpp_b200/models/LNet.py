@@ -36,6 +36,8 @@ class LNetEngine(EngineBase):
         sd = {k: v.detach().to(device) for k, v in sd.items()}
         # decoder levels (by channel count) whose spatial FFC runs as ONE GEMM with N = C (see _pack)
         self.merge_levels = tuple(int(v) for v in os.environ.get("S2V_MERGE", "128").split(",") if v)
+        # {channels of the decoder level: frames per L2-resident sub-batch}, e.g. S2V_SUB="128:32,256:64"
+        self.sub_batch = {int(k): int(v) for k, v in (kv.split(":") for kv in os.environ.get("S2V_SUB", "").split(",") if kv)}
         self._pack(sd)
 
     # ------------------------------------------------------------------ weights
@@ -212,38 +214,48 @@ class LNetEngine(EngineBase):
                 s1, s2 = buf(f"dec{i}.s1", (B, S, S, ch)), buf(f"dec{i}.s2", (B, S, S, ch))
                 F1, F2 = buf(f"dec{i}.F1", (B, S, S // 2 + 1, 2 * ch)), buf(f"dec{i}.F2", (B, S, S // 2 + 1, 2 * ch))
                 flat = lambda t: t.reshape(1, 1, -1, t.shape[-1])
-                cur = 0
-                for b in range(self.nblk):
-                    xin = xps[cur]
-                    mid, nxt = xps[(cur + 1) % 3], xps[(cur + 2) % 3]
-                    for cv, src, dst, res in (("conv1", xin, mid, None), ("conv2", mid, nxt, xin)):
-                        p = f"decoder.res{i}.res{b}.{cv}"
-                        q = p + ".ffc"
-                        inter = src[:, 1:-1, 1:-1, :]
-                        merged = (q + ".all") in self.W
-                        gm = max(ops.stats_groups(lib, cl, S, S, (3, 3)), ops.stats_groups(lib, cg, S, S, (3, 3))) if self.impl == "tc" else 1
-                        st = None
-                        if not merged:
-                            st = self.conv_stats(plan, ws, q + ".to_l", src, R[..., :cl], tag=p, c_total=c, gmax=gm)   # l2l + g2l, 3x3 reflect
-                        if self.impl != "tc":
-                            self.conv(plan, q + ".l2g", src[..., :cl], R[..., cl:])        # l2g, 3x3 reflect
-                        self.conv(plan, q + ".st1", inter[..., cl:], s1, act=L.ACT_RELU)   # 1x1 + BN + ReLU
-                        plan.add(ops.op_rfft2(lib, s1, F1))
-                        self.conv(plan, q + ".fu", flat(F1), flat(F2), act=L.ACT_RELU)     # spectral 1x1 + BN + ReLU
-                        plan.add(ops.op_irfft2(lib, F2, s1, s2))                           # x + fu(x)
-                        if merged:                                                         # whole spatial FFC + conv2 in one GEMM
-                            npx = B * S * S
-                            st = self.conv_stats(plan, ws, q + ".all", src, R, tag=p, c_total=c, x2=s2,
-                                                 alg_flops=2.0 * npx * (9 * (c * cl + cl * cg) + ch * cg))
-                        elif self.impl == "tc":                                            # l2g + conv2 in one GEMM
-                            self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], R[..., cl:], tag=p, c_total=c, c_off=cl, gmax=gm, x2=s2)
-                        else:
-                            self.conv(plan, q + ".st2", s2, R[..., cl:], res2=R[..., cl:])  # + l2g partial sum
-                        off = self.gb_off[p]
-                        self.adain(plan, ws, p, R, gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0),
-                                   dst[:, 1:-1, 1:-1, :], slope=0.01,
-                                   res=None if res is None else res[:, 1:-1, 1:-1, :], reflect1=1, stats=st)
-                    cur = (cur + 2) % 3
+                # L2 blocking: the 18 FFC layers of a level run per sub-batch of `sub` frames, so that the level's working set
+                # (3 rotating padded buffers + R + spectral scratch) stays inside the 126 MB L2 between the ~9 kernels of a layer
+                sub = self.sub_batch.get(c, B)
+                sub = B if sub <= 0 or sub > B else sub
+                for b0 in range(0, B, sub):
+                    bs = slice(b0, min(B, b0 + sub))
+                    nb = bs.stop - bs.start
+                    flat = lambda t: t.reshape(1, 1, -1, t.shape[-1])
+                    cur = 0
+                    for b in range(self.nblk):
+                        xin = xps[cur][bs]
+                        mid, nxt = xps[(cur + 1) % 3][bs], xps[(cur + 2) % 3][bs]
+                        for cv, src, dst, res in (("conv1", xin, mid, None), ("conv2", mid, nxt, xin)):
+                            p = f"decoder.res{i}.res{b}.{cv}"
+                            q = p + ".ffc"
+                            tg = p if sub == B else f"{p}.s{b0}"
+                            inter = src[:, 1:-1, 1:-1, :]
+                            merged = (q + ".all") in self.W
+                            fz = ops.stats_fusable(lib, cl) and ops.stats_fusable(lib, cg)    # both halves of R or neither
+                            st = None
+                            Rb, s1b, s2b, F1b, F2b = R[:nb], s1[:nb], s2[:nb], F1[:nb], F2[:nb]   # scratch: same (L2-hot) memory for every sub-batch
+                            if not merged:
+                                st = self.conv_stats(plan, ws, q + ".to_l", src, Rb[..., :cl], tag=tg, c_total=c, fuse=fz)   # l2l + g2l, 3x3 reflect
+                            if self.impl != "tc":
+                                self.conv(plan, q + ".l2g", src[..., :cl], Rb[..., cl:])        # l2g, 3x3 reflect
+                            self.conv(plan, q + ".st1", inter[..., cl:], s1b, act=L.ACT_RELU)   # 1x1 + BN + ReLU
+                            plan.add(ops.op_rfft2(lib, s1b, F1b))
+                            self.conv(plan, q + ".fu", flat(F1b), flat(F2b), act=L.ACT_RELU)     # spectral 1x1 + BN + ReLU
+                            plan.add(ops.op_irfft2(lib, F2b, s1b, s2b))                           # x + fu(x)
+                            if merged:                                                         # whole spatial FFC + conv2 in one GEMM
+                                npx = nb * S * S
+                                st = self.conv_stats(plan, ws, q + ".all", src, Rb, tag=tg, c_total=c, x2=s2b,
+                                                     alg_flops=2.0 * npx * (9 * (c * cl + cl * cg) + ch * cg))
+                            elif self.impl == "tc":                                            # l2g + conv2 in one GEMM
+                                self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], Rb[..., cl:], tag=tg, c_total=c, c_off=cl, fuse=fz, x2=s2b)
+                            else:
+                                self.conv(plan, q + ".st2", s2b, Rb[..., cl:], res2=Rb[..., cl:])  # + l2g partial sum
+                            off = self.gb_off[p]
+                            self.adain(plan, ws, tg, Rb, gb[bs, off:off + c], gb[bs, off + c:off + 2 * c], gb.stride(0),
+                                       dst[:, 1:-1, 1:-1, :], slope=0.01,
+                                       res=None if res is None else res[:, 1:-1, 1:-1, :], reflect1=1, stats=st)
+                        cur = (cur + 2) % 3
                 dec_out = xps[cur][:, 1:-1, 1:-1, :]
                 co = c // 4 if i == 2 else c // 2
                 S2 = 2 * S

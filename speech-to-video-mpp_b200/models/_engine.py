@@ -113,24 +113,21 @@ class EngineBase:
         self.conv(plan, name, win, y, pad=(0, 0), cin_true=cin_true * k)
         return None
 
-    def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, gmax=None, **kw):
-        """conv whose epilogue also emits the per-(image, tile, channel) sums of its output (tc path).
-        Returns (partial, chunks) for layernorm2d/adain(stats=...), or None on the simt path (the caller
-        then falls back to a chan_stats pass).  Measured on B200 (round 1): with the current non-overlapped
-        epilogue the fused statistics cost more inside the GEMM (+3.2 ms/step) than the separate
-        full-chip chan_stats pass they remove (2.7 ms/step), so this is opt-in (S2V_FUSED_STATS=1) until the
-        epilogue is overlapped with the next tile's main loop."""
-        if self.W[name]["impl"] != "tc" or os.environ.get("S2V_FUSED_STATS", "0") != "1":
+    def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, fuse=True, **kw):
+        """conv whose epilogue also emits the per-(image, spatial tile, channel) sum / sum of squares of its fp16 output
+        (tc path) - this replaces the separate full-tensor chan_stats pass.  Returns (partial, chunks) for
+        layernorm2d/adain(stats=...), or None when the statistics cannot be fused (simt path, odd tile widths,
+        S2V_FUSED_STATS=0): the caller then falls back to a chan_stats pass."""
+        n, h, w, c = y.shape
+        ct = c_total or c
+        if self.W[name]["impl"] != "tc" or os.environ.get("S2V_FUSED_STATS", "1") != "1" or not fuse or not ops.stats_fusable(self.lib, c):
             self.conv(plan, name, x, y, **kw)
             return None
-        n, h, w, c = y.shape
         k = kw.get("k", self.W[name]["k"])
         tiles = ops.box_tiles(h, w, n, k)
-        g = ops.stats_groups(self.lib, c, h, w, k)
-        gmax = max(g, gmax or 1)
-        partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * gmax * phases, c_total or c, 2), torch.float32, zero=True)
-        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles * gmax, g, gmax), **kw)
-        return partial, tiles * gmax * phases
+        partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
+        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), **kw)
+        return partial, tiles * phases
 
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):

@@ -128,8 +128,9 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     d.x2 = view(x2) if x2 is not None else null_view()
     d.k2h, d.k2w = k2
     d.pad2_h, d.pad2_w = pad2
-    if stats is not None:       # (partial [N,chunks,C,2] float32, c_off, chunk_off, groups, gmax): fused output statistics
-        partial, c_off, chunk_off, d.stats_groups, d.stats_gmax = stats
+    if stats is not None:       # (partial [N,chunks,C,2] float32, c_off, chunk_off): fused output statistics
+        partial, c_off, chunk_off = stats
+        d.stats_groups = d.stats_gmax = 1
         assert impl == "tc" and partial.dtype == torch.float32 and partial.dim() == 4 and partial.shape[0] == d.y.n
         d.stats_partial = partial.data_ptr()
         d.stats_c_off, d.stats_c_total = c_off, partial.shape[2]
@@ -169,16 +170,10 @@ def box_tiles(h: int, w: int, n: int, k=(1, 1)) -> int:
     return -(-w // bw) * -(-h // bh)
 
 
-def stats_groups(lib, cout: int, h: int, w: int, k=(1, 1)) -> int:
-    """Row groups the conv_tc epilogue splits a tile into for the fused statistics (see include/s2v.h):
-    (16-byte chunks of a <=128-column pass) x groups <= 128 epilogue threads, at most 8 groups."""
-    bn = lib.s2v_conv_tc_tile_n(cout)
-    bw, bh, _ = conv_box(h, w, k)
-    cks = min(bn, 128) // 8
-    g = 1
-    while g * 2 <= 8 and g * 2 * cks <= 128 and g * 2 <= bw * bh:
-        g *= 2
-    return g
+def stats_fusable(lib, cout: int) -> bool:
+    """Whether the conv_tc epilogue can emit the output statistics of a Cout-wide conv (its <=128-column passes must
+    be 32, 64 or 128 columns wide, see s2v_conv_tc)."""
+    return lib.s2v_conv_tc_tile_n(cout) in (32, 64, 128, 192, 256)
 
 
 def stats_chunks(n: int, hw: int, c: int = 64) -> int:

@@ -195,13 +195,14 @@ def test_fused_epilogue_statistics(G):
     """conv_tc's optional fused per-(image, tile, channel) sums feed the same finalize kernels as chan_stats."""
     lib, L, ops = G.lib(), G.L, G.ops
     torch.manual_seed(12)
-    for (n, s, cin, cout) in ((9, 12, 128, 256), (3, 48, 64, 32), (2, 24, 64, 96)):
+    for (n, s, cin, cout) in ((9, 12, 128, 256), (3, 48, 64, 32), (2, 24, 64, 192), (3, 24, 128, 64), (2, 96, 64, 128), (10, 12, 64, 768)):
         x = torch.randn(n, s, s, cin, device="cuda").half()
         wt = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
         y = torch.zeros(n, s, s, cout, dtype=torch.float16, device="cuda")
-        tiles, g = ops.box_tiles(s, s, n, (3, 3)), ops.stats_groups(lib, cout, s, s, (3, 3))
-        partial = torch.zeros(n, tiles * g, cout, 2, device="cuda")
-        ops.op_conv(lib, x, ops.pack_w_tc(wt), y, k=(3, 3), pad=(1, 1), stats=(partial, 0, 0, g, g)).run()
+        assert ops.stats_fusable(lib, cout)
+        tiles = ops.box_tiles(s, s, n, (3, 3))
+        partial = torch.full((n, tiles, cout, 2), float("nan"), device="cuda")       # every entry must be written
+        ops.op_conv(lib, x, ops.pack_w_tc(wt), y, k=(3, 3), pad=(1, 1), stats=(partial, 0, 0)).run()
         torch.cuda.synchronize()
         yf = y.float()
         ref_s, ref_q = yf.sum((1, 2)), (yf * yf).sum((1, 2))

@@ -58,3 +58,7 @@ xr = torch.randn(B, 12, 12, 256, device="cuda").half()
 X = torch.randn(B, 14, 14, 1024, device="cuda").half()[:, 1:-1, 1:-1, :512]
 wo = ops.pack_w_tc(torch.randn(512, 256, 1, 1, device="cuda") * 0.02)
 bench("ca.out+res2", xr, wo, X, res2=X, bias=torch.rand(512, device="cuda"))
+xd = torch.randn(B, 96, 96, 64, device="cuda").half()
+wd = ops.pack_w_tc(torch.randn(128, 64, 3, 3, device="cuda") * 0.02)
+yd = torch.empty(B, 96, 96, 128, device="cuda", dtype=torch.float16)
+bench("enc.down0", xd, wd, yd, k=(3, 3), pad=(1, 1), bias=torch.rand(128, device="cuda"))
