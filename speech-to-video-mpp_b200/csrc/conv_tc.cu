@@ -297,6 +297,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   const int m = q * 32 + lane;                     // tile row owned in phase 1
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
   const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
+  const bool affine = p.scale != nullptr || p.bias != nullptr;      // identity tables are skipped altogether
   const int half_n = p.bn > p.pass_cols ? p.pass_cols : p.bn;      // columns staged per pass (1 or 2 panels of 64 channels)
   // staging layout = what a SWIZZLE_128B TMA store expects: panels of 64 channels, [128 rows][128 B] each,
   // 16-byte chunk j of row r stored at chunk position j ^ (r & 7)  (also makes the smem stores conflict-free)
@@ -353,10 +354,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           const int ct = pass0 + cl;                // column within the N tile
           const int c = ntile * p.bn + ct;
           float* o = v + 8 * g;
-          const float4 s0 = *reinterpret_cast<const float4*>(s_scale + ct), s1 = *reinterpret_cast<const float4*>(s_scale + ct + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + ct), b1 = *reinterpret_cast<const float4*>(s_bias + ct + 4);
-          o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
-          o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
+          if (affine) {
+            const float4 s0 = *reinterpret_cast<const float4*>(s_scale + ct), s1 = *reinterpret_cast<const float4*>(s_scale + ct + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + ct), b1 = *reinterpret_cast<const float4*>(s_bias + ct + 4);
+            o[0] = fmaf(o[0], s0.x, b0.x); o[1] = fmaf(o[1], s0.y, b0.y); o[2] = fmaf(o[2], s0.z, b0.z); o[3] = fmaf(o[3], s0.w, b0.w);
+            o[4] = fmaf(o[4], s1.x, b1.x); o[5] = fmaf(o[5], s1.y, b1.y); o[6] = fmaf(o[6], s1.z, b1.z); o[7] = fmaf(o[7], s1.w, b1.w);
+          }
           if (!direct) {
             if (ACT != S2V_ACT_NONE) {
 #pragma unroll
