@@ -211,39 +211,31 @@ __device__ __forceinline__ float act_t(float v, float ap) {
   return v;
 }
 
-// Straight-line issue of every tap (KH x KW) x 4 K-steps of ONE 64-channel chunk against smem-resident weights, by the
-// single elected lane: the descriptors of all taps are two base registers plus compile-time multiples of the patch row
-// pitch / the per-tap weight pitch, so the instruction stream between two tcgen05.mma is a couple of uniform adds
-// (the generic loop spends ~50 instructions per 4 MMAs, which bounds every N <= 128 layer).
-template <int KH, int KW, bool C2>
+// Issue of every tap (kh x KW) x 4 K-steps of ONE 64-channel chunk against smem-resident weights, by the single elected
+// lane.  One patch row (KW taps = 4*KW MMAs) is straight-line code whose descriptors are two base registers plus
+// compile-time offsets - a couple of uniform adds between two tcgen05.mma (the generic loop spends ~50 instructions per
+// 4 MMAs, which bounds every N <= 128 layer); the rows are a rolled loop so that the body stays a few hundred bytes: the
+// MMA warp shares its scheduler's instruction cache with two epilogue warps (ncu: stall_no_inst was its top stall with
+// the fully unrolled 3x3 / 7x7 bodies).
+template <int KW, bool C2>
 __device__ __forceinline__ void issue_chunk_resident(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t row_units,
-                                                     uint32_t b_lo, uint32_t b_units, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+                                                     uint32_t b_lo, uint32_t b_units, uint32_t b_hi, uint32_t idesc, uint32_t accum,
+                                                     int kh) {
+#pragma unroll 1
+  for (int ky = 0; ky < kh; ++ky, a_lo += row_units) {
 #pragma unroll
-  for (int ky = 0; ky < KH; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < KW; ++kx) {
-      const uint32_t a = a_lo + (uint32_t)ky * row_units + (uint32_t)kx * 8u;
-      const uint32_t b = b_lo + (uint32_t)(ky * KW + kx) * b_units;
+    for (int kx = 0; kx < KW; ++kx, b_lo += b_units) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t acc = (ky == 0 && kx == 0 && k == 0) ? accum : 1u;
-        if (C2) umma_f16_lh_2sm(d_tmem, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, acc);
-        else umma_f16_lh(d_tmem, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, acc);
+        if (C2) umma_f16_lh_2sm(d_tmem, a_lo + (uint32_t)(kx * 8 + 2 * k), a_hi, b_lo + 2u * k, b_hi, idesc, accum);
+        else umma_f16_lh(d_tmem, a_lo + (uint32_t)(kx * 8 + 2 * k), a_hi, b_lo + 2u * k, b_hi, idesc, accum);
+        accum = 1u;
       }
     }
   }
 }
-// shape ids of the specialised instantiations (0 = generic loop)
-__device__ __forceinline__ int issue_shape(int kh, int kw) {
-  if (kh == 1 && kw == 1) return 1;
-  if (kh == 2 && kw == 2) return 2;
-  if (kh == 3 && kw == 3) return 3;
-  if (kh == 7 && kw == 7) return 4;
-  if (kh == 7 && kw == 1) return 5;
-  if (kh == 1 && kw == 2) return 6;
-  if (kh == 2 && kw == 1) return 7;
-  return 0;
-}
+// row widths with a specialised instantiation (0 = generic loop)
+__device__ __forceinline__ int issue_shape(int kh, int kw) { return (kw == 1 || kw == 2 || kw == 3 || kw == 7) ? kw : 0; }
 
 struct Smem {            // offsets (shared-space addresses) of the carved regions
   uint32_t ring, stage_out, full0, empty0, tfull0, tempty0, tptr, afull0, aempty0, ball, bring;
@@ -745,13 +737,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (shape) {
                 if (elect_one()) {
                   switch (shape) {
-                    case 1: issue_chunk_resident<1, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    case 2: issue_chunk_resident<2, 2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    case 3: issue_chunk_resident<3, 3, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    case 4: issue_chunk_resident<7, 7, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    case 5: issue_chunk_resident<7, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    case 6: issue_chunk_resident<1, 2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
-                    default: issue_chunk_resident<2, 1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum); break;
+                    case 1: issue_chunk_resident<1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
+                    case 2: issue_chunk_resident<2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
+                    case 3: issue_chunk_resident<3, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
+                    default: issue_chunk_resident<7, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
                   }
                 }
                 __syncwarp();

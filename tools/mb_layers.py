@@ -62,3 +62,18 @@ xd = torch.randn(B, 96, 96, 64, device="cuda").half()
 wd = ops.pack_w_tc(torch.randn(128, 64, 3, 3, device="cuda") * 0.02)
 yd = torch.empty(B, 96, 96, 128, device="cuda", dtype=torch.float16)
 bench("enc.down0", xd, wd, yd, k=(3, 3), pad=(1, 1), bias=torch.rand(128, device="cuda"))
+
+
+def level_all(tag, S, C):
+    cg = C * 3 // 4; cl = C - cg; ch = cg // 2
+    xp = torch.randn(B, S + 2, S + 2, C, device="cuda").half()
+    R = torch.empty(B, S, S, C, device="cuda", dtype=torch.float16)
+    s2 = torch.randn(B, S, S, ch, device="cuda").half()
+    wa = torch.cat([ops.pack_w_tc(torch.randn(C, C, 3, 3, device="cuda") * 0.02), ops.pack_w_tc(torch.randn(C, ch, 1, 1, device="cuda") * 0.02)], 1).contiguous()
+    bench(f"{tag}.all", xp, wa, R, k=(3, 3), x2=s2)
+    tiles = ops.box_tiles(S, S, B, (3, 3))
+    partial = torch.zeros(B, tiles, C, 2, device="cuda")
+    bench(f"{tag}.all+stats", xp, wa, R, k=(3, 3), x2=s2, stats=(partial, 0, 0))
+
+
+level_all("res0", 48, 128)
