@@ -212,7 +212,7 @@ def main():
     mel, face = synth.lnet_inputs(B, seed=rank)
     mel_d, face_d = mel.to(dev), face.to(dev)
     eng = net.engine()
-    ent = eng._get_plan(B, eng._build(B))
+    ent = eng.plan_for(B)
     ent["io"]["mel"].copy_(mel_d)
     ent["io"]["face"].copy_(face_d)
 

@@ -417,27 +417,35 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         const int rows_per_img = p.box_w * p.box_h;
         const int cks = pass_n >> 3;                // 4, 8 or 16 (validated on the host)
         const int G = 128 / cks;
-        const int ck = et / G, g = et - ck * G;
+        // multi-image boxes (12x12 level: 8 images x 16 rows): the G lanes are spread over min(G, box_n) images at a time,
+        // L = G / that lanes per image - with box_n >= G every lane owns whole images and no shuffle is needed
+        const int ipg = G < p.box_n ? G : p.box_n;  // images in flight per chunk group (box_n and G are powers of two)
+        const int L = G / ipg;
+        // L > 1: the lanes sharing a chunk are consecutive (butterfly inside the warp; their rows differ, so the swizzle
+        // spreads them over the banks).  L == 1: chunk-fastest mapping - a quarter warp reads one row's 8 chunks
+        // (lanes that own different images would otherwise hit the same banks).
+        const int ck = L > 1 ? et / G : et % cks, g = L > 1 ? et - ck * G : et / cks;
         const int c = ntile * p.bn + pass0 + ck * 8;
         const int chunk = p.st_chunk_off + tile_sp;
         const bool full_tile = (n0 + p.box_n <= p.N) && (y0 + p.box_h <= p.OH) && (x0 + p.box_w <= p.OW);
-        for (int im = 0; im < p.box_n; ++im) {
-          if (n0 + im >= p.N) break;
+        const int sub = g / L, r0 = g - sub * L;
+        for (int im = sub; im < p.box_n; im += ipg) {           // box_n % ipg == 0: the trip count is warp-uniform
+          const bool img_ok = n0 + im < p.N;
           float sa[8], qa[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) sa[i] = qa[i] = 0.f;
           const uint8_t* vp = s_valid + im * rows_per_img;
           if (full_tile) {                          // common case: no row mask, loads issued back to back
 #pragma unroll 4
-            for (int r = g; r < rows_per_img; r += G) {
+            for (int r = r0; r < rows_per_img; r += L) {
               float f[8];
               h8_to_f(ld_h8(stage_ptr(im * rows_per_img + r, ck * 8)), f);
 #pragma unroll
               for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
             }
-          } else {
+          } else if (img_ok) {
 #pragma unroll 2
-            for (int r = g; r < rows_per_img; r += G) {
+            for (int r = r0; r < rows_per_img; r += L) {
               if (!vp[r]) continue;
               float f[8];
               h8_to_f(ld_h8(stage_ptr(im * rows_per_img + r, ck * 8)), f);
@@ -445,14 +453,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
               for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
             }
           }
-          for (int o = G >> 1; o > 0; o >>= 1) {
+          for (int o = L >> 1; o > 0; o >>= 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
               qa[i] += __shfl_xor_sync(0xffffffffu, qa[i], o);
             }
           }
-          if (g == 0 && c < p.cout) {
+          if (r0 == 0 && img_ok && c < p.cout) {
             float4* o = reinterpret_cast<float4*>(p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2);
             o[0] = make_float4(sa[0], qa[0], sa[1], qa[1]);
             o[1] = make_float4(sa[2], qa[2], sa[3], qa[3]);

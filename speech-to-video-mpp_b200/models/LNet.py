@@ -287,10 +287,15 @@ class LNetEngine(EngineBase):
 
         return builder
 
+    def plan_for(self, B):
+        spec = lambda b: {"mel": ("in.mel", (b, 1, 80, 16), torch.float32), "face": ("in.face", (b, 6, 96, 96), torch.float32),
+                          "out": ("out", (b, 3, 96, 96), torch.float32)}
+        return self._get_plan(B, self._build(B), builder_of=self._build, batch=B, io_spec=spec)
+
     def forward(self, mel, face):
         """mel [B,1,80,16], face [B,6,96,96] float32 CUDA -> [B,3,96,96] float32 (a fresh tensor)."""
         B = mel.shape[0]
-        ent = self._get_plan(B, self._build(B))
+        ent = self.plan_for(B)
         io = ent["io"]
         io["mel"].copy_(mel, non_blocking=True)
         io["face"].copy_(face, non_blocking=True)

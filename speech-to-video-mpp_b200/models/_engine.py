@@ -188,28 +188,64 @@ class EngineBase:
         self.W[name] = dict(groups=gdev, tiles=tdev, n_tiles=len(tiles), keep=keep)
 
     # ---- plan execution ----------------------------------------------------------------
-    def _get_plan(self, key, builder):
+    # Frames are independent, so a batch can run as `self.streams` independent sub-batches on parallel streams (own
+    # workspace each, shared weights): while one sub-batch sits in a kernel's prologue / tail / launch gap the other's
+    # CTAs fill the idle SMs.  The I/O buffers stay whole-batch tensors; each part works on its slice.
+    streams = int(os.environ.get("S2V_STREAMS", "1"))
+
+    def _get_plan(self, key, builder, builder_of=None, batch=None, io_spec=None):
+        """builder(plan, ws) -> io dict.  With builder_of(B) / io_spec(B) -> {io name: (workspace name, shape, dtype)} given,
+        a batch of `batch` frames is split over `self.streams` parallel sub-plans."""
         if key not in self._plans:
-            ws = {}
-            plan = ops.Plan()
-            io = builder(plan, ws)
-            self._plans[key] = dict(plan=plan, ws=ws, io=io, graph=None, warm=0)
+            B = batch or 0
+            parts_n = self.streams if (builder_of and io_spec and self.streams > 1 and B % self.streams == 0 and B // self.streams >= 8) else 1
+            if parts_n == 1:
+                ws, plan = {}, ops.Plan()
+                io = builder(plan, ws)
+                self._plans[key] = dict(plan=plan, ws=ws, io=io, graph=None, warm=0, parts=None)
+            else:
+                sub = B // parts_n
+                spec = io_spec(B)
+                io = {name: torch.empty(shape, dtype=dt, device=self.dev) for name, (_, shape, dt) in spec.items()}
+                parts, allp = [], ops.Plan()
+                for i in range(parts_n):
+                    ws, plan = {}, ops.Plan()
+                    for name, (ws_name, _, _) in spec.items():      # part i works on rows [i*sub, (i+1)*sub) of the whole-batch I/O
+                        ws[ws_name] = io[name][i * sub:(i + 1) * sub]
+                    builder_of(sub)(plan, ws)
+                    parts.append(dict(plan=plan, ws=ws, stream=torch.cuda.Stream(device=self.dev)))
+                    allp.ops.extend(plan.ops)
+                self._plans[key] = dict(plan=allp, ws=None, io=io, graph=None, warm=0, parts=parts)
         return self._plans[key]
+
+    def _run_plan(self, ent):
+        if not ent["parts"]:
+            ent["plan"].run()
+            return
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for pt in ent["parts"]:
+            pt["stream"].wait_event(fork)
+            pt["plan"].run(C.c_void_p(pt["stream"].cuda_stream))
+            done = torch.cuda.Event()
+            done.record(pt["stream"])
+            main.wait_event(done)
 
     def _run(self, ent):
         """Runs the plan on the current stream; after two eager runs the op list is captured into a
-        CUDA graph (launch-bound: ~600 small kernels per LNet forward) and replayed."""
+        CUDA graph (launch-bound: ~500 small kernels per LNet forward) and replayed."""
         if not self.use_graph:
-            ent["plan"].run()
+            self._run_plan(ent)
             return
         if ent["graph"] is None:
-            ent["plan"].run()
+            self._run_plan(ent)
             ent["warm"] += 1
             if ent["warm"] >= 2 and not torch.cuda.is_current_stream_capturing():
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    ent["plan"].run()
+                    self._run_plan(ent)
                 ent["graph"] = g
             return
         ent["graph"].replay()
