@@ -159,14 +159,17 @@ typedef struct {
   /* optional fused statistics (tc, fp16 NHWC output only): the epilogue also writes, per image and per
    * spatial tile of the launch, the sum and sum of squares of every output channel it produced:
    *   stats_partial[((n*stats_chunks_total + chunk)*stats_c_total + stats_c_off + c)*2 + {0,1}],
-   *   chunk = stats_chunk_off + tile*stats_gmax + g
+   *   chunk = stats_chunk_off + tile
    * i.e. the [N][chunks][C][2] layout s2v_ln2d_finalize / s2v_adain_finalize consume (replaces a
-   * s2v_chan_stats pass over the output).  tile = tile_y*tiles_x + tile_x of the launch's pixel boxes;
-   * the rows of a tile are split over stats_groups (power of two, <= stats_gmax, groups*min(BN,128)/8 <= 128)
-   * interleaved row groups g so that all 128 epilogue threads take part; entries never written must be
-   * zero (allocate the buffer zeroed once).                                                           */
+   * s2v_chan_stats pass over the output).  tile = tile_y*tiles_x + tile_x of the launch's pixel boxes.
+   * stats_groups and stats_gmax must be 1 (one partial per image, tile and channel).                  */
   float*  stats_partial;
   int32_t stats_c_off, stats_c_total, stats_chunk_off, stats_chunks_total, stats_groups, stats_gmax;
+  /* s2v_conv_tc hint: a structural zero block of the weights.  Input channels >= narrow_cin_from (a multiple of 64) of
+   * x feed only the first narrow_cout (a multiple of 32) output channels - every other weight of those channels IS
+   * zero.  The kernel may then run those K chunks as narrower MMAs and keep only the non-zero rows in shared memory
+   * (FFC at 48x48: the global half of the input reaches only the 32 local outputs).  0 = no hint.           */
+  int32_t narrow_cin_from, narrow_cout;
 } s2v_conv;
 
 /* SIMT direct convolution (small / awkward layers: Cin=3 7x7, Cout=3, audio

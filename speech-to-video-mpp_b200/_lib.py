@@ -29,7 +29,8 @@ class Conv(C.Structure):
                 ("out_mode", c_i32), ("y_f32", c_vp),
                 ("x2", View), ("k2h", c_i32), ("k2w", c_i32), ("pad2_h", c_i32), ("pad2_w", c_i32),
                 ("stats_partial", c_vp), ("stats_c_off", c_i32), ("stats_c_total", c_i32),
-                ("stats_chunk_off", c_i32), ("stats_chunks_total", c_i32), ("stats_groups", c_i32), ("stats_gmax", c_i32)]
+                ("stats_chunk_off", c_i32), ("stats_chunks_total", c_i32), ("stats_groups", c_i32), ("stats_gmax", c_i32),
+                ("narrow_cin_from", c_i32), ("narrow_cout", c_i32)]
 
 
 class LinGroup(C.Structure):

@@ -39,6 +39,7 @@ struct TcParams {
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols, stage_bufs, n_tiles_n, epi_groups;
   int tab;                                                // per-group scale / bias table length (bn rounded up to 32)
+  int nf_chunk, bn_narrow;                                // segment-0 chunks >= nf_chunk run as N = bn_narrow MMAs (0 = off)
   int m_pairs, total_pair_tiles;                          // CTA-pair mode: the pair (leader, peer) owns M tiles (2*mp, 2*mp+1)
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
@@ -517,7 +518,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
 template <bool C2, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
+               const __grid_constant__ CUtensorMap tmBn, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_trigger_conv();     // the next kernel may start its prologue while this one runs (it waits for our completion itself)
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -554,6 +556,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.bn_narrow) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBn) : "memory");
     if (p.ki_total > p.ki0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     if (p.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(sm.full0 + 8u * s, 1); mbar_init(sm.empty0 + 8u * s, 1); }
@@ -603,8 +606,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } while (0)
       if (p.halo) {
         if (p.b_resident) {                         // the whole weight matrix of this (single) N tile stays in smem
-          if (leader) mbar_expect_tx(sm.ball, txm * (uint32_t)KI * b_bytes);
-          for (int it = 0; it < KI; ++it) load_b(sm.bring + (uint32_t)it * b_bytes, ball_r, it * kChunkK, brow0);
+          if (p.bn_narrow) {
+            // segment-0 chunks >= nf_chunk only feed the first bn_narrow output channels: their taps keep just those
+            // weight rows (box of the narrow map), packed right behind the full-width taps
+            const uint32_t nb_bytes = (uint32_t)(C2 ? (p.bn_narrow >> 1) : p.bn_narrow) * 128u;
+            const int it_n0 = p.nf_chunk * p.taps0, it_n1 = p.ki0;            // narrow chunk-taps [it_n0, it_n1)
+            const uint32_t n_narrow = (uint32_t)(it_n1 - it_n0);
+            if (leader) mbar_expect_tx(sm.ball, txm * (((uint32_t)KI - n_narrow) * b_bytes + n_narrow * nb_bytes));
+            const int brow0n = C2 ? crank * (p.bn_narrow >> 1) : 0;
+            uint32_t dst = sm.bring;
+            for (int it = 0; it < KI; ++it) {
+              if (it >= it_n0 && it < it_n1) {
+                if (C2) tma_load_2d_2sm(dst, &tmBn, ball_r, it * kChunkK, brow0n);
+                else tma_load_2d(dst, &tmBn, ball_r, it * kChunkK, brow0n);
+                dst += nb_bytes;
+              } else {
+                load_b(dst, ball_r, it * kChunkK, brow0);
+                dst += b_bytes;
+              }
+            }
+          } else {
+            if (leader) mbar_expect_tx(sm.ball, txm * (uint32_t)KI * b_bytes);
+            for (int it = 0; it < KI; ++it) load_b(sm.bring + (uint32_t)it * b_bytes, ball_r, it * kChunkK, brow0);
+          }
         }
         pdl_wait();
         uint32_t a = 0, aph = 0;
@@ -723,6 +747,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           sg_shape[seg] = p.b_resident ? issue_shape(sg_kh[seg], kw) : 0;
         }
         const uint32_t bu = b_bytes >> 4;
+        const uint32_t bu_n = ((uint32_t)(C2 ? (p.bn_narrow >> 1) : p.bn_narrow) * 128u) >> 4;
+        const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.bn_narrow >> 3) << 17) | ((uint32_t)((C2 ? 2 * kTileM : kTileM) >> 4) << 24);
         const uint32_t a_slot_units = (uint32_t)p.a_slot_bytes >> 4, a_slots = (uint32_t)p.a_slots;
         const uint32_t ring_lo = desc_lo(sm.ring), bring_lo = desc_lo(sm.bring);
         const bool b_res = p.b_resident != 0;
@@ -743,16 +769,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               uint32_t a_lo = ring_lo + a * a_slot_units;
               if (shape) {
+                // narrow chunks (structural zero block of the weights): same A patch, N = bn_narrow columns of the accumulator
+                const bool nrw = seg == 0 && p.bn_narrow != 0 && c >= p.nf_chunk;
+                const uint32_t idc = nrw ? idesc_n : idesc, buc = nrw ? bu_n : bu;
                 if (elect_one()) {
                   switch (shape) {
-                    case 1: issue_chunk_resident<1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
-                    case 2: issue_chunk_resident<2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
-                    case 3: issue_chunk_resident<3, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
-                    default: issue_chunk_resident<7, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, bu, hi1024, idesc, accum, kh); break;
+                    case 1: issue_chunk_resident<1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
+                    case 2: issue_chunk_resident<2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
+                    case 3: issue_chunk_resident<3, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
+                    default: issue_chunk_resident<7, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
                   }
                 }
                 __syncwarp();
-                b_res_lo += sg_bstep[seg];
+                b_res_lo += (uint32_t)(kh * kw) * buc;
                 accum = 1u;
               } else {
                 for (int ky = 0; ky < kh; ++ky, a_lo += row_step) {
@@ -914,13 +943,22 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   //    128-column ones do not fit;  one staging buffer / one group otherwise;
   //  * streaming weights: halo mode (one A patch per chunk serves all taps) when taps share a patch, else the plain
   //    (A box + B tile) per tap ring.
+  // structural zero block hint (see s2v.h): honoured only with resident weights and a specialised issue shape
+  int narrow_n = 0, narrow_taps = 0, nf_chunk = 0;
+  if (d->narrow_cout > 0 && d->narrow_cin_from > 0 && d->narrow_cin_from % kChunkK == 0 && d->narrow_cout % 32 == 0 && d->narrow_cout < bn &&
+      d->narrow_cin_from < d->x.c && p.n_tiles_n == 1 && (d->kw == 1 || d->kw == 2 || d->kw == 3 || d->kw == 7)) {
+    narrow_n = d->narrow_cout;
+    nf_chunk = d->narrow_cin_from / kChunkK;
+    narrow_taps = (p.cin_chunks - nf_chunk) * p.taps0;
+  }
   struct SmemPlan { bool ok, resident, halo; int pass_cols, bufs, a_slots, stages, ring_bytes, stage_out_bytes, b_bytes; };
   const int cap = 227 * 1024 - (16 * 8 + 176 + 4 * p.tab * (int)sizeof(float) + 256 + 1024);
   auto plan_smem = [&](bool pair) -> SmemPlan {
     SmemPlan sp = {};
     const int bb = (pair ? bn / 2 : bn) * 128;
     sp.b_bytes = bb;
-    const long long wb = (long long)p.ki_total * bb;
+    const int nbb = (pair ? narrow_n / 2 : narrow_n) * 128;
+    const long long wb = (long long)(p.ki_total - narrow_taps) * bb + (long long)narrow_taps * nbb;   // narrow taps only matter when resident
     auto staging = [&](int pc, int bufs) { return (((bn > pc ? pc : bn) + 63) / 64) * kTileM * 128 * bufs; };
     if (halo_ok && p.n_tiles_n == 1) {
       for (int bufs = 2; bufs >= 1; --bufs)
@@ -984,6 +1022,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.epi_groups = sp.bufs == 2 ? 2 : 1;
   p.halo = sp.halo ? 1 : 0;
   p.b_resident = sp.resident ? 1 : 0;
+  p.bn_narrow = sp.resident ? narrow_n : 0;
+  p.nf_chunk = nf_chunk;
   p.a_slots = sp.halo ? sp.a_slots : 0;
   p.a_slot_bytes = sp.halo ? a_slot_bytes : 0;
   p.ring_bytes = sp.ring_bytes;
@@ -1029,6 +1069,18 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
+  CUtensorMap tmBn = tmB;
+  if (p.bn_narrow) {
+    const cuuint64_t ktot = (cuuint64_t)p.ki_total * kChunkK;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)((cout + 7) / 8 * 8)};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)(cta2 ? p.bn_narrow / 2 : p.bn_narrow)};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&tmBn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return S2V_ECUDA;
+  }
   tmA2 = tmA;
   if (seg2) {
     cuuint64_t gdim[4] = {(cuuint64_t)d->x2.c, (cuuint64_t)d->x2.w, (cuuint64_t)d->x2.h, (cuuint64_t)d->x2.n};
@@ -1057,7 +1109,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);
   // one kernel per (pair mode, activation): keeps each launch's instruction footprint small (the MMA warp's issue
   // loop is instruction-fetch sensitive)
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
   static const KernelFn kernels[2][6] = {
       {conv_tc_kernel<false, S2V_ACT_NONE>, conv_tc_kernel<false, S2V_ACT_RELU>, conv_tc_kernel<false, S2V_ACT_LRELU>,
        conv_tc_kernel<false, S2V_ACT_SIGMOID>, conv_tc_kernel<false, S2V_ACT_TANH>, conv_tc_kernel<false, S2V_ACT_GELU>},
@@ -1090,8 +1142,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (dbg < 0) { const char* e = getenv("S2V_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   if (dbg)
     fprintf(stderr, "conv_tc: N=%d %dx%d cin=%d cout=%d k=%dx%d seg2=%d | bn=%d halo=%d resident=%d a_slots=%d stages=%d pass_cols=%d stage_bufs=%d "
-            "epi_groups=%d cta2=%d m_tiles=%d smem=%zu\n", N, OH, OW, d->x.c, cout, d->kh, d->kw, (int)seg2, bn, p.halo, p.b_resident, p.a_slots,
-            stages, p.pass_cols, p.stage_bufs, p.epi_groups, (int)cta2, p.m_tiles, smem);
+            "epi_groups=%d cta2=%d m_tiles=%d smem=%zu narrow=%d\n", N, OH, OW, d->x.c, cout, d->kh, d->kw, (int)seg2, bn, p.halo, p.b_resident, p.a_slots,
+            stages, p.pass_cols, p.stage_bufs, p.epi_groups, (int)cta2, p.m_tiles, smem, p.bn_narrow);
   if (cta2) {
     p.m_pairs = (p.m_tiles + 1) / 2;
     p.total_pair_tiles = p.m_pairs * p.n_tiles_n;
@@ -1108,11 +1160,11 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, p) != cudaSuccess) return S2V_ECUDA;
+    if (cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, tmBn, p) != cudaSuccess) return S2V_ECUDA;
   } else {
     p.m_pairs = 0; p.total_pair_tiles = 0;
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
-    launch_pdl(kernels[0][act_idx], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, tmA2, tmY, p);
+    launch_pdl(kernels[0][act_idx], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, tmA2, tmY, tmBn, p);
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;

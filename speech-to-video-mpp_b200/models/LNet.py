@@ -245,7 +245,9 @@ class LNetEngine(EngineBase):
                             plan.add(ops.op_irfft2(lib, F2b, s1b, s2b))                           # x + fu(x)
                             if merged:                                                         # whole spatial FFC + conv2 in one GEMM
                                 npx = nb * S * S
+                                nfrom = -(-cl // 64) * 64            # x_g channels from here on reach only the cl local outputs
                                 st = self.conv_stats(plan, ws, q + ".all", src, Rb, tag=tg, c_total=c, x2=s2b,
+                                                     narrow=(nfrom, cl) if (nfrom < c and cl % 32 == 0) else None,
                                                      alg_flops=2.0 * npx * (9 * (c * cl + cl * cg) + ch * cg))
                             elif self.impl == "tc":                                            # l2g + conv2 in one GEMM
                                 self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], Rb[..., cl:], tag=tg, c_total=c, c_off=cl, fuse=fz, x2=s2b)

@@ -102,7 +102,7 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
             out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0,
-            x2=None, k2=(1, 1), pad2=(0, 0), stats=None, alg_flops=None) -> Op:
+            x2=None, k2=(1, 1), pad2=(0, 0), stats=None, alg_flops=None, narrow=None) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
@@ -135,6 +135,9 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
         d.stats_partial = partial.data_ptr()
         d.stats_c_off, d.stats_c_total = c_off, partial.shape[2]
         d.stats_chunk_off, d.stats_chunks_total = chunk_off, partial.shape[1]
+    if narrow is not None:      # (cin_from, cout): input channels >= cin_from only feed the first `cout` outputs (zero weight block)
+        d.narrow_cin_from, d.narrow_cout = narrow
+        assert impl == "tc" and narrow[0] % 64 == 0 and narrow[1] % 32 == 0
     keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2, stats)
     cout, taps = d.y.c, k[0] * k[1]
     for t in (scale, bias):

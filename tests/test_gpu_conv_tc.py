@@ -209,3 +209,32 @@ def test_fused_epilogue_statistics(G):
         got = partial.sum(1)
         assert (got[..., 0] - ref_s).abs().max().item() < 2e-2 * max(1.0, ref_s.abs().max().item())
         assert (got[..., 1] - ref_q).abs().max().item() < 1e-3 * ref_q.abs().max().item()
+
+
+def test_narrow_zero_block_hint(G):
+    """s2v_conv.narrow_*: K chunks whose weights are zero outside the first `narrow_cout` rows run as narrower MMAs
+    (merged FFC GEMM at 48x48) - same result as the plain launch, with and without fused statistics."""
+    lib, L, ops = G.lib(), G.L, G.ops
+    torch.manual_seed(21)
+    n, s, c, cl, ch = 5, 48, 128, 32, 48
+    xp = torch.randn(n, s + 2, s + 2, c, device="cuda").half()
+    s2 = torch.randn(n, s, s, ch, device="cuda").half()
+    w3 = torch.randn(c, c, 3, 3, device="cuda") / (c * 9) ** 0.5
+    w3[cl:, cl:] = 0                       # global inputs reach only the local outputs
+    w1 = torch.randn(c, ch, 1, 1, device="cuda") / ch ** 0.5
+    w1[:cl] = 0
+    wcat = torch.cat([ops.pack_w_tc(w3), ops.pack_w_tc(w1)], 1).contiguous()
+    outs = []
+    for narrow in (None, (64, cl)):
+        R = torch.zeros(n, s, s, c, dtype=torch.float16, device="cuda")
+        tiles = ops.box_tiles(s, s, n, (3, 3))
+        partial = torch.full((n, tiles, c, 2), float("nan"), device="cuda")
+        ops.op_conv(lib, xp, wcat, R, k=(3, 3), x2=s2, narrow=narrow, stats=(partial, 0, 0)).run()
+        torch.cuda.synchronize()
+        outs.append((R, partial))
+    ref = F.conv2d(xp.permute(0, 3, 1, 2).float(), w3.half().float()) + F.conv2d(s2.permute(0, 3, 1, 2).float(), w1.half().float())
+    m, rel = G.report("conv_tc merged FFC with narrow hint", G.nchw(outs[1][0]), ref)
+    assert rel < 3e-3
+    assert (outs[0][0].float() - outs[1][0].float()).abs().max().item() < 2e-3 * ref.abs().max().item()
+    yf = outs[1][0].float()
+    assert (outs[1][1].sum(1)[..., 0] - yf.sum((1, 2))).abs().max().item() < 2e-2 * max(1.0, yf.sum((1, 2)).abs().max().item())
