@@ -124,7 +124,7 @@ class EngineBase:
             self.conv(plan, name, x, y, **kw)
             return None
         k = kw.get("k", self.W[name]["k"])
-        tiles = ops.box_tiles(h, w, n, k)
+        tiles = ops.box_tiles(h, w, n, k, kw.get("stride", (1, 1)), kw.get("dil", (1, 1)))
         partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
         self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), **kw)
         return partial, tiles * phases

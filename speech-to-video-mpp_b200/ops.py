@@ -167,9 +167,9 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     return op
 
 
-def box_tiles(h: int, w: int, n: int, k=(1, 1)) -> int:
+def box_tiles(h: int, w: int, n: int, k=(1, 1), stride=(1, 1), dil=(1, 1)) -> int:
     """Spatial tiles per image of a conv_tc launch with the default box (= statistics chunks it emits)."""
-    bw, bh, _ = conv_box(h, w, k)
+    bw, bh, _ = conv_box(h, w, k, stride, dil)
     return -(-w // bw) * -(-h // bh)
 
 
