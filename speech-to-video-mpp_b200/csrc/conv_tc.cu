@@ -29,6 +29,7 @@ namespace s2v {
 constexpr int kTileM = 128, kChunkK = 64, kUmmaK = 16;
 constexpr int kABytes = kTileM * kChunkK * 2;        // 16 KB
 constexpr int kThreads = 320;                        // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kMaxASlots = 8;                        // A-patch slots in flight (small 1x1 patches need many to cover the load latency)
 constexpr unsigned kSpinLimit = 1u << 26;            // bounded waits: trap instead of hanging the GPU
 
 struct TcParams {
@@ -539,9 +540,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   sm.empty0 = bar_base + 8u * p.stages;
   sm.tfull0 = bar_base + 16u * p.stages;
   sm.tempty0 = sm.tfull0 + 16u;
-  sm.afull0 = sm.tempty0 + 16u;             // up to 4 A-patch slots (halo mode)
-  sm.aempty0 = sm.afull0 + 32u;
-  sm.ball = sm.aempty0 + 32u;               // resident-weights barrier (halo mode)
+  sm.afull0 = sm.tempty0 + 16u;             // up to kMaxASlots A-patch slots (halo mode)
+  sm.aempty0 = sm.afull0 + 8u * kMaxASlots;
+  sm.ball = sm.aempty0 + 8u * kMaxASlots;               // resident-weights barrier (halo mode)
   sm.tptr = sm.ball + 16u;
   sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
   sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
@@ -561,7 +562,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(sm.full0 + 8u * s, 1); mbar_init(sm.empty0 + 8u * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull0 + 8u * b, 1); mbar_init(sm.tempty0 + 8u * b, C2 ? 8 : 4); }
-    for (int a = 0; a < 4; ++a) { mbar_init(sm.afull0 + 8u * a, 1); mbar_init(sm.aempty0 + 8u * a, 1); }
+    for (int a = 0; a < kMaxASlots; ++a) { mbar_init(sm.afull0 + 8u * a, 1); mbar_init(sm.aempty0 + 8u * a, 1); }
     mbar_init(sm.ball, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -952,7 +953,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     narrow_taps = (p.cin_chunks - nf_chunk) * p.taps0;
   }
   struct SmemPlan { bool ok, resident, halo; int pass_cols, bufs, a_slots, stages, ring_bytes, stage_out_bytes, b_bytes; };
-  const int cap = 227 * 1024 - (16 * 8 + 176 + 4 * p.tab * (int)sizeof(float) + 256 + 1024);
+  const int cap = 227 * 1024 - (16 * 8 + 240 + 4 * p.tab * (int)sizeof(float) + 256 + 1024);
   auto plan_smem = [&](bool pair) -> SmemPlan {
     SmemPlan sp = {};
     const int bb = (pair ? bn / 2 : bn) * 128;
@@ -969,7 +970,9 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
           sp.ok = sp.resident = sp.halo = true;
           sp.pass_cols = pc; sp.bufs = bufs; sp.stage_out_bytes = so; sp.stages = 1;
           sp.a_slots = (int)((cap - so - wb) / a_slot_bytes);
-          if (sp.a_slots > 4) sp.a_slots = 4;
+          if (sp.a_slots > kMaxASlots) sp.a_slots = kMaxASlots;
+          // ~64 KB of patches in flight covers the load latency; beyond that extra slots only cost shared memory
+          while (sp.a_slots > 4 && (long long)(sp.a_slots - 1) * a_slot_bytes >= 96 * 1024) --sp.a_slots;
           sp.ring_bytes = sp.a_slots * a_slot_bytes + (int)wb;
           return sp;
         }
@@ -1103,7 +1106,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
       p.use_tma_store = 0;                  // e.g. a stride the encoder rejects: fall back to the manual coalesced stores
   }
   // ring | output staging tile(s) | barriers + tmem ptr | scale/bias tables | row-valid mask
-  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 176 + 4 * p.tab * sizeof(float) + 256 + 1024;
+  const size_t smem = (size_t)p.ring_bytes + p.stage_out_bytes + 16 * stages + 240 + 4 * p.tab * sizeof(float) + 256 + 1024;
   if (smem > 227 * 1024) return S2V_EINVAL;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.total_tiles = p.m_tiles * ceil_div(cout, bn);
