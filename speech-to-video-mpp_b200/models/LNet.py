@@ -16,6 +16,7 @@ Data flow per forward (B frames):
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -142,22 +143,25 @@ class LNetEngine(EngineBase):
             out = buf("out", (B, 3, 96, 96), torch.float32)
 
             # ---- audio encoder -> z [B,1,1,512] ------------------------------------------
-            x = buf("aud.in", (B, 80, 16, 8))
-            plan.add(ops.op_pack(lib, mel_in, x, 0, 8))
-            for i, (cin, cout, k, stride, pad, res) in enumerate(_schema.AUDIO_CFG):
-                h, w = x.shape[1], x.shape[2]
-                oh, ow = (h + 2 * pad - k) // stride[0] + 1, (w + 2 * pad - k) // stride[1] + 1
-                y = buf(f"aud.{i}", (B, oh, ow, cout))
-                self.conv(plan, f"audio_encoder.{i}.conv_block", x, y, stride=stride, pad=(pad, pad),
-                          res1=x if res else None, act=L.ACT_RELU, cin_true=cin)
-                x = y
-            z = x
-            # ---- every AdaIN gamma/beta of the decoder (depends only on z) -----------------
-            hidden = buf("adain.hidden", (B, 1, 1, self.n_inst * 128))
-            self.conv(plan, "adain.shared", z, hidden, act=L.ACT_RELU)
-            gb = buf("adain.gb", (B, self.gb_total), torch.float32)
-            hd = self.W["adain.heads"]
-            plan.add(ops.op_grouped_linear(lib, hidden, hd["groups"], hd["tiles"], hd["n_tiles"], gb))
+            # (side branch: only the decoder consumes gb; these ~16 small-grid launches overlap the visual encoder)
+            side = plan.side() if os.environ.get("S2V_SIDE", "1") == "1" else contextlib.nullcontext()
+            with side:
+                x = buf("aud.in", (B, 80, 16, 8))
+                plan.add(ops.op_pack(lib, mel_in, x, 0, 8))
+                for i, (cin, cout, k, stride, pad, res) in enumerate(_schema.AUDIO_CFG):
+                    h, w = x.shape[1], x.shape[2]
+                    oh, ow = (h + 2 * pad - k) // stride[0] + 1, (w + 2 * pad - k) // stride[1] + 1
+                    y = buf(f"aud.{i}", (B, oh, ow, cout))
+                    self.conv(plan, f"audio_encoder.{i}.conv_block", x, y, stride=stride, pad=(pad, pad),
+                              res1=x if res else None, act=L.ACT_RELU, cin_true=cin)
+                    x = y
+                z = x
+                # ---- every AdaIN gamma/beta of the decoder (depends only on z) -----------------
+                hidden = buf("adain.hidden", (B, 1, 1, self.n_inst * 128))
+                self.conv(plan, "adain.shared", z, hidden, act=L.ACT_RELU)
+                gb = buf("adain.gb", (B, self.gb_total), torch.float32)
+                hd = self.W["adain.heads"]
+                plan.add(ops.op_grouped_linear(lib, hidden, hd["groups"], hd["tiles"], hd["n_tiles"], gb))
 
             # ---- visual encoder --------------------------------------------------------------
             xp2 = [buf(f"dec2.xp{j}", (B, 14, 14, 1024), zero=True) for j in range(3)]
@@ -204,6 +208,7 @@ class LNetEngine(EngineBase):
             plan.add(ops.op_reflect_border(lib, cat))
 
             # ---- decoder ---------------------------------------------------------------------
+            plan.join()
             xps = xp2
             for i in (2, 1, 0):
                 S = 12 << (2 - i)

@@ -214,7 +214,7 @@ class EngineBase:
                         ws[ws_name] = io[name][i * sub:(i + 1) * sub]
                     builder_of(sub)(plan, ws)
                     parts.append(dict(plan=plan, ws=ws, stream=torch.cuda.Stream(device=self.dev)))
-                    allp.ops.extend(plan.ops)
+                    allp.main_ops.extend(plan.ops)
                 self._plans[key] = dict(plan=allp, ws=None, io=io, graph=None, warm=0, parts=parts)
         return self._plans[key]
 

@@ -50,24 +50,75 @@ class Op:
 
 
 class Plan:
-    """Ordered list of Ops replayed on one stream."""
+    """Ordered list of Ops replayed on one stream, plus an optional SIDE branch: ops added inside ``with plan.side():``
+    run on a second stream, forked at the start of the plan and joined where ``plan.join()`` was called.  (LNet: the
+    audio encoder and the AdaIN MLPs are a chain of small-grid kernels that only the decoder needs - they overlap the
+    visual encoder instead of serialising ~16 launches in front of it.)"""
 
     def __init__(self):
-        self.ops: list[Op] = []
+        self.main_ops: list[Op] = []
+        self.side_ops: list[Op] = []
+        self._target = self.main_ops
+        self.join_at = None
+        self._side_stream = None
+
+    @property
+    def ops(self) -> list[Op]:
+        return self.side_ops + self.main_ops
 
     def add(self, op: Op) -> Op:
-        self.ops.append(op)
+        self._target.append(op)
         return op
 
+    def side(self):
+        plan = self
+
+        class _Side:
+            def __enter__(self_inner):
+                plan._target = plan.side_ops
+
+            def __exit__(self_inner, *a):
+                plan._target = plan.main_ops
+        return _Side()
+
+    def join(self):
+        """Everything added to the main branch from here on may consume the side branch's results."""
+        if self.join_at is None:
+            self.join_at = len(self.main_ops)
+
     def run(self, stream=None):
-        s = stream if stream is not None else cur_stream()
-        for op in self.ops:
-            rc = op.fn(*op.args, s)
+        if not self.side_ops or stream is not None:
+            s = stream if stream is not None else cur_stream()
+            for op in self.side_ops + self.main_ops:
+                rc = op.fn(*op.args, s)
+                if rc != 0:
+                    L.check(rc, op.name)
+            return
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=main.device)
+        side = self._side_stream
+        fork, joined = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        ss, ms = C.c_void_p(side.cuda_stream), C.c_void_p(main.cuda_stream)
+        for op in self.side_ops:
+            rc = op.fn(*op.args, ss)
             if rc != 0:
                 L.check(rc, op.name)
+        joined.record(side)
+        join_at = len(self.main_ops) if self.join_at is None else self.join_at
+        for i, op in enumerate(self.main_ops):
+            if i == join_at:
+                main.wait_event(joined)
+            rc = op.fn(*op.args, ms)
+            if rc != 0:
+                L.check(rc, op.name)
+        if join_at >= len(self.main_ops):
+            main.wait_event(joined)
 
     def __len__(self):
-        return len(self.ops)
+        return len(self.side_ops) + len(self.main_ops)
 
 
 def conv_box(h: int, w: int, k=(1, 1), stride=(1, 1), dil=(1, 1)) -> tuple[int, int, int]:
