@@ -7,7 +7,7 @@ from s2v_b200 import _lib as L, ops
 
 lib = L.require_device(0)
 torch.manual_seed(0)
-B = 128
+B = int(os.environ.get("MB_B", "128"))
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 
 
@@ -19,10 +19,18 @@ def bench(name, x, w, y, reps=20, **kw):
         op.run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        op.run()
-    b.record(); torch.cuda.synchronize()
+    if os.environ.get("MB_GRAPH", "0") == "1":      # GPU-side cost only: the launches are replayed from a CUDA graph
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                op.run()
+        g.replay(); torch.cuda.synchronize()
+        a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+    else:
+        a.record()
+        for _ in range(reps):
+            op.run()
+        b.record(); torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / reps
     print("%-40s %8.1f us  %7.1f TFLOP/s" % (name, us, op.alg_flops / us / 1e6), flush=True)
 
