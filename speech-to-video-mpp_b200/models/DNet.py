@@ -153,6 +153,10 @@ class DNetEngine(EngineBase):
             hd = self.W["adain.heads"]
             plan.add(ops.op_grouped_linear(lib, hidden, hd["groups"], hd["tiles"], hd["n_tiles"], gb))
 
+            def adain_fin(tag):
+                off, c = self.gb_off[tag]
+                return ("adain", gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0))
+
             def adain(tag, x, y, act=L.ACT_LRELU, res=None, stats=None):
                 off, c = self.gb_off[tag]
                 return self.adain(plan, ws, tag, x, gb[:, off:off + c], gb[:, off + c:off + 2 * c], gb.stride(0), y,
@@ -175,7 +179,7 @@ class DNetEngine(EngineBase):
                 xa = buf(p + ".a0", (B, s, s, cin))
                 adain(p + ".norm_0", x, xa)
                 y0 = buf(p + ".y0", (B, s // 2, s // 2, cout))
-                st = self.conv_stats(plan, ws, p + ".conv_0", xa, y0, stride=(2, 2), pad=(1, 1))
+                st = self.conv_stats(plan, ws, p + ".conv_0", xa, y0, stride=(2, 2), pad=(1, 1), fin=adain_fin(p + ".norm_1"))
                 ya = buf(p + ".a1", (B, s // 2, s // 2, cout))
                 adain(p + ".norm_1", y0, ya, stats=st)
                 y1 = enc_out.get(i) if i in enc_out else buf(p + ".y1", (B, s // 2, s // 2, cout))
@@ -192,7 +196,7 @@ class DNetEngine(EngineBase):
                     for qh in (0, 1):
                         self.conv(plan, f"{p}.conv_s.ph{ph}{qh}", xs_a, dst[:, ph::2, qh::2, :])
                 d0 = buf(p + ".d0", (B, s, s, cout))
-                st = self.conv_stats(plan, ws, p + ".conv_0", x0_a, d0, pad=(1, 1))
+                st = self.conv_stats(plan, ws, p + ".conv_0", x0_a, d0, pad=(1, 1), fin=adain_fin(p + ".norm_1"))
                 d0a = buf(p + ".d0a", (B, s, s, cout))
                 adain(p + ".norm_1", d0, d0a, stats=st)
                 for ph in (0, 1):                                # main branch, accumulated onto the shortcut
@@ -220,7 +224,7 @@ class DNetEngine(EngineBase):
             win = torch.as_strided(xp, (B, 262, 256, 64), (xp.stride(0), xp.stride(1), 8, 1))
             p = e + ".encoder.first.model"
             raw = buf("ed.raw0", (B, 256, 256, 64))
-            st = self.conv_stats(plan, ws, p, win, raw, pad=(0, 0), cin_true=6 * 7)
+            st = self.conv_stats(plan, ws, p, win, raw, pad=(0, 0), cin_true=6 * 7, fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
             f0 = buf("ed.f0", (B, 256, 256, 64))
             self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], f0, stats=st)
             feats, x = [f0], f0
@@ -228,7 +232,7 @@ class DNetEngine(EngineBase):
                 p = f"{e}.encoder.down{i}.model"
                 s, co = 256 >> i, min(128 << i, 256)
                 raw = buf(f"ed.raw{i + 1}", (B, s, s, co))
-                st = self.conv_stats(plan, ws, p, x, raw, pad=(1, 1))
+                st = self.conv_stats(plan, ws, p, x, raw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 y = buf(f"ed.f{i + 1}", (B, s // 2, s // 2, co))
                 self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], y, pool2=1, stats=st)
                 feats.append(y)
@@ -239,7 +243,7 @@ class DNetEngine(EngineBase):
                 for b in range(2):
                     p = f"{e}.decoder.res{i}.res{b}"
                     raw = buf(f"ed.res{i}.raw", (B, s, s, c))
-                    st = self.conv_stats(plan, ws, p + ".conv2", out, raw, pad=(1, 1))
+                    st = self.conv_stats(plan, ws, p + ".conv2", out, raw, pad=(1, 1), fin=adain_fin(p + ".norm2"))
                     y = buf(f"ed.res{i}.o{b}", (B, s, s, c))
                     adain(p + ".norm2", raw, y, act=L.ACT_NONE, res=out, stats=st)          # dx + x, no activation (quirk C.3)
                     out = y
@@ -249,12 +253,12 @@ class DNetEngine(EngineBase):
                 for ph in (0, 1):
                     for qh in (0, 1):
                         st = self.conv_stats(plan, ws, f"{p}.ph{ph}{qh}", out, uraw[:, ph::2, qh::2, :], tag=p, phase=2 * ph + qh, phases=4,
-                                             pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0)
+                                             pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0, fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 uact = buf(f"ed.up{i}.act", (B, 2 * s, 2 * s, co))
                 self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact, stats=st)
                 p = f"{e}.decoder.jump{i}.model"
                 jraw = buf(f"ed.jump{i}.raw", (B, 2 * s, 2 * s, co))
-                st = self.conv_stats(plan, ws, p, feats.pop(), jraw, pad=(1, 1))
+                st = self.conv_stats(plan, ws, p, feats.pop(), jraw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 nxt = buf(f"ed.dec{i}.out", (B, 2 * s, 2 * s, co))
                 self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], nxt, res=uact, stats=st)
                 out = nxt

@@ -170,7 +170,7 @@ class LNetEngine(EngineBase):
             for t, c_lo in (("inp", 0), ("ref", 3)):       # masked face = planes 0-2, reference = planes 3-5
                 p = f"encoder.first_{t}.model"
                 raw = buf("enc.raw0", (B, 96, 96, 64))
-                st = self.stem_conv(plan, ws, p, face_in[:, c_lo:c_lo + 3], raw, stats=True)
+                st = self.stem_conv(plan, ws, p, face_in[:, c_lo:c_lo + 3], raw, stats=True, fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 a0 = buf(f"enc.{t}.a0", (B, 96, 96, 64))
                 self.layernorm2d(plan, ws, p, raw, self.P[p + ".g"], self.P[p + ".b"], a0, stats=st)
                 x = a0
@@ -180,7 +180,7 @@ class LNetEngine(EngineBase):
                     p = f"encoder.{t}_down{i}.model"
                     s, co = 96 >> i, 128 << i
                     raw = buf(f"enc.raw{i + 1}", (B, s, s, co))
-                    st = self.conv_stats(plan, ws, p, x, raw, pad=(1, 1))
+                    st = self.conv_stats(plan, ws, p, x, raw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                     if i < 2:
                         y = buf(f"enc.{t}.a{i + 1}", (B, s // 2, s // 2, co))
                         if t == "inp":
@@ -239,9 +239,11 @@ class LNetEngine(EngineBase):
                             merged = (q + ".all") in self.W
                             fz = ops.stats_fusable(lib, cl) and ops.stats_fusable(lib, cg)    # both halves of R or neither
                             st = None
+                            off = self.gb_off[p]
+                            fin = ("adain", gb[bs, off:off + c], gb[bs, off + c:off + 2 * c], gb.stride(0))
                             Rb, s1b, s2b, F1b, F2b = R[:nb], s1[:nb], s2[:nb], F1[:nb], F2[:nb]   # scratch: same (L2-hot) memory for every sub-batch
                             if not merged:
-                                st = self.conv_stats(plan, ws, q + ".to_l", src, Rb[..., :cl], tag=tg, c_total=c, fuse=fz)   # l2l + g2l, 3x3 reflect
+                                st = self.conv_stats(plan, ws, q + ".to_l", src, Rb[..., :cl], tag=tg, c_total=c, fuse=fz, fin=fin)   # l2l + g2l, 3x3 reflect
                             if self.impl != "tc":
                                 self.conv(plan, q + ".l2g", src[..., :cl], Rb[..., cl:])        # l2g, 3x3 reflect
                             self.conv(plan, q + ".st1", inter[..., cl:], s1b, act=L.ACT_RELU)   # 1x1 + BN + ReLU
@@ -251,11 +253,11 @@ class LNetEngine(EngineBase):
                             if merged:                                                         # whole spatial FFC + conv2 in one GEMM
                                 npx = nb * S * S
                                 nfrom = -(-cl // 64) * 64            # x_g channels from here on reach only the cl local outputs
-                                st = self.conv_stats(plan, ws, q + ".all", src, Rb, tag=tg, c_total=c, x2=s2b,
+                                st = self.conv_stats(plan, ws, q + ".all", src, Rb, tag=tg, c_total=c, x2=s2b, fin=fin,
                                                      narrow=(nfrom, cl) if (nfrom < c and cl % 32 == 0) else None,
                                                      alg_flops=2.0 * npx * (9 * (c * cl + cl * cg) + ch * cg))
                             elif self.impl == "tc":                                            # l2g + conv2 in one GEMM
-                                self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], Rb[..., cl:], tag=tg, c_total=c, c_off=cl, fuse=fz, x2=s2b)
+                                self.conv_stats(plan, ws, q + ".l2g", src[..., :cl], Rb[..., cl:], tag=tg, c_total=c, c_off=cl, fuse=fz, x2=s2b, fin=fin)
                             else:
                                 self.conv(plan, q + ".st2", s2b, Rb[..., cl:], res2=Rb[..., cl:])  # + l2g partial sum
                             off = self.gb_off[p]
@@ -272,7 +274,8 @@ class LNetEngine(EngineBase):
                     for ph in (0, 1):
                         for qh in (0, 1):
                             st = self.conv_stats(plan, ws, f"{p}.ph{ph}{qh}", dec_out, uraw[:, ph::2, qh::2, :], tag=p,
-                                                 phase=2 * ph + qh, phases=4, pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0)
+                                                 phase=2 * ph + qh, phases=4, pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0,
+                                                 fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 else:
                     self.conv(plan, p, dec_out, uraw, pad=(1, 1), up2=1)
                     st = None
@@ -280,7 +283,7 @@ class LNetEngine(EngineBase):
                 self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact, stats=st)
                 p = f"decoder.jump{i}.model"
                 jraw = buf(f"dec{i}.jraw", (B, S2, S2, co))
-                st = self.conv_stats(plan, ws, p, skips[i], jraw, pad=(1, 1))
+                st = self.conv_stats(plan, ws, p, skips[i], jraw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 if i > 0:
                     xps = [buf(f"dec{i - 1}.xp{j}", (B, S2 + 2, S2 + 2, co), zero=True) for j in range(3)]
                     self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], xps[0][:, 1:-1, 1:-1, :],

@@ -92,7 +92,7 @@ class EngineBase:
         kw.setdefault("scale", e["scale"])
         return plan.add(ops.op_conv(self.lib, x, e["w"], y, impl=e["impl"], name=name, **kw))
 
-    def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3, stats=False):
+    def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3, stats=False, fin=None):
         """k x k zero-padded stem conv on a tiny-Cin NCHW float input (FirstBlock2d / input_layer,
         models/base_blocks.py:79-92,312).  tc path: the input is packed to 8 channels into a buffer
         padded by k//2; one row tap's k x 8 = 56 (+8 zero-weight) consecutive values are exactly one
@@ -109,15 +109,17 @@ class EngineBase:
         plan.add(ops.op_pack(self.lib, src_nchw, xp[:, pad:pad + h, pad:pad + w, :], 0, 8))
         win = torch.as_strided(xp, (n, h + 2 * pad, w, 64), (xp.stride(0), xp.stride(1), 8, 1))
         if stats:
-            return self.conv_stats(plan, ws, name, win, y, pad=(0, 0), cin_true=cin_true * k)
+            return self.conv_stats(plan, ws, name, win, y, pad=(0, 0), cin_true=cin_true * k, fin=fin)
         self.conv(plan, name, win, y, pad=(0, 0), cin_true=cin_true * k)
         return None
 
-    def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, fuse=True, **kw):
+    def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, fuse=True, fin=None, **kw):
         """conv whose epilogue also emits the per-(image, spatial tile, channel) sum / sum of squares of its fp16 output
-        (tc path) - this replaces the separate full-tensor chan_stats pass.  Returns (partial, chunks) for
-        layernorm2d/adain(stats=...), or None when the statistics cannot be fused (simt path, odd tile widths,
-        S2V_FUSED_STATS=0): the caller then falls back to a chan_stats pass."""
+        (tc path) - this replaces the separate full-tensor chan_stats pass.  With ``fin`` = ("adain", gamma, beta, gb_stride)
+        or ("ln", gamma, beta) the same launch also FINALIZES them (last contributing CTA per image) into the scale / shift
+        the apply kernel consumes, so no finalize launch is needed either.
+        Returns a dict for layernorm2d/adain(stats=...), or None when the statistics cannot be fused (simt path, odd tile
+        widths, S2V_FUSED_STATS=0): the caller then falls back to a chan_stats pass."""
         n, h, w, c = y.shape
         ct = c_total or c
         if self.W[name]["impl"] != "tc" or os.environ.get("S2V_FUSED_STATS", "1") != "1" or not fuse or not ops.stats_fusable(self.lib, c):
@@ -125,53 +127,68 @@ class EngineBase:
             return None
         k = kw.get("k", self.W[name]["k"])
         tiles = ops.box_tiles(h, w, n, k, kw.get("stride", (1, 1)), kw.get("dil", (1, 1)))
-        partial = self.buf(ws, (tag or name) + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
-        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), **kw)
-        return partial, tiles * phases
+        t = tag or name
+        partial = self.buf(ws, t + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
+        st = dict(partial=partial, chunks=tiles * phases, done=False)
+        f = None
+        # In-kernel finalize: opt-in.  Measured on B200 (LNet B=128): 435 instead of 503 launches but 14.49 vs 14.03 ms/step -
+        # the grid-wide barrier + finalize at the conv's tail costs more than the tiny finalize kernel it removes (which
+        # overlaps its launch with the conv's drain through PDL).  Never with two full-size kernels racing for the SMs.
+        if fin is not None and os.environ.get("S2V_FUSED_FINALIZE", "0") == "1" and self.streams == 1:
+            a = self.buf(ws, t + ".a", (n, ct), torch.float32)
+            b = self.buf(ws, t + ".b", (n, ct), torch.float32)
+            st.update(a=a, b=b, done=True)
+            if phase == phases - 1:         # the launch that completes the partials finalizes them (stream order)
+                counter = self.buf(ws, f"{name}.fin_counter", (2,), torch.int32, zero=True)
+                if fin[0] == "adain":
+                    f = dict(mode="adain", gamma=fin[1], beta=fin[2], gb_stride=fin[3], count=h * w * phases)
+                else:
+                    f = dict(mode="ln", gamma=fin[1], beta=fin[2], count=h * w * phases * ct)
+                f.update(a=a, b=b, counter=counter)
+        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), fin=f, **kw)
+        return st
 
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):
         n, h, w, c = x.shape
         chunks = ops.stats_chunks(n, h * w, c)
         partial = self.buf(ws, tag + ".partial", (n, chunks, c, 2), torch.float32)
-        a = self.buf(ws, tag + ".a", (n, c), torch.float32)
-        b = self.buf(ws, tag + ".b", (n, c), torch.float32)
         plan.add(ops.op_chan_stats(self.lib, x, chunks, partial))
-        return partial, chunks, a, b
+        return dict(partial=partial, chunks=chunks, done=False)
+
+    def _ab(self, ws, tag, st, n, c):
+        if st.get("done"):
+            return st["a"], st["b"]
+        return self.buf(ws, tag + ".a", (n, c), torch.float32), self.buf(ws, tag + ".b", (n, c), torch.float32)
 
     def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0, stats=None):
         """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124).
-        ``stats``: (partial, chunks) already produced by the conv epilogue."""
+        ``stats``: what conv_stats returned for the producer of x (partials, possibly already finalized)."""
         n, h, w, c = x.shape
-        if stats is None:
-            partial, chunks, a, b = self._stats(plan, ws, tag, x)
-        else:
-            partial, chunks = stats
-            a = self.buf(ws, tag + ".a", (n, c), torch.float32)
-            b = self.buf(ws, tag + ".b", (n, c), torch.float32)
-        plan.add(ops.op_ln2d_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, a, b))
+        st = stats if stats is not None else self._stats(plan, ws, tag, x)
+        a, b = self._ab(ws, tag, st, n, c)
+        if not st.get("done"):
+            plan.add(ops.op_ln2d_finalize(self.lib, st["partial"], n, st["chunks"], c, h * w, gamma, beta, a, b))
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=L.ACT_LRELU, act_param=slope, pool2=pool2, res=res,
                                    reflect1=reflect1))
 
     def adain(self, plan, ws, tag, x, gamma, beta, gb_stride, y, *, act=L.ACT_LRELU, slope=0.01, res=None, reflect1=0,
               stats=None):
         """InstanceNorm2d*(1+gamma)+beta + activation [+ res] (base_blocks.py:127-157).
-        ``stats``: reuse the (partial, chunks) of an earlier call on the same x (two AdaINs of one tensor)."""
+        ``stats``: what conv_stats returned for the producer of x, or the return value of an earlier adain() on the same x
+        (two AdaINs of one tensor share the partials, not the finalized scale / shift)."""
         n, h, w, c = x.shape
         if stats is None and act in (L.ACT_NONE, L.ACT_LRELU, L.ACT_RELU) and self.lib.s2v_adain_fused_fits(h, w, c) > 0 \
                 and os.environ.get("S2V_ADAIN_FUSED", "0") == "1":
             plan.add(ops.op_adain_fused(self.lib, x, gamma, beta, gb_stride, y, act=act, act_param=slope, res=res,
                                         reflect1=reflect1))
             return None
-        if stats is None:
-            partial, chunks, a, b = self._stats(plan, ws, tag, x)
-        else:
-            partial, chunks = stats
-            a = self.buf(ws, tag + ".a", (n, c), torch.float32)
-            b = self.buf(ws, tag + ".b", (n, c), torch.float32)
-        plan.add(ops.op_adain_finalize(self.lib, partial, n, chunks, c, h * w, gamma, beta, gb_stride, a, b))
+        st = stats if stats is not None else self._stats(plan, ws, tag, x)
+        a, b = self._ab(ws, tag, st, n, c)
+        if not st.get("done"):
+            plan.add(ops.op_adain_finalize(self.lib, st["partial"], n, st["chunks"], c, h * w, gamma, beta, gb_stride, a, b))
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=act, act_param=slope, res=res, reflect1=reflect1))
-        return partial, chunks
+        return dict(partial=st["partial"], chunks=st["chunks"], done=False)
 
     # ---- grouped AdaIN heads -----------------------------------------------------------
     def pack_lin_groups(self, name, groups):

@@ -98,7 +98,7 @@ def test_lnet_module_state_dict_and_plan():
     for impl in ("tc", "simt"):
         eng = LNetEngine(sd, torch.device("cpu"), conv_impl=impl)       # plan build only: validates shapes/ABI structs
         ent = eng._get_plan(3, eng._build(3))
-        assert len(ent["plan"]) > 500
+        assert len(ent["plan"]) > (400 if impl == "tc" else 500)      # tc: statistics fused into the convs
         assert ent["io"]["out"].shape == (3, 3, 96, 96)
 
 
