@@ -142,6 +142,106 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) flow_warp_kernel(const f
   sample_store<4>(src + (size_t)b * C * H * W, out + (size_t)b * C * H * W, C, H, W, Y, X, gx, gy, p16);
 }
 
+// ---- 4 pixels per thread --------------------------------------------------------------------------------------------
+// The one-pixel-per-thread kernel above executes ~400 instructions per pixel (tile bounding box, scale divisions, 64-bit
+// addressing - all per thread) and is issue-bound at 1.2-1.4 TB/s whatever the flow looks like.  Here a thread owns a
+// COLUMN of 4 pixels (lanes = consecutive x, so every gather / store instruction of a warp touches one or two 128-byte
+// lines when the flow is smooth): the per-thread setup and the column interpolation are shared, the resize scales come
+// precomputed from the host (same fp32 divisions), offsets are 32-bit and the 48 gathers of the 4 pixels are issued
+// before any arithmetic.  Arithmetic (operation order, rounding) is identical to the kernel above.
+constexpr int kW4BX = 32, kW4BY = 4, kW4Cells = 16 * 12;      // block = 32 x 16 pixels
+
+__global__ void __launch_bounds__(kW4BX * kW4BY) flow_warp4_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                                  float* __restrict__ out, int C, int H, int W, int h, int w,
+                                                                  View o16, int c_off, float sch, float scw, float inv_wm1,
+                                                                  float inv_hm1) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float2 s_def[kW4Cells];
+  const int b = blockIdx.z;
+  const float* fx = flow + (size_t)b * 2 * h * w;
+  const float* fy = fx + (size_t)h * w;
+  const int ty0 = blockIdx.y * (kW4BY * 4), tx0 = blockIdx.x * kW4BX;
+  // flow-cell rectangle under this tile (block-uniform)
+  const int cy_lo = min((int)fmaxf(sch * ((float)ty0 + 0.5f) - 0.5f, 0.f), h - 1);
+  const int cx_lo = min((int)fmaxf(scw * ((float)tx0 + 0.5f) - 0.5f, 0.f), w - 1);
+  const int cy_hi = min((int)fmaxf(sch * ((float)min(ty0 + kW4BY * 4, H) - 0.5f) - 0.5f, 0.f) + 1, h - 1);
+  const int cx_hi = min((int)fmaxf(scw * ((float)min(tx0 + kW4BX, W) - 0.5f) - 0.5f, 0.f) + 1, w - 1);
+  const int ncx = cx_hi - cx_lo + 1, ncy = cy_hi - cy_lo + 1;          // <= kW4Cells (checked on the host)
+  for (int i = threadIdx.y * kW4BX + threadIdx.x; i < ncx * ncy; i += kW4BX * kW4BY) {
+    const int ci = i / ncx, cj = i - ci * ncx;
+    s_def[i] = deform_at(fx, fy, cy_lo + ci, cx_lo + cj, w, inv_wm1, inv_hm1);
+  }
+  __syncthreads();
+  const int X = tx0 + threadIdx.x, Y0 = ty0 + threadIdx.y * 4;
+  if (X >= W || Y0 >= H) return;
+  // column interpolation of the deformation grid (shared by the 4 pixels)
+  const float sx = fmaxf(scw * ((float)X + 0.5f) - 0.5f, 0.f);
+  const int x0 = min((int)sx, w - 1);
+  const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f), hx = 1.f - lx;
+  const int plane = H * W;
+  const float* sb = src + (size_t)b * C * plane;
+  int off[4][4];
+  float wt[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int Y = Y0 + p;                                   // rows beyond H (H % 4 != 0 never reaches here) are not stored
+    const float sy = fmaxf(sch * ((float)Y + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)sy, h - 1);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), hy = 1.f - ly;
+    const float2* r0 = s_def + (y0 - cy_lo) * ncx - cx_lo;
+    const float2* r1 = s_def + (y1 - cy_lo) * ncx - cx_lo;
+    const float2 d00 = r0[x0], d01 = r0[x1], d10 = r1[x0], d11 = r1[x1];
+    const float gx = hy * (hx * d00.x + lx * d01.x) + ly * (hx * d10.x + lx * d11.x);
+    const float gy = hy * (hx * d00.y + lx * d01.y) + ly * (hx * d10.y + lx * d11.y);
+    // grid_sample, bilinear, zeros padding, align_corners=False (same arithmetic as sample_store)
+    float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), -1.f), 0.5f);
+    float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), -1.f), 0.5f);
+    ix = (fabsf(ix) < 1e9f) ? ix : -10.f;
+    iy = (fabsf(iy) < 1e9f) ? iy : -10.f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int ax0 = (int)fx0, ay0 = (int)fy0, ax1 = ax0 + 1, ay1 = ay0 + 1;
+    const bool vx0 = (ax0 >= 0) & (ax0 < W), vx1 = (ax1 >= 0) & (ax1 < W);
+    const bool vy0 = (ay0 >= 0) & (ay0 < H), vy1 = (ay1 >= 0) & (ay1 < H);
+    wt[p][0] = (vy0 & vx0) ? wx0 * wy0 : 0.f; wt[p][1] = (vy0 & vx1) ? wx1 * wy0 : 0.f;
+    wt[p][2] = (vy1 & vx0) ? wx0 * wy1 : 0.f; wt[p][3] = (vy1 & vx1) ? wx1 * wy1 : 0.f;
+    const int cx0 = min(max(ax0, 0), W - 1), cx1 = min(max(ax1, 0), W - 1);
+    const int cy0 = min(max(ay0, 0), H - 1) * W, cy1 = min(max(ay1, 0), H - 1) * W;
+    off[p][0] = cy0 + cx0; off[p][1] = cy0 + cx1; off[p][2] = cy1 + cx0; off[p][3] = cy1 + cx1;
+  }
+  const int po = Y0 * W + X;
+  float* ob = out + (size_t)b * C * plane + po;
+  __half* p16 = o16.p ? o16.p + (size_t)b * o16.sn + (size_t)Y0 * o16.sh + (size_t)X * o16.sw + c_off : nullptr;
+  for (int c0 = 0; c0 < C; c0 += 3) {              // 3 planes at a time: 48 gathers in flight
+    float v[3][4][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) {
+        const float* sp = sb + (c0 + c) * plane;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v[c][p][t] = __ldg(sp + off[p][t]);
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {               // same accumulation order as the reference kernel: nw, ne, sw, se
+          float a = v[c][p][0] * wt[p][0];
+          a += v[c][p][1] * wt[p][1];
+          a += v[c][p][2] * wt[p][2];
+          a += v[c][p][3] * wt[p][3];
+          ob[(c0 + c) * plane + p * W] = a;
+          if (p16) p16[(size_t)p * o16.sh + c0 + c] = __float2half_rn(a);
+        }
+      }
+  }
+}
+
 __global__ void flow_to_deformation_kernel(const float* __restrict__ flow, float* __restrict__ def, int h, int w) {
   pdl_trigger();
   pdl_wait();
@@ -190,6 +290,15 @@ extern "C" int s2v_flow_warp_f32(const float* src, const float* flow, float* out
   if (B > 65535 || H > 65535) return S2V_EINVAL;
   View o16 = mk(out16);
   if (out16 && out16->ptr && (out16->n < B || out16->h != H || out16->w != W || c_off + C > out16->c)) return S2V_EINVAL;
+  const float sch = (float)h / (float)H, scw = (float)w / (float)W;
+  const bool fits4 = ((int)(scw * kW4BX) + 3) * ((int)(sch * (kW4BY * 4)) + 3) <= kW4Cells;
+  if (!(h == H && w == W) && H % 4 == 0 && fits4 && (long long)C * H * W < (1ll << 31) && !getenv("S2V_WARP1")) {
+    dim3 grid(ceil_div(W, kW4BX), ceil_div(H, kW4BY * 4), B);
+    launch_pdl(flow_warp4_kernel, grid, dim3(kW4BX, kW4BY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16, c_off, sch, scw,
+               1.f / (float)(w - 1), 1.f / (float)(h - 1));
+    S2V_CHECK_LAUNCH();
+    return S2V_OK;
+  }
   dim3 grid(ceil_div(W, kWarpBX), ceil_div(H, kWarpBY), B);
   launch_pdl(flow_warp_kernel, grid, dim3(kWarpBX, kWarpBY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16, c_off);
   S2V_CHECK_LAUNCH();
