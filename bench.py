@@ -291,10 +291,16 @@ def main():
                     g.replay()
                 b.record(side)
                 torch.cuda.synchronize(dev)
-            acc[cls] = [a.elapsed_time(b) / reps, len(cops), sum(getattr(op, "alg_flops", 0.0) for op in cops)]
+            acc[cls] = [a.elapsed_time(b) / reps, len(cops), sum(getattr(op, "alg_flops", 0.0) for op in cops),
+                        sum(getattr(op, "alg_bytes", 0.0) for op in cops)]
         total = sum(v[0] for v in acc.values())
-        table = {k: {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)} for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
         peaks = _peaks()
+        table = {}
+        for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+            table[k] = {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)}
+            if v[3] > 0:       # memory-bound class: algorithmic bytes (each tensor read / written once) against the measured HBM peak
+                gbs = v[3] / (v[0] * 1e-3) / 1e9
+                table[k].update({"GBps_algorithmic": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)})
         tc = acc.get("conv_tc")
         if tc:
             ach = tc[2] / (tc[0] * 1e-3) / 1e12

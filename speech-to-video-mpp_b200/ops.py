@@ -44,6 +44,7 @@ class Op:
     fn: object
     args: tuple
     keep: tuple = field(default_factory=tuple, repr=False)
+    alg_bytes: float = 0.0      # algorithmic HBM bytes of a memory-bound op: every input read once + every output written once
 
     def run(self, stream=None):
         L.check(self.fn(*self.args, stream if stream is not None else cur_stream()), self.name)
@@ -251,7 +252,9 @@ def stats_chunks(n: int, hw: int, c: int = 64) -> int:
 
 def op_chan_stats(lib, x, chunks, partial) -> Op:
     v = view(x)
-    return Op("chan_stats", lib.s2v_chan_stats, (C.byref(v), chunks, _ptr(partial)), (v, x, partial))
+    op = Op("chan_stats", lib.s2v_chan_stats, (C.byref(v), chunks, _ptr(partial)), (v, x, partial))
+    op.alg_bytes = 2.0 * x.numel()
+    return op
 
 
 def op_ln2d_finalize(lib, partial, n, chunks, c, count, gamma, beta, a, b, eps=1e-5) -> Op:
@@ -269,9 +272,12 @@ def op_adain_finalize(lib, partial, n, chunks, c, count, gamma, beta, gb_stride,
 def op_affine_act(lib, x, a, b, y, *, act=L.ACT_NONE, act_param=0.0, pool2=0, res=None, reflect1=0) -> Op:
     vx, vy = view(x), view(y)
     vr = view(res) if res is not None else null_view()
-    return Op("affine_act", lib.s2v_affine_act,
-              (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), pool2, C.byref(vr), C.byref(vy), reflect1),
-              (vx, vy, vr, x, y, res, a, b))
+    op = Op("affine_act", lib.s2v_affine_act,
+            (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), pool2, C.byref(vr), C.byref(vy), reflect1),
+            (vx, vy, vr, x, y, res, a, b))
+    pad = (y.shape[1] + 2) * (y.shape[2] + 2) / float(y.shape[1] * y.shape[2]) if reflect1 else 1.0
+    op.alg_bytes = 2.0 * (x.numel() + (res.numel() if res is not None else 0) + y.numel() * pad)
+    return op
 
 
 def op_adain_fused(lib, x, gamma, beta, gb_stride, y, *, act=L.ACT_NONE, act_param=0.0, res=None, reflect1=0, eps=1e-5) -> Op:
@@ -284,8 +290,10 @@ def op_adain_fused(lib, x, gamma, beta, gb_stride, y, *, act=L.ACT_NONE, act_par
 
 def op_token_ln(lib, x, gamma, beta, y, eps=1e-5) -> Op:
     vx, vy = view(x), view(y)
-    return Op("token_layernorm", lib.s2v_token_layernorm, (C.byref(vx), _ptr(gamma), _ptr(beta), eps, C.byref(vy)),
-              (vx, vy, x, y, gamma, beta))
+    op = Op("token_layernorm", lib.s2v_token_layernorm, (C.byref(vx), _ptr(gamma), _ptr(beta), eps, C.byref(vy)),
+            (vx, vy, x, y, gamma, beta))
+    op.alg_bytes = 2.0 * (x.numel() + y.numel())
+    return op
 
 
 def op_add(lib, a, b, y) -> Op:
@@ -300,13 +308,17 @@ def op_reflect_border(lib, interior) -> Op:
 
 def op_rfft2(lib, x, spec) -> Op:
     vx, vs = view(x), view(spec)
-    return Op("rfft2", lib.s2v_rfft2, (C.byref(vx), C.byref(vs)), (vx, vs, x, spec))
+    op = Op("rfft2", lib.s2v_rfft2, (C.byref(vx), C.byref(vs)), (vx, vs, x, spec))
+    op.alg_bytes = 2.0 * (x.numel() + spec.numel())
+    return op
 
 
 def op_irfft2(lib, spec, add, y) -> Op:
     vs, vy = view(spec), view(y)
     va = view(add) if add is not None else null_view()
-    return Op("irfft2", lib.s2v_irfft2, (C.byref(vs), C.byref(va), C.byref(vy)), (vs, va, vy, spec, add, y))
+    op = Op("irfft2", lib.s2v_irfft2, (C.byref(vs), C.byref(va), C.byref(vy)), (vs, va, vy, spec, add, y))
+    op.alg_bytes = 2.0 * (spec.numel() + (add.numel() if add is not None else 0) + y.numel())
+    return op
 
 
 def op_attention(lib, q, k, v, o, heads, scale) -> Op:
