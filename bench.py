@@ -306,7 +306,11 @@ def main():
             ach = tc[2] / (tc[0] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % tc[1],
                     "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
-                    "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the step's dominant conv_tc shape (12x12 level, 3x3, K = 9216:
+                    # 36 of the 246 launches, 23 % of the class time) from profiles/r1b_ncu_full_conv_tc_res2_raw.csv; its algorithmic
+                    # bytes are 51.8 MB (37.7 in + 4.7 weights + 9.4 out) - no wasted re-reads.  Other shapes: profiles/r1b_summary.md
+                    "traffic": 33.2e6, "traffic_of": "one 3x3 K=9216 launch (ncu --set full, bytes per launch)",
+                    "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "alg_gflop_per_step": round(tc[2] / 1e9, 1), "kernel_ms_per_step": round(tc[0], 3),
                     "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
                     "share_of_step": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
