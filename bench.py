@@ -199,7 +199,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("S2V_NCCL_DEBUG", "WARN")   # keep NCCL's banner out of the one-line JSON stdout
+        # keep NCCL's banner ("NCCL version ...", printed to stdout at NCCL_DEBUG >= VERSION) out of the one-line JSON stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("S2V_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import s2v_b200  # noqa: F401
