@@ -270,6 +270,11 @@ class DNetEngine(EngineBase):
 
     def forward(self, img, coeff, stage=None):
         B, T = img.shape[0], coeff.shape[2]
+        if B == 0:                                  # empty batch: empty outputs with the reference's shapes
+            out = {"flow_field": img.new_empty(0, 2, 64, 64), "warp_image": img.new_empty(0, 3, 256, 256)}
+            if stage != "warp":
+                out["fake_image"] = img.new_empty(0, 3, 256, 256)
+            return out
         key = (B, T, "warp" if stage == "warp" else "full")
         ent = self._get_plan(key, self._build(B, T, key[2]))
         io = ent["io"]

@@ -305,6 +305,8 @@ class LNetEngine(EngineBase):
     def forward(self, mel, face):
         """mel [B,1,80,16], face [B,6,96,96] float32 CUDA -> [B,3,96,96] float32 (a fresh tensor)."""
         B = mel.shape[0]
+        if B == 0:                                  # empty batch: the reference returns an empty tensor
+            return torch.empty(0, 3, 96, 96, dtype=torch.float32, device=mel.device)
         ent = self.plan_for(B)
         io = ent["io"]
         io["mel"].copy_(mel, non_blocking=True)

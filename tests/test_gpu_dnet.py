@@ -71,6 +71,14 @@ def test_dnet_vs_oracle_batch_and_stage(env):
     assert (again - out["warp_image"]).abs().max().item() < 1e-5
 
 
+def test_dnet_empty_batch(env):
+    G, sd, net = env
+    out = net(torch.zeros(0, 3, 256, 256, device="cuda"), torch.zeros(0, 73, 26, device="cuda"))
+    assert out["flow_field"].shape == (0, 2, 64, 64) and out["warp_image"].shape == (0, 3, 256, 256) and out["fake_image"].shape == (0, 3, 256, 256)
+    out = net(torch.zeros(0, 3, 256, 256, device="cuda"), torch.zeros(0, 73, 26, device="cuda"), stage="warp")
+    assert "fake_image" not in out
+
+
 def test_dnet_errors(env):
     G, sd, net = env
     with pytest.raises(RuntimeError):

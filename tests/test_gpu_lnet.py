@@ -76,6 +76,19 @@ def test_lnet_vs_oracle_ragged_batch_and_5d(env):
     assert torch.equal(out5[:, :, 0], out[:2]) and torch.equal(out5[:, :, 1], out[2:4])
 
 
+def test_lnet_empty_and_single_frame(env):
+    """Edge cases: an empty batch gives an empty tensor (no launch), a single frame equals that frame of a larger batch."""
+    G, sd, net = env
+    from oracle import synth
+    mel, face = synth.lnet_inputs(3, seed=5)
+    mel, face = mel.cuda(), face.cuda()
+    e = net(mel[:0], face[:0])
+    assert e.shape == (0, 3, 96, 96) and e.dtype == torch.float32
+    full = net(mel, face)
+    one = net(mel[1:2], face[1:2])
+    assert one.shape == (1, 3, 96, 96) and torch.equal(one, full[1:2])
+
+
 def test_lnet_simt_path_agrees(env):
     """The SIMT convolution path (every conv on CUDA cores, fp32 weights) is an independent
     implementation of the same layers; both must sit on the oracle."""
