@@ -206,6 +206,13 @@ int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, void* stream
 /* N tile (BN) s2v_conv_tc picks for a given Cout (host-side sizing of the statistics groups) */
 int s2v_conv_tc_tile_n(int cout);
 
+/* 7x7, stride 1, pad 3 "head" convolutions with Cout <= 8 (FinalBlock2d, models/base_blocks.py:444-457; flow_out,
+ * models/DNet.py:72-76) on tcgen05 with the kx taps folded into the GEMM's N dimension (7x fewer MMAs than
+ * s2v_conv_tc).  d->x: fp16 NHWC, C a multiple of 64; d->out_mode = S2V_OUT_F32_NCHW, d->y = {n, h, w, c = Cout} shape
+ * only, d->y_f32 [N][Cout][H][W]; bias optional; act NONE / RELU / LRELU / SIGMOID / TANH.
+ * d->w: fp16 [64][chunks*7*64]: row kx*8 + co, column (chunk*7 + ky)*64 + ci; rows 56..63 and co >= Cout zero.   */
+int s2v_conv_head(const s2v_conv* d, void* stream);
+
 /* grouped small linears (all AdaIN gamma/beta heads of a net in one launch,
  * models/base_blocks.py:136-141,149-151):
  *   out[b][g.out_off + j] = bias_g[j] + sum_k hidden[b][g.in_off + k] * wt_g[k][j]

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "s2v_conv_simt": (C.c_int, [C.POINTER(Conv), c_vp]),
     "s2v_conv_tc": (C.c_int, [C.POINTER(Conv), C.c_int, C.c_int, C.c_int, c_vp]),
     "s2v_conv_tc_tile_n": (C.c_int, [C.c_int]),
+    "s2v_conv_head": (C.c_int, [C.POINTER(Conv), c_vp]),
     "s2v_grouped_linear": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_i64, c_vp]),
     "s2v_chan_stats": (C.c_int, [VP, C.c_int, c_vp, c_vp]),
     "s2v_ln2d_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),

@@ -207,7 +207,7 @@ class DNetEngine(EngineBase):
             p = "warpping_net.flow_out"
             fa = buf("wd.flow_in", (B, 64, 64, 256))
             self.layernorm2d(plan, ws, p, x, self.P[p + ".g"], self.P[p + ".b"], fa)
-            self.conv(plan, p + ".2", fa, None, pad=(3, 3), y_f32=flow, out_shape=(B, 2, 64, 64))
+            self.head_conv(plan, p + ".2", fa, flow)
             io = dict(img=img, coeff=coeff, flow=flow, warp=warp)
             if stage == "warp":
                 plan.add(ops.op_flow_warp(lib, img, flow, warp))
@@ -262,8 +262,7 @@ class DNetEngine(EngineBase):
                 nxt = buf(f"ed.dec{i}.out", (B, 2 * s, 2 * s, co))
                 self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], nxt, res=uact, stats=st)
                 out = nxt
-            self.conv(plan, e + ".decoder.final.model.0", out, None, pad=(3, 3), act=L.ACT_TANH, y_f32=fake,
-                      out_shape=(B, 3, 256, 256))
+            self.head_conv(plan, e + ".decoder.final.model.0", out, fake, act=L.ACT_TANH)
             return io
 
         return builder

@@ -291,8 +291,7 @@ class LNetEngine(EngineBase):
                 else:
                     last = buf("dec.last", (B, 96, 96, 64))
                     self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uact, stats=st)
-            self.conv(plan, "decoder.final.model.0", last, None, pad=(3, 3), act=L.ACT_SIGMOID, y_f32=out,
-                      out_shape=(B, 3, 96, 96))
+            self.head_conv(plan, "decoder.final.model.0", last, out, act=L.ACT_SIGMOID)
             return dict(mel=mel_in, face=face_in, out=out)
 
         return builder

@@ -78,6 +78,8 @@ class EngineBase:
         ent = dict(impl=impl, k=(w.shape[2], w.shape[3]), cout=w.shape[0],
                    bias=None if bias is None else bias.float().contiguous(),
                    scale=None if scale is None else scale.float().contiguous())
+        if impl == "tc" and tuple(w.shape[2:]) == (7, 7) and w.shape[0] <= 8 and w.shape[1] % 64 == 0:
+            ent["w_f32"] = w.float()              # kept for the folded-tap head packing (ops.pack_w_head)
         if impl == "tc" and rowtaps:
             ent["w"], ent["k"] = ops.pack_w_tc_rowtaps(w, cin_pad or 8), (w.shape[2], 1)
         else:
@@ -91,6 +93,17 @@ class EngineBase:
         kw.setdefault("bias", e["bias"])
         kw.setdefault("scale", e["scale"])
         return plan.add(ops.op_conv(self.lib, x, e["w"], y, impl=e["impl"], name=name, **kw))
+
+    def head_conv(self, plan, name, x, y_f32, *, act=L.ACT_NONE, act_param=0.0):
+        """7x7 pad-3 head conv with Cout <= 8 to a float32 NCHW tensor (FinalBlock2d, flow_out): s2v_conv_head (kx taps folded
+        into N) on the tc path when the geometry allows, else the generic conv."""
+        e = self.W[name]
+        n, co, oh, ow = y_f32.shape
+        if e["impl"] == "tc" and e["k"] == (7, 7) and co <= 8 and x.shape[3] % 64 == 0 and os.environ.get("S2V_HEAD", "1") == "1":
+            if "w_head" not in e:
+                e["w_head"] = ops.pack_w_head(e["w_f32"])
+            return plan.add(ops.op_conv_head(self.lib, x, e["w_head"], y_f32, bias=e["bias"], act=act, act_param=act_param, name=name))
+        return self.conv(plan, name, x, None, pad=(3, 3), act=act, act_param=act_param, y_f32=y_f32, out_shape=(n, co, oh, ow))
 
     def stem_conv(self, plan, ws, name, src_nchw, y, *, k=7, cin_true=3, stats=False, fin=None):
         """k x k zero-padded stem conv on a tiny-Cin NCHW float input (FirstBlock2d / input_layer,

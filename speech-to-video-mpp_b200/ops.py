@@ -381,6 +381,38 @@ def pack_w_tc(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(co8, kh * kw * ci64).contiguous()
 
 
+def pack_w_head(w: torch.Tensor) -> torch.Tensor:
+    """7x7 head conv [Cout<=8, Cin, 7, 7] -> fp16 [64][chunks*7*64] for s2v_conv_head: row kx*8 + co, column
+    (chunk*7 + ky)*64 + ci (the kx taps are folded into the GEMM's N dimension)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 7 and kw == 7 and co <= 8 and ci % 64 == 0
+    chunks = ci // 64
+    out = torch.zeros(8, 8, chunks, 7, 64, dtype=torch.float16, device=w.device)          # [kx][co][chunk][ky][ci]
+    out[:7, :co] = w.reshape(co, chunks, 64, 7, 7).permute(4, 0, 1, 3, 2).to(torch.float16)   # (kx, co, chunk, ky, ci)
+    return out.reshape(64, chunks * 7 * 64).contiguous()
+
+
+def op_conv_head(lib, x, w, y_f32, *, bias=None, act=L.ACT_NONE, act_param=0.0, name="head") -> Op:
+    """x fp16 NHWC [N,H,W,Cin]; y_f32 float32 [N,Cout,H,W]; w from pack_w_head."""
+    d = L.Conv()
+    d.x = view(x)
+    n, co, oh, ow = y_f32.shape
+    d.y = L.View(None, n, oh, ow, co, 0, 0, 0)
+    d.out_mode = L.OUT_F32_NCHW
+    d.y_f32 = y_f32.data_ptr()
+    d.w = w.data_ptr()
+    d.bias = None if bias is None else bias.data_ptr()
+    d.res1, d.res2, d.x2 = null_view(), null_view(), null_view()
+    d.kh = d.kw = 7
+    d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
+    d.pad_h = d.pad_w = 3
+    d.act, d.act_param = act, float(act_param)
+    assert w.dtype == torch.float16 and tuple(w.shape) == (64, x.shape[3] // 64 * 7 * 64) and x.shape[3] % 64 == 0
+    op = Op(name + "[tc]", lib.s2v_conv_head, (C.byref(d),), (d, x, w, y_f32, bias))
+    op.alg_flops = 2.0 * n * oh * ow * co * 49 * x.shape[3]
+    return op
+
+
 def pack_w_tc_rowtaps(w: torch.Tensor, cpad: int = 8) -> torch.Tensor:
     """Stem convs with tiny Cin (3 or 6): [Cout,Cin,kh,kw] -> fp16 [Cout][kh][64] where the 64-wide K
     chunk of row tap ky holds (kx, c) = kx*cpad + c, i.e. kw consecutive pixels of a channels-last
