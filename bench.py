@@ -269,7 +269,8 @@ def main():
     roof, table = None, None
     if rank == 0:
         ops_l = ent["plan"].ops
-        cls_of = lambda op: "conv_tc" if op.name.endswith("[tc]") else "conv_simt" if op.name.endswith("[simt]") else op.name
+        cls_of = lambda op: ("conv_tc" if op.name.endswith("[tc]") else "conv_head" if op.name.endswith("[head]")
+                             else "conv_simt" if op.name.endswith("[simt]") else op.name)
         classes = {}
         for op in ops_l:
             classes.setdefault(cls_of(op), []).append(op)
@@ -297,6 +298,10 @@ def main():
                         sum(getattr(op, "alg_bytes", 0.0) for op in cops)]
         total = sum(v[0] for v in acc.values())
         peaks = _peaks()
+        # per-layer roofline of the tensor-core class: a layer cannot run faster than max(flops / tensor peak, bytes / HBM peak);
+        # many of LNet's layers (1x1 spectral convs, 48x48 / 96x96 levels with 48-128 channels) are HBM-bound by that measure
+        lay_ms = sum(max(op.alg_flops / (peaks["tf_sus"] * 1e12), op.io_bytes / (peaks["hbm"] * 1e9)) * 1e3 for op in classes.get("conv_tc", []))
+        lay_hbm = sum(1 for op in classes.get("conv_tc", []) if op.io_bytes / (peaks["hbm"] * 1e9) > op.alg_flops / (peaks["tf_sus"] * 1e12))
         table = {}
         for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0]):
             table[k] = {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)}
@@ -316,6 +321,8 @@ def main():
                     "alg_gflop_per_step": round(tc[2] / 1e9, 1), "kernel_ms_per_step": round(tc[0], 3),
                     "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
                     "share_of_step": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
+                    "per_layer_roofline": {"min_ms_per_step": round(lay_ms, 3), "frac": round(lay_ms / tc[0], 4), "hbm_bound_launches": lay_hbm,
+                                           "how": "sum over the class's launches of max(flops / tensor peak, min HBM bytes / HBM peak) / measured class time"},
                     "how": "all conv_tc launches of one step replayed from their own CUDA graph, CUDA events on that stream"}
         if args.breakdown:
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops_l]

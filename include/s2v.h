@@ -95,6 +95,18 @@ int s2v_mel_window_starts_host(int64_t n_cols, double fps, int32_t* starts_host,
 int s2v_mel_windows_f32(const float* mel, int64_t n_cols, double fps, int64_t first, int64_t count,
                         float* out, void* stream);
 
+/* ------------------------------------------------- 3DMM coefficient windows ---
+ * replaces futils/inference_utils.py:73-76 (obtain_seq_index) + :78-91 (transform_semantic), called once per
+ * frame at preprocessing/facing.py:184, for a whole batch of frames in one launch:
+ *   semantic   [n_rows, D] float32 (is_f64 = 0) or float64 (is_f64 = 1) device table, D >= 262
+ *   frame_idx  nullable int32 [count] device array of frame indices; NULL = frames first .. first+count-1
+ *   ratio      crop_norm_ratio (find_crop_norm_ratio, :93-99); applied to crop[:, 0] (column 259) in the table's
+ *              dtype when use_ratio != 0 (the reference's `if crop_norm_ratio:` truthiness is the caller's job)
+ *   out        float32 [count, 73, 26]: rows exp 80:144 | angle 224:227 | trans 254:257 | crop 259:262, columns =
+ *              table rows clamp(i-13 .. i+12, 0, n_rows-1).  Bit-exact.  count <= 65535 per call.            */
+int s2v_semantic_windows(const void* semantic, int is_f64, int n_rows, int D, const int32_t* frame_idx,
+                         int first, int count, double ratio, int use_ratio, float* out, void* stream);
+
 /* ----------------------------------------------------------- flow warp ---
  * replaces futils/flow_util.py:3-15 + :41-56 (convert_flow_to_deformation,
  * bilinear resize of the grid, F.grid_sample bilinear/zeros/align_corners=False)

@@ -20,6 +20,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
   __half* o = d.p + n * d.sn + y * d.sh + x * d.sw + c_off;
   const float* s = src + (size_t)n * src_sn + (size_t)y * W + x;
   const size_t plane = (size_t)H * W;
+  if (c_fill == 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {      // the usual stem packing: one 16-byte store
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = c < C ? fmaf(s[c * plane], scale, shift) : 0.f;
+    st_h8(o, f_to_h8(f));
+    return;
+  }
   for (int c = 0; c < c_fill; ++c) o[c] = __float2half_rn(c < C ? fmaf(s[c * plane], scale, shift) : 0.f);
 }
 

@@ -59,22 +59,24 @@ __global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict_
   }
 }
 
-// grid N, block 256: fixed-order reduction over chunks and channels (double accumulators)
-__global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
-                                                            double inv_count, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float eps,
-                                                            float* __restrict__ a, float* __restrict__ b) {
+// grid N, block T (256, or 1024 for long partial lists): fixed-order reduction over chunks and channels (double
+// accumulators).  T depends only on chunks * C (per-image geometry), never on the batch, so results are batch-independent.
+template <int T>
+__global__ void __launch_bounds__(T) ln2d_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
+                                                          double inv_count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps,
+                                                          float* __restrict__ a, float* __restrict__ b) {
   pdl_trigger();
   pdl_wait();
-  __shared__ double ss[256], sq[256];
+  __shared__ double ss[T], sq[T];
   const int n = blockIdx.x;
   double s = 0.0, q = 0.0;
-  // thread = (channel c, chunk lane): all 256 threads stream the [chunks][C][2] partials of this image with
+  // thread = (channel c, chunk lane): all T threads stream the [chunks][C][2] partials of this image with
   // 8 independent float2 loads in flight; fixed order per thread + fixed tree below => deterministic
-  const int lanes = C >= 256 ? 1 : 256 / C;                 // chunk lanes when C < 256 (C divides 256 or lanes = 1)
-  const int c_of = threadIdx.x % (lanes > 1 ? C : 256), lane = lanes > 1 ? threadIdx.x / C : 0;
+  const int lanes = C >= T ? 1 : T / C;                     // chunk lanes when C < T (C divides T or lanes = 1)
+  const int c_of = threadIdx.x % (lanes > 1 ? C : T), lane = lanes > 1 ? threadIdx.x / C : 0;
   if (lane < lanes) {
-    for (int c = c_of; c < C; c += (lanes > 1 ? C : 256)) {
+    for (int c = c_of; c < C; c += (lanes > 1 ? C : T)) {
       const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * C + c;
 #pragma unroll 8
       for (int k = lane; k < chunks; k += lanes) {
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restr
   }
   ss[threadIdx.x] = s; sq[threadIdx.x] = q;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = T / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
     __syncthreads();
   }
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) ln2d_finalize_kernel(const float* __restr
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float fmean = (float)mean;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += T) {
     const float av = rstd * gamma[c];
     a[(size_t)n * C + c] = av;
     b[(size_t)n * C + c] = beta[c] - fmean * av;
@@ -471,8 +473,11 @@ extern "C" int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, voi
 extern "C" int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
                                  const float* gamma, const float* beta, float eps, float* a, float* b, void* stream) {
   if (!partial || !gamma || !beta || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
-  launch_pdl(ln2d_finalize_kernel, N, 256, 0, (cudaStream_t)stream, partial, chunks, C, 1.0 / ((double)count_per_channel * C),
-                                                            gamma, beta, eps, a, b);
+  const double inv = 1.0 / ((double)count_per_channel * C);
+  if ((long long)chunks * C >= 8192)
+    launch_pdl(ln2d_finalize_kernel<1024>, N, 1024, 0, (cudaStream_t)stream, partial, chunks, C, inv, gamma, beta, eps, a, b);
+  else
+    launch_pdl(ln2d_finalize_kernel<256>, N, 256, 0, (cudaStream_t)stream, partial, chunks, C, inv, gamma, beta, eps, a, b);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -1,0 +1,85 @@
+"""Drop-in for the 3DMM-coefficient helpers of the reference's futils/inference_utils.py (:73-99): the step in front
+of DNet.forward that turns the per-frame coefficient table into DNet's ``driving_source`` windows.
+
+Same names, argument meaning and return types as the reference (``transform_semantic`` returns a CPU float32 tensor
+[73, 26]); ``semantic_windows`` is the batched form the pipeline uses (one launch for a whole frame range, result stays
+in HBM).  The gather runs in libs2v's ``s2v_semantic_windows`` kernel - no CPU path, a CUDA device is required.
+``find_crop_norm_ratio`` is a once-per-clip host reduction over the table (as in the reference: numpy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+
+def obtain_seq_index(index, num_frames):
+    """inference_utils.py:73-76: the 26 table rows of frame ``index`` (index-13 .. index+12, clamped)."""
+    seq = list(range(index - 13, index + 13))
+    return [min(max(item, 0), num_frames - 1) for item in seq]
+
+
+def find_crop_norm_ratio(source_coeff, target_coeffs):
+    """inference_utils.py:93-99 (host, once per clip): ratio of the source crop scale to the crop scale of the target
+    frame closest in expression (weight 0.3) and pose (0.7).  numpy in, numpy [1] out, dtype preserved."""
+    alpha = 0.3
+    exp_diff = np.mean(np.abs(target_coeffs[:, 80:144] - source_coeff[:, 80:144]), 1)
+    angle_diff = np.mean(np.abs(target_coeffs[:, 224:227] - source_coeff[:, 224:227]), 1)
+    index = np.argmin(alpha * exp_diff + (1 - alpha) * angle_diff)
+    return source_coeff[:, -3] / target_coeffs[index:index + 1, -3]
+
+
+def _ratio_args(crop_norm_ratio):
+    """The reference tests ``if crop_norm_ratio:`` (:87): None, 0 and [0.] leave the crop untouched."""
+    if crop_norm_ratio is None:
+        return 0.0, 0
+    r = np.asarray(crop_norm_ratio.detach().cpu().numpy() if torch.is_tensor(crop_norm_ratio) else crop_norm_ratio)
+    if r.size != 1:
+        raise ValueError("crop_norm_ratio must hold one value (the truth value of a longer array is ambiguous)")
+    r = float(r.reshape(-1)[0])
+    return r, int(bool(r))
+
+
+def upload_semantic(semantic, device) -> torch.Tensor:
+    """The [T, D] coefficient table as a device tensor (float32 or float64 kept as given; D >= 262)."""
+    t = semantic if torch.is_tensor(semantic) else torch.from_numpy(np.ascontiguousarray(semantic))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.float()
+    if t.dim() != 2 or t.shape[1] < 262:
+        raise ValueError("semantic must be [T, D >= 262], got %s" % (tuple(t.shape),))
+    return t.to(device).contiguous()
+
+
+def semantic_windows(semantic: torch.Tensor, frames, crop_norm_ratio=None) -> torch.Tensor:
+    """semantic: CUDA table [T, D]; frames: (first, count) or an int sequence / tensor of frame indices.
+    Returns CUDA float32 [count, 73, 26] - transform_semantic of every frame, stacked."""
+    if not semantic.is_cuda:
+        raise L.S2VError("semantic must be a CUDA tensor: this package has no CPU path (see upload_semantic)")
+    lib = L.require_device(semantic.device.index)
+    ratio, use = _ratio_args(crop_norm_ratio)
+    if isinstance(frames, tuple) and len(frames) == 2:
+        first, count, idx = int(frames[0]), int(frames[1]), None
+    else:
+        idx = torch.as_tensor(frames, dtype=torch.int32).to(semantic.device).contiguous()
+        first, count = 0, int(idx.numel())
+    out = torch.empty(count, 73, 26, dtype=torch.float32, device=semantic.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with torch.cuda.device(semantic.device):
+        for s in range(0, count, 65535):
+            n = min(65535, count - s)
+            L.check(lib.s2v_semantic_windows(semantic.data_ptr(), int(semantic.dtype == torch.float64), semantic.shape[0],
+                                             semantic.shape[1], None if idx is None else idx[s:].data_ptr(), first + s, n,
+                                             ratio, use, out[s:].data_ptr(), stream), "s2v_semantic_windows")
+    return out
+
+
+def transform_semantic(semantic, frame_index, crop_norm_ratio=None):
+    """inference_utils.py:78-91: numpy table [T, D] + frame index -> CPU float32 tensor [73, 26]."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if dev is None:
+        raise L.S2VError("a CUDA device is required: this package has no CPU path")
+    table = semantic if torch.is_tensor(semantic) and semantic.is_cuda else upload_semantic(semantic, dev)
+    return semantic_windows(table, (int(frame_index), 1), crop_norm_ratio)[0].cpu()

@@ -44,6 +44,7 @@ class Op:
     fn: object
     args: tuple
     keep: tuple = field(default_factory=tuple, repr=False)
+    io_bytes: float = 0.0       # tensor-core ops: minimum HBM bytes (operands once + output once), for the per-layer roofline
     alg_bytes: float = 0.0      # algorithmic HBM bytes of a memory-bound op: every input read once + every output written once
 
     def run(self, stream=None):
@@ -226,6 +227,11 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
         op.alg_flops += 2.0 * d.y.n * d.y.h * d.y.w * cout * k2[0] * k2[1] * x2.shape[3]
     if alg_flops is not None:           # launches that execute structurally-zero weight blocks report the reference's work
         op.alg_flops = float(alg_flops)
+    # minimum HBM bytes of this launch (every operand read once, the output written once): with alg_flops it gives the
+    # per-layer roofline time max(flops / tensor peak, bytes / HBM peak) that bench.py sums over the step
+    out_b = (4.0 if y is None else 2.0) * d.y.n * d.y.h * d.y.w * cout
+    op.io_bytes = (2.0 * x.numel() + w.numel() * w.element_size() + out_b
+                   + sum(2.0 * t.numel() for t in (res1, res2, x2) if t is not None))
     return op
 
 
@@ -408,8 +414,9 @@ def op_conv_head(lib, x, w, y_f32, *, bias=None, act=L.ACT_NONE, act_param=0.0, 
     d.pad_h = d.pad_w = 3
     d.act, d.act_param = act, float(act_param)
     assert w.dtype == torch.float16 and tuple(w.shape) == (64, x.shape[3] // 64 * 7 * 64) and x.shape[3] % 64 == 0
-    op = Op(name + "[tc]", lib.s2v_conv_head, (C.byref(d),), (d, x, w, y_f32, bias))
+    op = Op(name + "[head]", lib.s2v_conv_head, (C.byref(d),), (d, x, w, y_f32, bias))
     op.alg_flops = 2.0 * n * oh * ow * co * 49 * x.shape[3]
+    op.io_bytes = 2.0 * x.numel() + 2.0 * w.numel() + 4.0 * y_f32.numel()
     return op
 
 

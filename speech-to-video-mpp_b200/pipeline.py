@@ -11,7 +11,7 @@ import torch
 
 from . import _lib as L
 from . import parallel
-from .futils import audio
+from .futils import audio, inference_utils
 
 
 def glue_fake_to_face(fake: torch.Tensor, size: int = 96) -> torch.Tensor:
@@ -34,19 +34,25 @@ class LipSyncPipeline:
         return audio.mel_window_count(1 + n_samples // 200, self.fps)
 
     @torch.no_grad()
-    def run(self, wav: torch.Tensor, sources: torch.Tensor, coeffs: torch.Tensor, rank: int = 0, world: int = 1):
+    def run(self, wav: torch.Tensor, sources: torch.Tensor, coeffs: torch.Tensor | None, rank: int = 0, world: int = 1,
+            semantic: torch.Tensor | None = None, crop_norm_ratio=None):
         """wav: float32 CUDA [n_samples]; sources [N,3,256,256], coeffs [N,73,26] for THIS rank's frame
-        range (or all N frames when world == 1).  Returns this rank's generated frames [n_r,3,96,96]."""
+        range (or all N frames when world == 1).  Instead of ``coeffs``, ``semantic`` may hold the clip's whole 3DMM
+        coefficient table [T,262] on the device (+ ``crop_norm_ratio``): the [73,26] windows of this rank's frames are
+        then built per DNet batch by s2v_semantic_windows (futils/inference_utils.py:78-91 of the reference, which runs
+        it per frame on the CPU at preprocessing/facing.py:184).  Returns this rank's generated frames [n_r,3,96,96]."""
         mel = audio.melspectrogram_device(wav)
         total = audio.mel_window_count(mel.shape[1], self.fps)
         lo, hi = parallel.shard_range(total, rank, world)
         n = hi - lo
-        assert sources.shape[0] >= n and coeffs.shape[0] >= n
+        assert sources.shape[0] >= n and (coeffs is None) != (semantic is None)
+        assert coeffs is None or coeffs.shape[0] >= n
         windows = audio.mel_windows(mel, self.fps, lo, n)
         faces = torch.empty(n, 6, 96, 96, dtype=torch.float32, device=wav.device)
         for s in range(0, n, self.db):
             e = min(n, s + self.db)
-            out = self.dnet(sources[s:e], coeffs[s:e])
+            drive = coeffs[s:e] if coeffs is not None else inference_utils.semantic_windows(semantic, (lo + s, e - s), crop_norm_ratio)
+            out = self.dnet(sources[s:e], drive)
             faces[s:e] = glue_fake_to_face(out["fake_image"])
         frames = torch.empty(n, 3, 96, 96, dtype=torch.float32, device=wav.device)
         for s in range(0, n, self.lb):

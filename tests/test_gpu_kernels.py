@@ -327,3 +327,33 @@ def test_grouped_linear(G):
     G.ops.op_grouped_linear(lib, hidden, gdev, tdev, len(tiles), out).run()
     ref = torch.cat([hidden.reshape(B, -1)[:, ino:ino + 128].float() @ wts[i] + bs[i] for i, (ino, _) in enumerate(specs)], 1)
     assert G.report("grouped_linear", out, ref)[1] < 1e-5
+
+
+def test_semantic_windows_bit_exact(G):
+    """s2v_semantic_windows (futils/inference_utils.py:73-91 for a whole batch) against the reference's own outputs
+    (tests/golden/semantic_golden.npz) and the oracle at clip size: bit-exact, float32 and float64 tables."""
+    import os
+    from oracle import semantic as osem
+    from s2v_b200.futils import inference_utils as iu
+    gold = np.load(os.path.join(GOLDEN, "semantic_golden.npz"))
+    for tag, dtype, n in (("f32", np.float32, 40), ("f64", np.float64, 17)):
+        table = osem.synth_table(n, seed=3, dtype=dtype)
+        ratio = iu.find_crop_norm_ratio(table[0:1], table[1:])
+        assert np.array_equal(ratio, gold[tag + "_ratio"])
+        dev = iu.upload_semantic(table, "cuda")
+        frames = gold[tag + "_frames"]
+        assert np.array_equal(iu.semantic_windows(dev, frames).cpu().numpy(), gold[tag + "_plain"])
+        assert np.array_equal(iu.semantic_windows(dev, frames, ratio).cpu().numpy(), gold[tag + "_scaled"])
+        assert np.array_equal(iu.semantic_windows(dev, (3, 1), np.zeros(1, dtype))[0].cpu().numpy(), gold[tag + "_zero_ratio"])
+        one = iu.transform_semantic(table, int(frames[4]), ratio)                 # the reference's per-frame signature
+        assert one.device.type == "cpu" and one.dtype == torch.float32 and tuple(one.shape) == (73, 26)
+        assert np.array_equal(one.numpy(), gold[tag + "_scaled"][4])
+    # a 60 s clip's worth of frames as one contiguous range == the oracle per frame
+    table = osem.synth_table(1497, seed=5)
+    ratio = osem.find_crop_norm_ratio(table[0:1], table)
+    got = iu.semantic_windows(iu.upload_semantic(table, "cuda"), (0, 1497), ratio).cpu().numpy()
+    for i in (0, 1, 12, 13, 700, 1483, 1484, 1496):
+        assert np.array_equal(got[i], osem.transform_semantic(table, i, ratio)), i
+    assert iu.semantic_windows(iu.upload_semantic(table, "cuda"), (0, 0)).shape == (0, 73, 26)
+    with pytest.raises(Exception):
+        iu.semantic_windows(torch.from_numpy(table), (0, 1))                     # CPU tensor: no CPU path

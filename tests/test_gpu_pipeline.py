@@ -48,3 +48,39 @@ def test_full_path_vs_oracle_and_shard_equivalence():
         lo, hi = parallel.shard_range(n, r, 2)
         parts.append(pipe.run(torch.from_numpy(wav).cuda(), src[lo:hi], coeff[lo:hi], rank=r, world=2))
     assert torch.equal(torch.cat(parts, 0), frames)
+
+
+def test_pipeline_builds_driving_windows_from_semantic_table():
+    """pipeline.run(semantic=...) == pipeline.run(coeffs = the oracle's per-frame transform_semantic windows), bit-for-bit,
+    unsharded and as rank r of 2 (the window of a shard's first frame reaches back into the previous shard's rows)."""
+    import numpy as np
+    import gpu_util as G
+    from oracle import mel as omel, semantic as osem, synth, weights
+    from s2v_b200 import parallel
+    from s2v_b200.futils import inference_utils as iu
+    from s2v_b200.models.DNet import DNet
+    from s2v_b200.models.LNet import LNet
+    from s2v_b200.pipeline import LipSyncPipeline
+    G.lib()
+    lnet, dnet = LNet().cuda().eval(), DNet().cuda().eval()
+    lnet.load_state_dict(weights.make_state_dict("lnet", 0), strict=True)
+    dnet.load_state_dict(weights.make_state_dict("dnet", 0), strict=True)
+    wav = torch.from_numpy(synth.wav(0.5, seed=0)).cuda()
+    n = len(omel.mel_window_starts(1 + wav.numel() // 200))
+    src, _ = synth.dnet_inputs(n, seed=2)
+    src = src.cuda()
+    table = osem.synth_table(n, seed=7)
+    table[:, 80:144] *= 0.3                      # expression coefficients at a realistic scale
+    table[:, 257:262] = (table[:, 257:262] - 50.0) / 100.0
+    ratio = iu.find_crop_norm_ratio(table[0:1], table)
+    coeff = torch.from_numpy(np.stack([osem.transform_semantic(table, i, ratio) for i in range(n)])).cuda()
+    pipe = LipSyncPipeline(lnet, dnet, lnet_batch=4, dnet_batch=4)
+    a = pipe.run(wav, src, coeff)
+    dev_table = iu.upload_semantic(table, "cuda")
+    b = pipe.run(wav, src, None, semantic=dev_table, crop_norm_ratio=ratio)
+    assert torch.equal(a, b)
+    parts = []
+    for r in range(2):
+        lo, hi = parallel.shard_range(n, r, 2)
+        parts.append(pipe.run(wav, src[lo:hi], None, rank=r, world=2, semantic=dev_table, crop_norm_ratio=ratio))
+    assert torch.equal(torch.cat(parts, 0), a)
