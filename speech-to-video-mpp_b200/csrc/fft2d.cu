@@ -50,13 +50,14 @@ __device__ __forceinline__ void fft(float2 (&x)[N]) {
 
 // x [N,S,S,C] -> spec [N,S,S/2+1,2C]; block (n, CB channels), threads (S/2+1)*CB
 template <int S, int CB>
-__global__ void __launch_bounds__((S / 2 + 1) * CB) rfft2_kernel(View x, View sp) {
+__global__ void __launch_bounds__((S / 2 + 1) * CB) rfft2_kernel(View x, View sp, int rev) {
   pdl_trigger();
   pdl_wait();
   constexpr int K = S / 2 + 1;
   extern __shared__ float2 sm[];      // [S][K][CB]
   const int c = threadIdx.x % CB, t = threadIdx.x / CB;
-  const int n = blockIdx.y, ch = blockIdx.x * CB + c;
+  // rev: images from the end of the tensor first (the part the producing conv wrote last and L2 still holds)
+  const int n = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, ch = blockIdx.x * CB + c;
   if (t < S / 2) {                    // row pass: rows 2t, 2t+1 as one complex signal
     float2 z[S];
     const __half* r0 = x.p + n * x.sn + (2 * t) * x.sh + ch;
@@ -89,13 +90,14 @@ __global__ void __launch_bounds__((S / 2 + 1) * CB) rfft2_kernel(View x, View sp
 
 // spec [N,S,S/2+1,2C] -> y [N,S,S,C] (+ add)
 template <int S, int CB>
-__global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View add, View y) {
+__global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View add, View y, int rev) {
   pdl_trigger();
   pdl_wait();
   constexpr int K = S / 2 + 1;
   extern __shared__ float2 sm[];      // [S][K][CB]
   const int c = threadIdx.x % CB, t = threadIdx.x / CB;
-  const int n = blockIdx.y, ch = blockIdx.x * CB + c;
+  // rev: images from the end of the tensor first (the part the producing conv wrote last and L2 still holds)
+  const int n = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, ch = blockIdx.x * CB + c;
   {                                   // inverse along H for column k = t
     const int k = t;
     float2 col[S];
@@ -153,13 +155,18 @@ __global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View 
   }
 }
 
+static int fft_rev() {
+  static const int rev = [] { const char* e = getenv("S2V_FFT_REV"); return e ? atoi(e) : 0; }();
+  return rev;
+}
+
 template <int S, int CB>
 static int launch_rfft2(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
   constexpr int K = S / 2 + 1;
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
   static bool attr = false;   // idempotent attribute set (same value every time)
   if (!attr) { cudaFuncSetAttribute(rfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  launch_pdl(rfft2_kernel<S, CB>, dim3(x->c / CB, x->n), K * CB, smem, st, mk(x), mk(sp));
+  launch_pdl(rfft2_kernel<S, CB>, dim3(x->c / CB, x->n), K * CB, smem, st, mk(x), mk(sp), fft_rev());
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }
 template <int S, int CB>
@@ -168,7 +175,7 @@ static int launch_irfft2(const s2v_view* sp, const s2v_view* add, const s2v_view
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(irfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  launch_pdl(irfft2_kernel<S, CB>, dim3(y->c / CB, y->n), K * CB, smem, st, mk(sp), mk(add && add->ptr ? add : nullptr), mk(y));
+  launch_pdl(irfft2_kernel<S, CB>, dim3(y->c / CB, y->n), K * CB, smem, st, mk(sp), mk(add && add->ptr ? add : nullptr), mk(y), fft_rev());
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }
 

@@ -168,7 +168,7 @@ __device__ __forceinline__ float act_c(float v, float ap) {
 template <int POOL, int ACT>
 __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
                                                          const float* __restrict__ b, float ap, View res, View y,
-                                                         int reflect1) {
+                                                         int reflect1, int rev) {
   pdl_trigger();
   pdl_wait();
   constexpr int U = 2;
@@ -176,11 +176,15 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= y.w * C8) return;
   const int ox = idx / C8, c8 = idx - ox * C8;
-  const int n = blockIdx.z;
+  // rev: walk the images (and rows) from the END of the tensor - the producer (a conv walking tiles in ascending order)
+  // wrote those last, so they are the part of x still resident in L2; this kernel's own first writes (high images) age
+  // out while its last writes (low images) are what the next ascending conv reads first.  Pure scheduling, same results.
+  const int n = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int by = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int hh = (y.h + 1) >> 1;
   int oy[U];
   bool ok[U];
-  oy[0] = blockIdx.y; oy[1] = blockIdx.y + hh;
+  oy[0] = by; oy[1] = by + hh;
   ok[0] = true; ok[1] = oy[1] < y.h;
   H8 xin[U][POOL ? 4 : 1], rin[U];
 #pragma unroll
@@ -504,7 +508,8 @@ extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b,
   const dim3 grid(ceil_div((long long)y->w * (y->c >> 3), 256), (y->h + 1) / 2, y->n);
   const View vx = mk(x), vr = mk(res && res->ptr ? res : nullptr), vy = mk(y);
   cudaStream_t st = (cudaStream_t)stream;
-#define S2V_AFFINE(P, A) launch_pdl(affine_act_kernel<P, A>, grid, 256, 0, st, vx, a, b, act_param, vr, vy, reflect1)
+  static const int rev = [] { const char* e = getenv("S2V_AFFINE_REV"); return e ? atoi(e) : 0; }();
+#define S2V_AFFINE(P, A) launch_pdl(affine_act_kernel<P, A>, grid, 256, 0, st, vx, a, b, act_param, vr, vy, reflect1, rev)
   if (pool2) {
     if (act == S2V_ACT_LRELU) S2V_AFFINE(1, S2V_ACT_LRELU);
     else if (act == S2V_ACT_RELU) S2V_AFFINE(1, S2V_ACT_RELU);

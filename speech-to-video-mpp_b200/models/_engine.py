@@ -263,15 +263,17 @@ class EngineBase:
             main.wait_event(done)
 
     def _run(self, ent):
-        """Runs the plan on the current stream; after two eager runs the op list is captured into a
-        CUDA graph (launch-bound: ~500 small kernels per LNet forward) and replayed."""
+        """Runs the plan on the current stream; the first call runs the op list eagerly (one-time kernel attribute
+        setup happens there) and then captures it into a CUDA graph (launch-bound: ~500 small kernels per LNet forward);
+        later calls replay the graph.  Capturing on the first call matters for the pipeline's tail batches, whose
+        plans run once per clip."""
         if not self.use_graph:
             self._run_plan(ent)
             return
         if ent["graph"] is None:
             self._run_plan(ent)
             ent["warm"] += 1
-            if ent["warm"] >= 2 and not torch.cuda.is_current_stream_capturing():
+            if ent["warm"] >= 1 and not torch.cuda.is_current_stream_capturing():
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):

@@ -74,7 +74,8 @@ def main():
             frames = pipe.run(wav, srcs, coeffs, rank, world)
             return parallel.gather_frames(frames, total)
 
-        out = step()                                     # warm-up: plans, graphs, NCCL channels
+        for _ in range(2):                               # warm-up: plans, graph capture (tail batches too), NCCL channels
+            out = step()
         assert out.shape[0] == total
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
