@@ -258,6 +258,13 @@ int s2v_adain_finalize(const float* partial, int N, int chunks, int C, int64_t c
  * y (y must be the interior view of a buffer padded by 1).                      */
 int s2v_affine_act(const s2v_view* x, const float* a, const float* b, int act, float act_param,
                    int pool2, const s2v_view* res, const s2v_view* y, int reflect1, void* stream);
+/* y = act(x*a + b) + act(res*ra + rb): the decoder's  up-branch LayerNorm2d + LeakyReLU  and  jump-branch LayerNorm2d +
+ * LeakyReLU + add  (models/LNet.py:66-72, base_blocks.py:112-124,429-441) applied in ONE pass over the two raw conv
+ * outputs - the normalised up-branch tensor is never materialised (saves one write + one read of it).
+ * ra / rb: per-(n,c) scale / shift of `res` (from s2v_ln2d_finalize), same layout as a / b.                          */
+int s2v_affine_act2(const s2v_view* x, const float* a, const float* b, int act, float act_param,
+                    const s2v_view* res, const float* ra, const float* rb, const s2v_view* y, int reflect1, void* stream);
+
 /* Single-pass InstanceNorm2d + AdaIN + activation [+res] [reflect border] for maps whose (image, channel group)
  * slab fits in shared memory (s2v_adain_fused_fits > 0): one read of x instead of chan_stats + adain_finalize
  * + affine_act.  Same arithmetic and the same fixed reduction order for every batch size.                     */

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "s2v_ln2d_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),
     "s2v_adain_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "s2v_affine_act": (C.c_int, [VP, c_vp, c_vp, C.c_int, c_f32, C.c_int, VP, VP, C.c_int, c_vp]),
+    "s2v_affine_act2": (C.c_int, [VP, c_vp, c_vp, C.c_int, c_f32, VP, c_vp, c_vp, VP, C.c_int, c_vp]),
     "s2v_adain_fused_fits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "s2v_adain_fused": (C.c_int, [VP, c_vp, c_vp, c_i64, c_f32, C.c_int, c_f32, VP, VP, C.c_int, c_vp]),
     "s2v_token_layernorm": (C.c_int, [VP, c_vp, c_vp, c_f32, VP, c_vp]),

@@ -165,10 +165,11 @@ __device__ __forceinline__ float act_c(float v, float ap) {
 
 // grid (ceil(W*C8/256), ceil(H/2), N): thread = (ox, c8) of output rows oy and oy + ceil(H/2) of image n.
 // Both rows share the per-(n,c) affine; all loads of both rows are issued before any math.
-template <int POOL, int ACT>
+template <int POOL, int ACT, int R2>
 __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __restrict__ a,
                                                          const float* __restrict__ b, float ap, View res, View y,
-                                                         int reflect1, int rev) {
+                                                         int reflect1, int rev, const float* __restrict__ ra,
+                                                         const float* __restrict__ rb) {
   pdl_trigger();
   pdl_wait();
   constexpr int U = 2;
@@ -199,8 +200,9 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
     }
     if (res.p) rin[u] = ld_h8(res.p + n * res.sn + oy[u] * res.sh + ox * res.sw + c8 * 8);
   }
-  float av[8], bv[8];
+  float av[8], bv[8], rav[R2 ? 8 : 1], rbv[R2 ? 8 : 1];
   load_ab(a, b, n, x.c, c8, av, bv);
+  if (R2) load_ab(ra, rb, n, x.c, c8, rav, rbv);
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (!ok[u]) continue;
@@ -226,8 +228,13 @@ __global__ void __launch_bounds__(256) affine_act_kernel(View x, const float* __
     if (res.p) {
       float f[8];
       h8_to_f(rin[u], f);
+      if (R2) {               // the residual is itself a raw conv output: its own per-(n,c) affine + the same activation
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += f[i];
+        for (int i = 0; i < 8; ++i) o[i] += act_c<ACT>(fmaf(f[i], rav[R2 ? i : 0], rbv[R2 ? i : 0]), ap);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += f[i];
+      }
     }
     affine_store(y, n, oy[u], ox, c8, o, reflect1);
   }
@@ -496,8 +503,23 @@ extern "C" int s2v_adain_finalize(const float* partial, int N, int chunks, int C
   return S2V_OK;
 }
 
+static int affine_act_impl(const s2v_view* x, const float* a, const float* b, int act, float act_param, int pool2,
+                           const s2v_view* res, const float* ra, const float* rb, const s2v_view* y, int reflect1, void* stream);
+
 extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b, int act, float act_param, int pool2,
                               const s2v_view* res, const s2v_view* y, int reflect1, void* stream) {
+  return affine_act_impl(x, a, b, act, act_param, pool2, res, nullptr, nullptr, y, reflect1, stream);
+}
+
+extern "C" int s2v_affine_act2(const s2v_view* x, const float* a, const float* b, int act, float act_param,
+                               const s2v_view* res, const float* ra, const float* rb, const s2v_view* y, int reflect1,
+                               void* stream) {
+  if (!res || !res->ptr || !ra || !rb) return S2V_EINVAL;
+  return affine_act_impl(x, a, b, act, act_param, 0, res, ra, rb, y, reflect1, stream);
+}
+
+static int affine_act_impl(const s2v_view* x, const float* a, const float* b, int act, float act_param, int pool2,
+                           const s2v_view* res, const float* ra, const float* rb, const s2v_view* y, int reflect1, void* stream) {
   if (!view_ok(x) || !view_ok(y) || !a || !b) return S2V_EINVAL;
   if (y->c != x->c || y->n != x->n) return S2V_EINVAL;
   if (pool2 ? (x->h != 2 * y->h || x->w != 2 * y->w) : (x->h != y->h || x->w != y->w)) return S2V_EINVAL;
@@ -509,15 +531,19 @@ extern "C" int s2v_affine_act(const s2v_view* x, const float* a, const float* b,
   const View vx = mk(x), vr = mk(res && res->ptr ? res : nullptr), vy = mk(y);
   cudaStream_t st = (cudaStream_t)stream;
   static const int rev = [] { const char* e = getenv("S2V_AFFINE_REV"); return e ? atoi(e) : 0; }();
-#define S2V_AFFINE(P, A) launch_pdl(affine_act_kernel<P, A>, grid, 256, 0, st, vx, a, b, act_param, vr, vy, reflect1, rev)
-  if (pool2) {
-    if (act == S2V_ACT_LRELU) S2V_AFFINE(1, S2V_ACT_LRELU);
-    else if (act == S2V_ACT_RELU) S2V_AFFINE(1, S2V_ACT_RELU);
-    else S2V_AFFINE(1, S2V_ACT_NONE);
+#define S2V_AFFINE(P, A, R) launch_pdl(affine_act_kernel<P, A, R>, grid, 256, 0, st, vx, a, b, act_param, vr, vy, reflect1, rev, ra, rb)
+  if (ra) {                     // double affine (s2v_affine_act2): LeakyReLU / none only, no pooling
+    if (act == S2V_ACT_LRELU) S2V_AFFINE(0, S2V_ACT_LRELU, 1);
+    else if (act == S2V_ACT_NONE) S2V_AFFINE(0, S2V_ACT_NONE, 1);
+    else return S2V_EINVAL;
+  } else if (pool2) {
+    if (act == S2V_ACT_LRELU) S2V_AFFINE(1, S2V_ACT_LRELU, 0);
+    else if (act == S2V_ACT_RELU) S2V_AFFINE(1, S2V_ACT_RELU, 0);
+    else S2V_AFFINE(1, S2V_ACT_NONE, 0);
   } else {
-    if (act == S2V_ACT_LRELU) S2V_AFFINE(0, S2V_ACT_LRELU);
-    else if (act == S2V_ACT_RELU) S2V_AFFINE(0, S2V_ACT_RELU);
-    else S2V_AFFINE(0, S2V_ACT_NONE);
+    if (act == S2V_ACT_LRELU) S2V_AFFINE(0, S2V_ACT_LRELU, 0);
+    else if (act == S2V_ACT_RELU) S2V_AFFINE(0, S2V_ACT_RELU, 0);
+    else S2V_AFFINE(0, S2V_ACT_NONE, 0);
   }
 #undef S2V_AFFINE
   S2V_CHECK_LAUNCH();

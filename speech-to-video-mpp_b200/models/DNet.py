@@ -169,7 +169,8 @@ class DNetEngine(EngineBase):
             cat2 = buf("wd.cat2", (B, 32, 32, 512))      # [decoder3 out | e2]
             cat1 = buf("wd.cat1", (B, 64, 64, 256))      # [decoder2 out | e1]
             x = buf("we.out0", (B, 256, 256, 32))
-            self.stem_conv(plan, ws, h + ".encoder.input_layer", img, x)
+            # the statistics of every encoder tensor are emitted by the conv that produces it (no chan_stats pass)
+            st_x = self.stem_conv(plan, ws, h + ".encoder.input_layer", img, x, stats=True, fin=adain_fin(h + ".encoder.encoder0.norm_0"))
             enc_out = {1: cat1[..., 128:], 2: cat2[..., 256:], 3: cat3[..., 256:]}
             ngf, img_f = 32, 256
             for i in range(5):
@@ -177,20 +178,22 @@ class DNetEngine(EngineBase):
                 s = 256 >> i
                 p = f"{h}.encoder.encoder{i}"
                 xa = buf(p + ".a0", (B, s, s, cin))
-                adain(p + ".norm_0", x, xa)
+                adain(p + ".norm_0", x, xa, stats=st_x)
                 y0 = buf(p + ".y0", (B, s // 2, s // 2, cout))
                 st = self.conv_stats(plan, ws, p + ".conv_0", xa, y0, stride=(2, 2), pad=(1, 1), fin=adain_fin(p + ".norm_1"))
                 ya = buf(p + ".a1", (B, s // 2, s // 2, cout))
                 adain(p + ".norm_1", y0, ya, stats=st)
                 y1 = enc_out.get(i) if i in enc_out else buf(p + ".y1", (B, s // 2, s // 2, cout))
-                self.conv(plan, p + ".conv_1", ya, y1, pad=(1, 1))
+                # (encoder4's output feeds TWO AdaINs of decoder4 with different gamma / beta: partials only, no in-kernel finalize)
+                st_x = self.conv_stats(plan, ws, p + ".conv_1", ya, y1, pad=(1, 1),
+                                       fin=adain_fin(f"{h}.encoder.encoder{i + 1}.norm_0") if i < 4 else None)
                 x = y1
             for i, dst in ((4, cat3[..., :256]), (3, cat2[..., :256]), (2, cat1[..., :128])):
                 cin, s = x.shape[3], x.shape[1]
                 cout = dst.shape[3]
                 p = f"{h}.decoder.decoder{i}"
                 xs_a, x0_a = buf(p + ".as", (B, s, s, cin)), buf(p + ".a0", (B, s, s, cin))
-                st = adain(p + ".norm_s", x, xs_a)
+                st = adain(p + ".norm_s", x, xs_a, stats=st_x if i == 4 else None)
                 adain(p + ".norm_0", x, x0_a, stats=st)
                 for ph in (0, 1):                                # shortcut: ConvTranspose2d phases
                     for qh in (0, 1):
@@ -254,13 +257,13 @@ class DNetEngine(EngineBase):
                     for qh in (0, 1):
                         st = self.conv_stats(plan, ws, f"{p}.ph{ph}{qh}", out, uraw[:, ph::2, qh::2, :], tag=p, phase=2 * ph + qh, phases=4,
                                              pad=(1 - ph, 1 - qh), alg_scale=9.0 / 4.0, fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
-                uact = buf(f"ed.up{i}.act", (B, 2 * s, 2 * s, co))
-                self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact, stats=st)
+                # up-branch LN + LReLU is applied inside the jump-branch pass (s2v_affine_act2): uact is never materialised
+                uab = self.ln2d_scale_shift(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], stats=st)
                 p = f"{e}.decoder.jump{i}.model"
                 jraw = buf(f"ed.jump{i}.raw", (B, 2 * s, 2 * s, co))
                 st = self.conv_stats(plan, ws, p, feats.pop(), jraw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 nxt = buf(f"ed.dec{i}.out", (B, 2 * s, 2 * s, co))
-                self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], nxt, res=uact, stats=st)
+                self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], nxt, res=uraw, res_ab=uab, stats=st)
                 out = nxt
             self.head_conv(plan, e + ".decoder.final.model.0", out, fake, act=L.ACT_TANH)
             return io

@@ -279,18 +279,18 @@ class LNetEngine(EngineBase):
                 else:
                     self.conv(plan, p, dec_out, uraw, pad=(1, 1), up2=1)
                     st = None
-                uact = buf(f"dec{i}.uact", (B, S2, S2, co))
-                self.layernorm2d(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], uact, stats=st)
+                # the up-branch LN + LReLU is applied inside the jump-branch pass (s2v_affine_act2): never materialised
+                uab = self.ln2d_scale_shift(plan, ws, p, uraw, self.P[p + ".g"], self.P[p + ".b"], stats=st)
                 p = f"decoder.jump{i}.model"
                 jraw = buf(f"dec{i}.jraw", (B, S2, S2, co))
                 st = self.conv_stats(plan, ws, p, skips[i], jraw, pad=(1, 1), fin=("ln", self.P[p + ".g"], self.P[p + ".b"]))
                 if i > 0:
                     xps = [buf(f"dec{i - 1}.xp{j}", (B, S2 + 2, S2 + 2, co), zero=True) for j in range(3)]
                     self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], xps[0][:, 1:-1, 1:-1, :],
-                                     res=uact, reflect1=1, stats=st)
+                                     res=uraw, res_ab=uab, reflect1=1, stats=st)
                 else:
                     last = buf("dec.last", (B, 96, 96, 64))
-                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uact, stats=st)
+                    self.layernorm2d(plan, ws, p, jraw, self.P[p + ".g"], self.P[p + ".b"], last, res=uraw, res_ab=uab, stats=st)
             self.head_conv(plan, "decoder.final.model.0", last, out, act=L.ACT_SIGMOID)
             return dict(mel=mel_in, face=face_in, out=out)
 

@@ -174,16 +174,23 @@ class EngineBase:
             return st["a"], st["b"]
         return self.buf(ws, tag + ".a", (n, c), torch.float32), self.buf(ws, tag + ".b", (n, c), torch.float32)
 
-    def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0, stats=None):
-        """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124).
-        ``stats``: what conv_stats returned for the producer of x (partials, possibly already finalized)."""
+    def ln2d_scale_shift(self, plan, ws, tag, x, gamma, beta, *, stats=None):
+        """The per-(n,c) scale / shift of LayerNorm2d(x) without applying it (for layernorm2d(res_ab=...))."""
         n, h, w, c = x.shape
         st = stats if stats is not None else self._stats(plan, ws, tag, x)
         a, b = self._ab(ws, tag, st, n, c)
         if not st.get("done"):
             plan.add(ops.op_ln2d_finalize(self.lib, st["partial"], n, st["chunks"], c, h * w, gamma, beta, a, b))
+        return a, b
+
+    def layernorm2d(self, plan, ws, tag, x, gamma, beta, y, *, slope=0.1, pool2=0, res=None, reflect1=0, stats=None, res_ab=None):
+        """LayerNorm2d over (C,H,W) + LeakyReLU(slope) [+ AvgPool2] [+ res] (base_blocks.py:52-69,79-124).
+        ``stats``: what conv_stats returned for the producer of x (partials, possibly already finalized).
+        ``res_ab``: res is a RAW tensor whose own LayerNorm2d scale / shift (ln2d_scale_shift) and the same LeakyReLU
+        are applied on the fly: y = lrelu(LN(x)) + lrelu(LN(res)) in one pass."""
+        a, b = self.ln2d_scale_shift(plan, ws, tag, x, gamma, beta, stats=stats)
         plan.add(ops.op_affine_act(self.lib, x, a, b, y, act=L.ACT_LRELU, act_param=slope, pool2=pool2, res=res,
-                                   reflect1=reflect1))
+                                   reflect1=reflect1, res_ab=res_ab))
 
     def adain(self, plan, ws, tag, x, gamma, beta, gb_stride, y, *, act=L.ACT_LRELU, slope=0.01, res=None, reflect1=0,
               stats=None):

@@ -275,9 +275,18 @@ def op_adain_finalize(lib, partial, n, chunks, c, count, gamma, beta, gb_stride,
               (partial, gamma, beta, a, b))
 
 
-def op_affine_act(lib, x, a, b, y, *, act=L.ACT_NONE, act_param=0.0, pool2=0, res=None, reflect1=0) -> Op:
+def op_affine_act(lib, x, a, b, y, *, act=L.ACT_NONE, act_param=0.0, pool2=0, res=None, reflect1=0, res_ab=None) -> Op:
     vx, vy = view(x), view(y)
     vr = view(res) if res is not None else null_view()
+    if res_ab is not None:          # y = act(x*a+b) + act(res*ra+rb): res is a raw conv output with its own affine
+        assert res is not None and not pool2
+        ra, rb = res_ab
+        op = Op("affine_act", lib.s2v_affine_act2,
+                (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), C.byref(vr), _ptr(ra), _ptr(rb), C.byref(vy), reflect1),
+                (vx, vy, vr, x, y, res, a, b, ra, rb))
+        pad = (y.shape[1] + 2) * (y.shape[2] + 2) / float(y.shape[1] * y.shape[2]) if reflect1 else 1.0
+        op.alg_bytes = 2.0 * (x.numel() + res.numel() + y.numel() * pad)
+        return op
     op = Op("affine_act", lib.s2v_affine_act,
             (C.byref(vx), _ptr(a), _ptr(b), act, float(act_param), pool2, C.byref(vr), C.byref(vy), reflect1),
             (vx, vy, vr, x, y, res, a, b))

@@ -357,3 +357,29 @@ def test_semantic_windows_bit_exact(G):
     assert iu.semantic_windows(iu.upload_semantic(table, "cuda"), (0, 0)).shape == (0, 73, 26)
     with pytest.raises(Exception):
         iu.semantic_windows(torch.from_numpy(table), (0, 1))                     # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("n,c,h,w,reflect", [(3, 64, 24, 24, 0), (2, 128, 10, 14, 1), (1, 256, 8, 8, 0)])
+def test_double_layernorm_add(G, n, c, h, w, reflect):
+    """s2v_affine_act2: lrelu(LN2d(x)) + lrelu(LN2d(r)) in one pass (decoder up + jump branches, models/LNet.py:66-72)."""
+    lib, L = G.lib(), G.L
+    outs = []
+    xs = [_norm_inputs(n, c, h, w)[1] for _ in range(2)]
+    ab, ref = [], 0.0
+    for xh in xs:
+        xf = xh.permute(0, 3, 1, 2).float()
+        gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+        ref = ref + F.leaky_relu(F.layer_norm(xf, xf.shape[1:], gamma[:, None, None].expand(c, h, w), beta[:, None, None].expand(c, h, w)), 0.1)
+        chunks = G.ops.stats_chunks(n, h * w, c)
+        partial = torch.empty(n, chunks, c, 2, device="cuda")
+        a, b = torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda")
+        G.ops.op_chan_stats(lib, xh, chunks, partial).run()
+        G.ops.op_ln2d_finalize(lib, partial, n, chunks, c, h * w, gamma, beta, a, b).run()
+        ab.append((a, b))
+    yp = torch.zeros(n, h + 2, w + 2, c, dtype=torch.float16, device="cuda")
+    y = yp[:, 1:-1, 1:-1, :]
+    G.ops.op_affine_act(lib, xs[0], ab[0][0], ab[0][1], y, act=L.ACT_LRELU, act_param=0.1, res=xs[1], res_ab=ab[1], reflect1=reflect).run()
+    m, rel = G.report("double LN2d add n%d c%d %dx%d" % (n, c, h, w), G.nchw(y), ref)
+    assert rel < 2e-3
+    if reflect:
+        assert torch.equal(G.nchw(yp), F.pad(G.nchw(y), (1, 1, 1, 1), mode="reflect"))

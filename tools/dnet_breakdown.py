@@ -30,6 +30,16 @@ for r in range(3):
         key = re.sub(r"res(\d)\.res\d", r"res\1.*", key)
         d = acc.setdefault(key, [0.0, 0, 0.0])
         d[0] += a.elapsed_time(b) / 2; d[1] += 1 if r == 1 else 0; d[2] += getattr(op, "alg_flops", 0.0) if r == 1 else 0.0
+if os.environ.get("BD_AFFINE", "0") == "1":
+    rows = []
+    for op, (a, b) in zip(ops_l, evs):
+        if op.name == "affine_act":
+            ms = a.elapsed_time(b)
+            rows.append((ms, op.alg_bytes))
+    print("affine_act launches (last pass): total %.3f ms, %.1f MB -> %.0f GB/s overall" % (
+        sum(r[0] for r in rows), sum(r[1] for r in rows) / 1e6, sum(r[1] for r in rows) / sum(r[0] for r in rows) / 1e6))
+    for ms, by in sorted(rows, reverse=True)[:12]:
+        print("   %8.1f us  %8.1f MB  %6.0f GB/s" % (ms * 1e3, by / 1e6, by / ms / 1e6))
 tot = sum(v[0] for v in acc.values())
 print("sum of ops %.3f ms (B=%d), %d launches" % (tot, B, len(ops_l)))
 for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])[:40]:
