@@ -174,7 +174,12 @@ typedef struct {
    *   chunk = stats_chunk_off + tile
    * i.e. the [N][chunks][C][2] layout s2v_ln2d_finalize / s2v_adain_finalize consume (replaces a
    * s2v_chan_stats pass over the output).  tile = tile_y*tiles_x + tile_x of the launch's pixel boxes.
-   * stats_groups and stats_gmax must be 1 (one partial per image, tile and channel).                  */
+   * stats_groups = stats_gmax = 1: one partial per image, tile and channel (the layout above).
+   * stats_gmax = 0, stats_groups = 4, stats_c_total = 4, stats_c_off = 0 (s2v_conv_tc, single N tile): LayerNorm2d
+   * TOTALS - the consumer normalises over (C,H,W), so per image and tile only the sum / sum of squares over all
+   * channels is kept, one entry per group of 32 output rows of the tile:
+   *   stats_partial[((n*stats_chunks_total + chunk)*4 + row_group)*2 + {0,1}]      (consumed by s2v_ln2d_finalize_totals)
+   * taken from the fp32 accumulators in registers - no shared-memory pass over the staged tile.           */
   float*  stats_partial;
   int32_t stats_c_off, stats_c_total, stats_chunk_off, stats_chunks_total, stats_groups, stats_gmax;
   /* s2v_conv_tc hint: a structural zero block of the weights.  Input channels >= narrow_cin_from (a multiple of 64) of
@@ -246,6 +251,9 @@ int s2v_chan_stats(const s2v_view* x, int chunks, float* partial, void* stream);
  *   a[n][c] = rstd[n]*gamma[c],  b[n][c] = beta[c] - mean[n]*a[n][c]            */
 int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
                       const float* gamma, const float* beta, float eps, float* a, float* b, void* stream);
+/* same, for the LayerNorm2d-totals partial layout [N][chunks][4][2] written by s2v_conv_tc with stats_gmax = 0 */
+int s2v_ln2d_finalize_totals(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                             const float* gamma, const float* beta, float eps, float* a, float* b, void* stream);
 /* InstanceNorm2d + AdaIN (models/base_blocks.py:127-157):
  *   a = rstd[n][c]*(1+gamma[n][c]),  b = beta[n][c] - mean[n][c]*a
  * gamma/beta float32 with row stride gb_stride (rows of the grouped_linear out) */

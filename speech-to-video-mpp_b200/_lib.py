@@ -70,6 +70,7 @@ _SIGNATURES = {
     "s2v_grouped_linear": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_i64, c_vp]),
     "s2v_chan_stats": (C.c_int, [VP, C.c_int, c_vp, c_vp]),
     "s2v_ln2d_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),
+    "s2v_ln2d_finalize_totals": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]),
     "s2v_adain_finalize": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "s2v_affine_act": (C.c_int, [VP, c_vp, c_vp, C.c_int, c_f32, C.c_int, VP, VP, C.c_int, c_vp]),
     "s2v_affine_act2": (C.c_int, [VP, c_vp, c_vp, C.c_int, c_f32, VP, c_vp, c_vp, VP, C.c_int, c_vp]),

@@ -362,6 +362,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
   const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
   const bool affine = p.scale != nullptr || p.bias != nullptr;      // identity tables are skipped altogether
+  const bool st_scalar = p.stats != nullptr && p.st_gmax == 0;      // LayerNorm2d totals instead of per-channel partials
   const int half_n = p.bn > p.pass_cols ? p.pass_cols : p.bn;      // columns staged per pass (1 or 2 panels of 64 channels)
   // staging layout = what a SWIZZLE_128B TMA store expects: panels of 64 channels, [128 rows][128 B] each,
   // 16-byte chunk j of row r stored at chunk position j ^ (r & 7)  (also makes the smem stores conflict-free)
@@ -395,6 +396,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
     mbar_wait(sm.tfull0 + 8u * buf, ((uint32_t)j >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.tmem_buf_cols;
+    float ln_s = 0.f, ln_q = 0.f;
     for (int pass0 = 0; pass0 < p.bn; pass0 += half_n) {
       const int pass_n = min(half_n, p.bn - pass0);
       if (!direct) {
@@ -428,6 +430,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
             if (ACT != S2V_ACT_NONE) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
+            }
+            if (st_scalar && c < p.cout) {          // LayerNorm2d totals: this thread's row, all channels, straight from fp32
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { ln_s += o[i]; ln_q = fmaf(o[i], o[i], ln_q); }
             }
             st_h8(stage_ptr(m, cl), f_to_h8(o));
             continue;
@@ -481,7 +487,25 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (p.stats) {
+      if (st_scalar && last_pass) {
+        // LayerNorm2d consumer: only the totals over (C, H, W) are needed.  Every thread summed its own output row over
+        // all channels in registers (fp32, before the fp16 rounding); a fixed xor-butterfly over the lanes that share an
+        // image (32, or rows-per-image when a box holds several images) leaves ONE partial per (image, tile, row group of
+        // 32): stats[n][chunk][(m % rows_per_img) / 32][2].  No shared-memory pass, no per-channel work.
+        const int rows_per_img = p.box_w * p.box_h;
+        const int wdt = rows_per_img < 32 ? rows_per_img : 32;
+        float ss = valid ? ln_s : 0.f, qq = valid ? ln_q : 0.f;
+        for (int o = wdt >> 1; o > 0; o >>= 1) {
+          ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        }
+        if ((lane & (wdt - 1)) == 0 && n < p.N) {
+          const int slot = (m % rows_per_img) >> 5;
+          float2* o2 = reinterpret_cast<float2*>(p.stats) + ((size_t)n * p.st_chunks_total + p.st_chunk_off + tile_sp) * 4 + slot;
+          *o2 = make_float2(ss, qq);
+        }
+      }
+      if (p.stats && !st_scalar) {
         // Column sums (sum, sum of squares) of the staged fp16 tile, ONE partial per (image, spatial tile, channel):
         // the G = 128 / (pass_n / 8) consecutive lanes that share a 16-byte chunk (8 channels) each walk rows g, g+G, ...
         // of one image of the box with conflict-free 128-bit smem loads, then a fixed butterfly over those lanes
@@ -1150,6 +1174,12 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   // fused statistics: one partial per (image, spatial tile, channel); every <=128-column epilogue pass must be 32, 64 or
   // 128 columns wide (the lanes sharing a 16-byte chunk form a power-of-two group inside a warp)
   const bool st_bn_ok = bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256;
+  if (p.stats && p.st_gmax == 0) {
+    // LayerNorm2d totals: [N][chunks][4][2], one N tile only (a tile's channels are summed by one thread), no in-kernel finalize
+    if (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_groups != 4 || p.st_c_total != 4 || p.st_c_off != 0 ||
+        p.n_tiles_n != 1 || p.fin_mode || p.st_chunks_total <= 0 || p.st_chunk_off + p.tiles_w * p.tiles_h > p.st_chunks_total)
+      return S2V_EINVAL;
+  } else
   if (p.stats && (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_c_total <= 0 || p.st_chunks_total <= 0 ||
                   p.st_groups != 1 || p.st_gmax != 1 || !st_bn_ok || (p.st_c_off & 7) || (p.st_c_total & 7) ||
                   p.st_chunk_off + p.tiles_w * p.tiles_h > p.st_chunks_total || p.st_c_off + cout > p.st_c_total))

@@ -62,7 +62,7 @@ __global__ void chan_stats_kernel(View x, int chunks, int PG, float* __restrict_
 // grid N, block T (256, or 1024 for long partial lists): fixed-order reduction over chunks and channels (double
 // accumulators).  T depends only on chunks * C (per-image geometry), never on the batch, so results are batch-independent.
 template <int T>
-__global__ void __launch_bounds__(T) ln2d_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
+__global__ void __launch_bounds__(T) ln2d_finalize_kernel(const float* __restrict__ partial, int chunks, int PC, int C,
                                                           double inv_count, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps,
                                                           float* __restrict__ a, float* __restrict__ b) {
@@ -73,14 +73,15 @@ __global__ void __launch_bounds__(T) ln2d_finalize_kernel(const float* __restric
   double s = 0.0, q = 0.0;
   // thread = (channel c, chunk lane): all T threads stream the [chunks][C][2] partials of this image with
   // 8 independent float2 loads in flight; fixed order per thread + fixed tree below => deterministic
-  const int lanes = C >= T ? 1 : T / C;                     // chunk lanes when C < T (C divides T or lanes = 1)
-  const int c_of = threadIdx.x % (lanes > 1 ? C : T), lane = lanes > 1 ? threadIdx.x / C : 0;
+  // PC = entries per chunk of the partial list: C (per-channel partials) or 4 (LayerNorm2d totals written by s2v_conv_tc)
+  const int lanes = PC >= T ? 1 : T / PC;                   // chunk lanes when PC < T (PC divides T or lanes = 1)
+  const int c_of = threadIdx.x % (lanes > 1 ? PC : T), lane = lanes > 1 ? threadIdx.x / PC : 0;
   if (lane < lanes) {
-    for (int c = c_of; c < C; c += (lanes > 1 ? C : T)) {
-      const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * C + c;
+    for (int c = c_of; c < PC; c += (lanes > 1 ? PC : T)) {
+      const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * PC + c;
 #pragma unroll 8
       for (int k = lane; k < chunks; k += lanes) {
-        const float2 v = pp[(size_t)k * C];
+        const float2 v = pp[(size_t)k * PC];
         s += (double)v.x; q += (double)v.y;
       }
     }
@@ -486,9 +487,18 @@ extern "C" int s2v_ln2d_finalize(const float* partial, int N, int chunks, int C,
   if (!partial || !gamma || !beta || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
   const double inv = 1.0 / ((double)count_per_channel * C);
   if ((long long)chunks * C >= 8192)
-    launch_pdl(ln2d_finalize_kernel<1024>, N, 1024, 0, (cudaStream_t)stream, partial, chunks, C, inv, gamma, beta, eps, a, b);
+    launch_pdl(ln2d_finalize_kernel<1024>, N, 1024, 0, (cudaStream_t)stream, partial, chunks, C, C, inv, gamma, beta, eps, a, b);
   else
-    launch_pdl(ln2d_finalize_kernel<256>, N, 256, 0, (cudaStream_t)stream, partial, chunks, C, inv, gamma, beta, eps, a, b);
+    launch_pdl(ln2d_finalize_kernel<256>, N, 256, 0, (cudaStream_t)stream, partial, chunks, C, C, inv, gamma, beta, eps, a, b);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_ln2d_finalize_totals(const float* partial, int N, int chunks, int C, int64_t count_per_channel,
+                                        const float* gamma, const float* beta, float eps, float* a, float* b, void* stream) {
+  if (!partial || !gamma || !beta || !a || !b || N <= 0 || chunks <= 0 || C <= 0 || count_per_channel <= 0) return S2V_EINVAL;
+  const double inv = 1.0 / ((double)count_per_channel * C);
+  launch_pdl(ln2d_finalize_kernel<256>, N, 256, 0, (cudaStream_t)stream, partial, chunks, 4, C, inv, gamma, beta, eps, a, b);
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -170,7 +170,9 @@ class DNetEngine(EngineBase):
             cat1 = buf("wd.cat1", (B, 64, 64, 256))      # [decoder2 out | e1]
             x = buf("we.out0", (B, 256, 256, 32))
             # the statistics of every encoder tensor are emitted by the conv that produces it (no chan_stats pass)
-            st_x = self.stem_conv(plan, ws, h + ".encoder.input_layer", img, x, stats=True, fin=adain_fin(h + ".encoder.encoder0.norm_0"))
+            # (the 32-channel stem keeps a separate chan_stats pass: its per-channel epilogue statistics cost +100 us on a 256 us
+            # launch - 32-column passes leave 32 lanes per channel chunk, a 5-stage butterfly per tile - vs a 45 us pass)
+            st_x = self.stem_conv(plan, ws, h + ".encoder.input_layer", img, x)
             enc_out = {1: cat1[..., 128:], 2: cat2[..., 256:], 3: cat3[..., 256:]}
             ngf, img_f = 32, 256
             for i in range(5):

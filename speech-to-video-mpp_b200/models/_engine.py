@@ -141,6 +141,14 @@ class EngineBase:
         k = kw.get("k", self.W[name]["k"])
         tiles = ops.box_tiles(h, w, n, k, kw.get("stride", (1, 1)), kw.get("dil", (1, 1)))
         t = tag or name
+        # LayerNorm2d consumer (fin = ("ln", ...)): the conv only emits totals over all channels, from its accumulator
+        # registers - no shared-memory statistics pass in the epilogue and a 4-entry-per-tile partial list to finalize
+        totals = (fin is not None and fin[0] == "ln" and c_off == 0 and ct == c and c <= 256 and self.lib.s2v_conv_tc_tile_n(c) >= c
+                  and os.environ.get("S2V_LN_TOTALS", "1") == "1" and os.environ.get("S2V_FUSED_FINALIZE", "0") != "1")
+        if totals:
+            partial = self.buf(ws, t + ".epi_totals", (n, tiles * phases, 4, 2), torch.float32, zero=True)
+            self.conv(plan, name, x, y, stats=(partial, 0, phase * tiles, "totals"), **kw)
+            return dict(partial=partial, chunks=tiles * phases, done=False, totals=True)
         partial = self.buf(ws, t + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
         st = dict(partial=partial, chunks=tiles * phases, done=False)
         f = None
@@ -179,7 +187,9 @@ class EngineBase:
         n, h, w, c = x.shape
         st = stats if stats is not None else self._stats(plan, ws, tag, x)
         a, b = self._ab(ws, tag, st, n, c)
-        if not st.get("done"):
+        if st.get("totals"):
+            plan.add(ops.op_ln2d_finalize_totals(self.lib, st["partial"], n, st["chunks"], c, h * w, gamma, beta, a, b))
+        elif not st.get("done"):
             plan.add(ops.op_ln2d_finalize(self.lib, st["partial"], n, st["chunks"], c, h * w, gamma, beta, a, b))
         return a, b
 

@@ -181,9 +181,12 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     d.x2 = view(x2) if x2 is not None else null_view()
     d.k2h, d.k2w = k2
     d.pad2_h, d.pad2_w = pad2
-    if stats is not None:       # (partial [N,chunks,C,2] float32, c_off, chunk_off): fused output statistics
-        partial, c_off, chunk_off = stats
+    if stats is not None:       # (partial [N,chunks,C,2] float32, c_off, chunk_off[, "totals"]): fused output statistics
+        partial, c_off, chunk_off = stats[:3]
         d.stats_groups = d.stats_gmax = 1
+        if len(stats) > 3 and stats[3] == "totals":      # LayerNorm2d consumer: [N,chunks,4,2] totals over all channels
+            d.stats_groups, d.stats_gmax = 4, 0
+            assert partial.shape[2] == 4 and c_off == 0
         assert impl == "tc" and partial.dtype == torch.float32 and partial.dim() == 4 and partial.shape[0] == d.y.n
         d.stats_partial = partial.data_ptr()
         d.stats_c_off, d.stats_c_total = c_off, partial.shape[2]
@@ -265,6 +268,14 @@ def op_chan_stats(lib, x, chunks, partial) -> Op:
 
 def op_ln2d_finalize(lib, partial, n, chunks, c, count, gamma, beta, a, b, eps=1e-5) -> Op:
     return Op("ln2d_finalize", lib.s2v_ln2d_finalize,
+              (_ptr(partial), n, chunks, c, count, _ptr(gamma), _ptr(beta), eps, _ptr(a), _ptr(b)),
+              (partial, gamma, beta, a, b))
+
+
+def op_ln2d_finalize_totals(lib, partial, n, chunks, c, count, gamma, beta, a, b, eps=1e-5) -> Op:
+    """partial [n, chunks, 4, 2]: LayerNorm2d totals written by s2v_conv_tc (stats_gmax = 0)."""
+    assert tuple(partial.shape) == (n, chunks, 4, 2)
+    return Op("ln2d_finalize", lib.s2v_ln2d_finalize_totals,
               (_ptr(partial), n, chunks, c, count, _ptr(gamma), _ptr(beta), eps, _ptr(a), _ptr(b)),
               (partial, gamma, beta, a, b))
 

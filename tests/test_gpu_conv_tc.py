@@ -256,3 +256,36 @@ def test_conv_head_7x7_folded_taps(G):
         ref = torch.sigmoid(ref) if act == L.ACT_SIGMOID else torch.tanh(ref) if act == L.ACT_TANH else ref
         m, rel = G.report("conv_head %dx%d cin%d cout%d" % (h, w_, cin, cout), y, ref)
         assert rel < 2e-3, (h, w_, cin, cout, rel)
+
+
+def test_fused_layernorm_totals(G):
+    """conv_tc stats_gmax = 0: per-(image, tile, 32-row group) totals over ALL channels from the fp32 accumulators
+    (LayerNorm2d consumers), finalized by s2v_ln2d_finalize_totals; against torch on the stored fp16 output."""
+    lib, L, ops = G.lib(), G.L, G.ops
+    torch.manual_seed(13)
+    for (n, h, w_, cin, cout, k) in ((9, 12, 12, 128, 256, 3), (3, 48, 48, 64, 32, 3), (3, 24, 24, 128, 64, 3), (2, 96, 96, 64, 128, 3),
+                                      (2, 50, 37, 64, 64, 3), (5, 12, 12, 64, 128, 1), (1, 64, 64, 64, 64, 3)):
+        x = torch.randn(n, h, w_, cin, device="cuda").half()
+        wt = torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5
+        bias = torch.randn(cout, device="cuda") * 0.2
+        y = torch.zeros(n, h, w_, cout, dtype=torch.float16, device="cuda")
+        tiles = ops.box_tiles(h, w_, n, (k, k))
+        partial = torch.zeros(n, tiles, 4, 2, device="cuda")
+        ops.op_conv(lib, x, ops.pack_w_tc(wt), y, k=(k, k), pad=(k // 2, k // 2), bias=bias, stats=(partial, 0, 0, "totals")).run()
+        torch.cuda.synchronize()
+        ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.half().float(), bias, padding=k // 2)
+        assert (G.nchw(y) - ref).abs().max().item() < 3e-3 * ref.abs().max().item()
+        yf = y.float()
+        ref_s, ref_q = yf.sum((1, 2, 3)), (yf * yf).sum((1, 2, 3))
+        got = partial.sum((1, 2))
+        assert (got[:, 0] - ref_s).abs().max().item() < 2e-2 * max(1.0, ref_s.abs().max().item()) + 2e-4 * yf[0].numel() ** 0.5, (h, cout)
+        assert (got[:, 1] - ref_q).abs().max().item() < 1e-3 * ref_q.abs().max().item(), (h, cout)
+        # finalize -> the LayerNorm2d scale / shift
+        gamma, beta = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda") * 0.1
+        a, b = torch.empty(n, cout, device="cuda"), torch.empty(n, cout, device="cuda")
+        ops.op_ln2d_finalize_totals(lib, partial, n, tiles, cout, h * w_, gamma, beta, a, b).run()
+        torch.cuda.synchronize()
+        mean = yf.mean((1, 2, 3))
+        rstd = 1.0 / torch.sqrt(yf.var((1, 2, 3), unbiased=False) + 1e-5)
+        assert (a - rstd[:, None] * gamma[None]).abs().max().item() < 2e-3 * a.abs().max().item()
+        assert (b - (beta[None] - mean[:, None] * rstd[:, None] * gamma[None])).abs().max().item() < 2e-3 * max(1.0, b.abs().max().item())
