@@ -315,9 +315,10 @@ def main():
             roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % tc[1],
                     "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
                     # dram__bytes_read.sum + dram__bytes_write.sum of the step's dominant conv_tc shape (12x12 level, 3x3, K = 9216:
-                    # 36 of the 246 launches, 23 % of the class time) from profiles/r1b_ncu_full_conv_tc_res2_raw.csv; its algorithmic
-                    # bytes are 51.8 MB (37.7 in + 4.7 weights + 9.4 out) - no wasted re-reads.  Other shapes: profiles/r1b_summary.md
-                    "traffic": 33.2e6, "traffic_of": "one 3x3 K=9216 launch (ncu --set full, bytes per launch)",
+                    # 36 of the 245 launches, ~23 % of the class time) from profiles/r1c_ncu_full_conv_tc_res2_raw.csv (56.2 MB read +
+                    # 1.3 MB written to DRAM; the 9.4 MB output is still in L2 when the kernel ends); its algorithmic bytes are 51.8 MB
+                    # (37.7 in + 4.7 weights + 9.4 out), the rest is the 148 CTAs' weight tiles missing L2.  Other shapes: profiles/r1c_summary.md
+                    "traffic": 57.5e6, "traffic_of": "one 3x3 K=9216 launch (ncu --set full, DRAM bytes per launch; algorithmic 51.8e6)",
                     "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "alg_gflop_per_step": round(tc[2] / 1e9, 1), "kernel_ms_per_step": round(tc[0], 3),
                     "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
