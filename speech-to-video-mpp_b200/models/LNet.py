@@ -306,12 +306,20 @@ class LNetEngine(EngineBase):
         B = mel.shape[0]
         if B == 0:                                  # empty batch: the reference returns an empty tensor
             return torch.empty(0, 3, 96, 96, dtype=torch.float32, device=mel.device)
-        ent = self.plan_for(B)
+        # Batches that are not a multiple of 8 run on the next multiple's plan: the 12 x 12 level tiles 8 images per
+        # 128-pixel box and its 1 x 1 convs run on flattened [B*144] views, so a ragged batch pays masked epilogue paths
+        # and clipped boxes in ~150 launches (measured on B200: B = 89 16.0 ms vs B = 96 11.2 ms; B = 25 7.5 vs B = 32 6.4).
+        # Frames are independent, so the (zeroed) padding rows cannot influence the first B outputs.
+        Bp = B if (B < 8 or B % 8 == 0) else (B + 7) // 8 * 8
+        ent = self.plan_for(Bp)
         io = ent["io"]
-        io["mel"].copy_(mel, non_blocking=True)
-        io["face"].copy_(face, non_blocking=True)
+        io["mel"][:B].copy_(mel, non_blocking=True)
+        io["face"][:B].copy_(face, non_blocking=True)
+        if Bp != B:
+            io["mel"][B:].zero_()
+            io["face"][B:].zero_()
         self._run(ent)
-        return io["out"].clone()
+        return io["out"][:B].clone()
 
 
 class LNet(nn.Module):
