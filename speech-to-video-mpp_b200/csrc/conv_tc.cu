@@ -549,19 +549,45 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
               for (int i = 0; i < 8; ++i) { sa[i] += f[i]; qa[i] = fmaf(f[i], f[i], qa[i]); }
             }
           }
-          for (int o = L >> 1; o > 0; o >>= 1) {
+          // Reduce-scatter over the L lanes of the group (recursive halving): at every stage a lane keeps one half of its
+          // values and hands the other half to its xor partner, so the 16 values (sum, sumsq of 8 channels) cost
+          // 8+4+2+1 = 15 shuffles instead of 16 per stage, and the result ends up spread over the lanes - lane r0 holds
+          // the 16 / L consecutive values starting at r0 * 16 / L (one coalesced store per group).  Fixed order:
+          // deterministic and independent of the batch.
+          float val[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
-              qa[i] += __shfl_xor_sync(0xffffffffu, qa[i], o);
+          for (int i = 0; i < 8; ++i) { val[2 * i] = sa[i]; val[2 * i + 1] = qa[i]; }
+#pragma unroll
+          for (int st = 0; st < 5; ++st) {                // offsets L/2, L/4, ... 1; 16 >> st values held at stage st
+            const int o = L >> (st + 1);
+            if (o == 0) break;
+            if (st < 4) {
+              const bool up = (r0 & o) != 0;              // this lane keeps the upper half
+#pragma unroll
+              for (int i = 0; i < (8 >> st); ++i) {
+                const float lo = val[i], hi = val[i + (8 >> st)];
+                const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, o);
+                val[i] = (up ? hi : lo) + recv;
+              }
+            } else {
+              val[0] += __shfl_xor_sync(0xffffffffu, val[0], o);     // L = 32: the last stage has a single value left
             }
           }
-          if (r0 == 0 && img_ok && c < p.cout) {
-            float4* o = reinterpret_cast<float4*>(p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2);
-            o[0] = make_float4(sa[0], qa[0], sa[1], qa[1]);
-            o[1] = make_float4(sa[2], qa[2], sa[3], qa[3]);
-            o[2] = make_float4(sa[4], qa[4], sa[5], qa[5]);
-            o[3] = make_float4(sa[6], qa[6], sa[7], qa[7]);
+          if (img_ok && c < p.cout) {
+            float* o = p.stats + (((size_t)(n0 + im) * p.st_chunks_total + chunk) * p.st_c_total + p.st_c_off + c) * 2;
+            if (L == 32) { if ((r0 & 1) == 0) o[r0 >> 1] = val[0]; }
+            else if (L == 16) o[r0] = val[0];
+            else if (L == 8) *reinterpret_cast<float2*>(o + 2 * r0) = make_float2(val[0], val[1]);
+            else if (L == 4) *reinterpret_cast<float4*>(o + 4 * r0) = make_float4(val[0], val[1], val[2], val[3]);
+            else {                                        // L = 2 (8 values per lane) or L = 1 (all 16)
+              float4* o4 = reinterpret_cast<float4*>(o + (L == 2 ? 8 * r0 : 0));
+              o4[0] = make_float4(val[0], val[1], val[2], val[3]);
+              o4[1] = make_float4(val[4], val[5], val[6], val[7]);
+              if (L == 1) {
+                o4[2] = make_float4(val[8], val[9], val[10], val[11]);
+                o4[3] = make_float4(val[12], val[13], val[14], val[15]);
+              }
+            }
           }
         }
       }
