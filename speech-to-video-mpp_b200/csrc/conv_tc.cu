@@ -1113,8 +1113,9 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     const long long wb = (long long)(p.ki_total - narrow_taps) * bb + (long long)narrow_taps * nbb;   // narrow taps only matter when resident
     auto staging = [&](int pc, int bufs) { return (((bn > pc ? pc : bn) + 63) / 64) * kTileM * 128 * bufs; };
     if (halo_ok && p.n_tiles_n == 1) {
+      static const int pc_max = [] { const char* e = getenv("S2V_PC_MAX"); return e && atoi(e) == 64 ? 64 : 128; }();   // development knob
       for (int bufs = 2; bufs >= 1; --bufs)
-        for (int pc = 128; pc >= 64; pc -= 64) {
+        for (int pc = (bn > 64 ? pc_max : 128); pc >= 64; pc -= 64) {
           if (pc == 64 && bn <= 64) continue;
           const int so = staging(pc, bufs);
           if (wb + 2LL * a_slot_bytes + so > cap) continue;

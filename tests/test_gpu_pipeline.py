@@ -84,3 +84,30 @@ def test_pipeline_builds_driving_windows_from_semantic_table():
         lo, hi = parallel.shard_range(n, r, 2)
         parts.append(pipe.run(wav, src[lo:hi], None, rank=r, world=2, semantic=dev_table, crop_norm_ratio=ratio))
     assert torch.equal(torch.cat(parts, 0), a)
+
+
+def test_stream_batches_matches_direct_forward():
+    """pipeline.stream_batches (copy-in / forward / copy-out on three streams, two slots in flight) returns exactly what
+    the plain per-batch loop returns, including a ragged last batch and more batches than slots."""
+    import gpu_util as G
+    from oracle import synth, weights
+    from s2v_b200.models.LNet import LNet
+    from s2v_b200.pipeline import stream_batches
+    G.lib()
+    lnet = LNet().cuda().eval()
+    lnet.load_state_dict(weights.make_state_dict("lnet", 0), strict=True)
+    sizes = [8, 8, 8, 8, 5]
+    ins, outs, refs = [], [], []
+    for i, b in enumerate(sizes):
+        mel, face = synth.lnet_inputs(b, seed=10 + i)
+        ins.append((mel.pin_memory(), face.pin_memory()))
+        outs.append(torch.full((b, 3, 96, 96), float("nan")).pin_memory())
+        refs.append(lnet(mel.cuda(), face.cuda()).cpu())
+    for depth in (3, 2, 1):
+        for o in outs:
+            o.fill_(float("nan"))
+        n = stream_batches(lnet, zip(ins, outs), depth=depth)
+        assert n == len(sizes)
+        for o, r in zip(outs, refs):
+            assert torch.equal(o, r), depth
+    assert stream_batches(lnet, iter(())) == 0

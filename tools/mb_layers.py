@@ -82,6 +82,12 @@ def level_all(tag, S, C):
     tiles = ops.box_tiles(S, S, B, (3, 3))
     partial = torch.zeros(B, tiles, C, 2, device="cuda")
     bench(f"{tag}.all+stats", xp, wa, R, k=(3, 3), x2=s2, stats=(partial, 0, 0))
+    nfrom = -(-cl // 64) * 64           # the net's configuration: structural zero block hint (models/LNet.py:254-257)
+    if nfrom < C and cl % 32 == 0:
+        bench(f"{tag}.all+narrow", xp, wa, R, k=(3, 3), x2=s2, narrow=(nfrom, cl))
+        bench(f"{tag}.all+narrow+stats", xp, wa, R, k=(3, 3), x2=s2, narrow=(nfrom, cl), stats=(partial, 0, 0))
+        tot = torch.zeros(B, tiles, 4, 2, device="cuda")
+        bench(f"{tag}.all+narrow+totals", xp, wa, R, k=(3, 3), x2=s2, narrow=(nfrom, cl), stats=(tot, 0, 0, "totals"))
 
 
 level_all("res0", 48, 128)
