@@ -107,6 +107,22 @@ int s2v_mel_windows_f32(const float* mel, int64_t n_cols, double fps, int64_t fi
 int s2v_semantic_windows(const void* semantic, int is_f64, int n_rows, int D, const int32_t* frame_idx,
                          int first, int count, double ratio, int use_ratio, float* out, void* stream);
 
+/* ------------------------------------------------- Laplacian-pyramid blend ---
+ * replaces futils/inference_utils.py:181-222 (Laplacian_Pyramid_Blending_with_mask, called per frame at
+ * inference.py:312; cv2.pyrDown / cv2.pyrUp / cv2.add on the CPU) for a batch of frames.  Images are channels-last
+ * [N,H,W,C] as cv2 holds them, C = 1, 3 or 4.
+ *   s2v_pyrdown_u8 / _f32: cv2.pyrDown ([1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, output (H+1)/2 x (W+1)/2); the 8-bit
+ *     form is bit-exact ((sum + 128) >> 8).
+ *   s2v_lap_blend_level: one level of the collapse, fused (Laplacian levels of A and B, mask blend, reconstruction):
+ *       out = pyrUp(coarse_out) + (a_fine - pyrUp(a_coarse)) * m_fine + (b_fine - pyrUp(b_coarse)) * (1 - m_fine)
+ *     with a/b the uint8 Gaussian-pyramid levels, m_fine float32 [N,h,w], coarse_out float32 [N,h/2,w/2,C];
+ *     coarse_out == NULL: the coarsest level, out = a_fine * m_fine + b_fine * (1 - m_fine).                       */
+int s2v_pyrdown_u8(const uint8_t* src, int N, int H, int W, int C, uint8_t* dst, void* stream);
+int s2v_pyrdown_f32(const float* src, int N, int H, int W, int C, float* dst, void* stream);
+int s2v_lap_blend_level(const float* coarse_out, const uint8_t* a_fine, const uint8_t* b_fine, const float* m_fine,
+                        const uint8_t* a_coarse, const uint8_t* b_coarse, int N, int h, int w, int C, float* out,
+                        void* stream);
+
 /* ----------------------------------------------------------- flow warp ---
  * replaces futils/flow_util.py:3-15 + :41-56 (convert_flow_to_deformation,
  * bilinear resize of the grid, F.grid_sample bilinear/zeros/align_corners=False)

@@ -83,3 +83,59 @@ def transform_semantic(semantic, frame_index, crop_norm_ratio=None):
         raise L.S2VError("a CUDA device is required: this package has no CPU path")
     table = semantic if torch.is_tensor(semantic) and semantic.is_cuda else upload_semantic(semantic, dev)
     return semantic_windows(table, (int(frame_index), 1), crop_norm_ratio)[0].cpu()
+
+
+# ---- Laplacian-pyramid blend (inference_utils.py:181-222, called at inference.py:312) --------------------------------------
+def laplacian_blend(A: torch.Tensor, B: torch.Tensor, m: torch.Tensor, num_levels: int = 6) -> torch.Tensor:
+    """Batched form: A, B uint8 CUDA [N,H,W,C] (C = 1, 3 or 4, channels-last as cv2 holds images), m float32 CUDA [N,H,W]
+    -> float32 CUDA [N,H,W,C].  The 8-bit Gaussian pyramids are bit-exact cv2.pyrDown; each level of the collapse is one
+    fused launch (Laplacian levels of A and B, mask blend and reconstruction) - ~3 * num_levels launches per batch."""
+    if not (A.is_cuda and B.is_cuda and m.is_cuda):
+        raise L.S2VError("laplacian_blend needs CUDA tensors: this package has no CPU path")
+    if A.dtype != torch.uint8 or B.dtype != torch.uint8:
+        raise TypeError("A and B must be uint8 images (what inference.py:311-312 passes)")
+    if A.dim() != 4 or A.shape != B.shape or tuple(m.shape) != tuple(A.shape[:3]) or A.shape[3] not in (1, 3, 4):
+        raise ValueError("expected A, B [N,H,W,C] and m [N,H,W], got %s %s %s" % (tuple(A.shape), tuple(B.shape), tuple(m.shape)))
+    if num_levels < 1:
+        raise IndexError("num_levels must be >= 1")          # the reference indexes gp[num_levels - 1]
+    n, h, w, c = A.shape
+    div = 1 << (num_levels - 1)
+    if h % div or w % div:
+        # the reference fails in np.subtract(gp[i-1], cv2.pyrUp(gp[i])) when a level's size is odd
+        raise ValueError("operands could not be broadcast together: H and W must be multiples of 2**(num_levels-1) = %d" % div)
+    lib = L.require_device(A.device.index)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gA, gB, gM = [A.contiguous()], [B.contiguous()], [m.contiguous().float()]
+    with torch.cuda.device(A.device):
+        for i in range(1, num_levels):            # the reference also builds level num_levels, which nothing reads
+            hh, ww = gA[-1].shape[1], gA[-1].shape[2]
+            oh, ow = (hh + 1) // 2, (ww + 1) // 2
+            a = torch.empty(n, oh, ow, c, dtype=torch.uint8, device=A.device)
+            b = torch.empty_like(a)
+            mm = torch.empty(n, oh, ow, dtype=torch.float32, device=A.device)
+            L.check(lib.s2v_pyrdown_u8(gA[-1].data_ptr(), n, hh, ww, c, a.data_ptr(), st), "s2v_pyrdown_u8")
+            L.check(lib.s2v_pyrdown_u8(gB[-1].data_ptr(), n, hh, ww, c, b.data_ptr(), st), "s2v_pyrdown_u8")
+            L.check(lib.s2v_pyrdown_f32(gM[-1].data_ptr(), n, hh, ww, 1, mm.data_ptr(), st), "s2v_pyrdown_f32")
+            gA.append(a); gB.append(b); gM.append(mm)
+        top = num_levels - 1
+        out = torch.empty(gA[top].shape, dtype=torch.float32, device=A.device)
+        L.check(lib.s2v_lap_blend_level(None, gA[top].data_ptr(), gB[top].data_ptr(), gM[top].data_ptr(), None, None,
+                                        n, gA[top].shape[1], gA[top].shape[2], c, out.data_ptr(), st), "s2v_lap_blend_level")
+        for i in range(top, 0, -1):
+            fine = torch.empty(gA[i - 1].shape, dtype=torch.float32, device=A.device)
+            L.check(lib.s2v_lap_blend_level(out.data_ptr(), gA[i - 1].data_ptr(), gB[i - 1].data_ptr(), gM[i - 1].data_ptr(),
+                                            gA[i].data_ptr(), gB[i].data_ptr(), n, fine.shape[1], fine.shape[2], c,
+                                            fine.data_ptr(), st), "s2v_lap_blend_level")
+            out = fine
+    return out
+
+
+def Laplacian_Pyramid_Blending_with_mask(A, B, m, num_levels=6):
+    """inference_utils.py:181-222, same signature: numpy uint8 images [H,W,3] + float32 mask [H,W] -> numpy float32 [H,W,3]."""
+    if not torch.cuda.is_available():
+        raise L.S2VError("a CUDA device is required: this package has no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = torch.from_numpy(np.ascontiguousarray(A)).to(dev)[None]
+    b = torch.from_numpy(np.ascontiguousarray(B)).to(dev)[None]
+    mm = torch.from_numpy(np.ascontiguousarray(m, dtype=np.float32)).to(dev)[None]
+    return laplacian_blend(a, b, mm, num_levels)[0].cpu().numpy()

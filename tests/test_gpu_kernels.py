@@ -383,3 +383,48 @@ def test_double_layernorm_add(G, n, c, h, w, reflect):
     assert rel < 2e-3
     if reflect:
         assert torch.equal(G.nchw(yp), F.pad(G.nchw(y), (1, 1, 1, 1), mode="reflect"))
+
+
+def test_laplacian_blend_vs_reference_golden_and_oracle(G):
+    """s2v_pyrdown_u8 / _f32 / s2v_lap_blend_level (futils/inference_utils.py:181-222) against outputs of the reference's own
+    function on the real cv2 (tests/golden/blend_golden.npz) and the oracle: 8-bit pyramids bit-exact, blends within 1e-3
+    on the 0..255 scale (float32 summation order)."""
+    import os
+    from oracle import blend as ob
+    from s2v_b200.futils import inference_utils as iu
+    lib = G.lib()
+    gold = np.load(os.path.join(GOLDEN, "blend_golden.npz"))
+    import ctypes as C
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for i in range(7):                       # cv2.pyrDown itself, edge shapes (1 x 1, 2 x 1, odd sizes)
+        x = torch.from_numpy(gold[f"down_u8_{i}_in"]).cuda()[None].contiguous()
+        h, w = x.shape[1:3]
+        y = torch.empty(1, (h + 1) // 2, (w + 1) // 2, 3, dtype=torch.uint8, device="cuda")
+        G.L.check(lib.s2v_pyrdown_u8(x.data_ptr(), 1, h, w, 3, y.data_ptr(), st))
+        assert np.array_equal(y[0].cpu().numpy(), gold[f"down_u8_{i}"]), i
+        f = torch.from_numpy(gold[f"down_f32_{i}_in"]).cuda()[None].contiguous()
+        g = torch.empty(1, (h + 1) // 2, (w + 1) // 2, device="cuda")
+        G.L.check(lib.s2v_pyrdown_f32(f.data_ptr(), 1, h, w, 1, g.data_ptr(), st))
+        assert np.abs(g[0].cpu().numpy() - gold[f"down_f32_{i}"]).max() <= 1e-6, i
+    for key, hw, seed, levels in (("blend64_l6", (64, 64), 0, 6), ("blend64_l7", (64, 64), 0, 7), ("blend48x80_l4", (48, 80), 2, 4)):
+        A, B, m = ob.synth_images(*hw, seed=seed)
+        got = iu.Laplacian_Pyramid_Blending_with_mask(A, B, m, levels)              # the reference's signature
+        assert got.dtype == np.float32 and got.shape == gold[key].shape
+        d = np.abs(got - gold[key]).max()
+        G.report("laplacian blend %s" % key, torch.from_numpy(got), torch.from_numpy(gold[key]))
+        assert d <= 1e-3, (key, d)
+    # the call of inference.py:312 (512 x 512, 10 levels), batched: frame 0 against the golden rows, every frame against the oracle
+    A, B, m = ob.synth_images(512, 512, seed=1)
+    A2, B2, m2 = ob.synth_images(512, 512, seed=4)
+    out = iu.laplacian_blend(torch.from_numpy(np.stack([A, A2])).cuda(), torch.from_numpy(np.stack([B, B2])).cuda(),
+                             torch.from_numpy(np.stack([m, m2])).cuda(), 10).cpu().numpy()
+    assert np.abs(out[0][::37] - gold["blend512_l10_rows"]).max() <= 1e-3
+    assert np.abs(out[1] - ob.laplacian_pyramid_blending_with_mask(A2, B2, m2, 10)).max() <= 1e-3
+    # properties at full size: blending an image with itself returns it; mask 1 -> A, mask 0 -> B
+    dev = lambda a: torch.from_numpy(a).cuda()[None]
+    assert (iu.laplacian_blend(dev(A), dev(A), dev(m), 10)[0].cpu() - torch.from_numpy(A).float()).abs().max().item() <= 2e-3
+    assert (iu.laplacian_blend(dev(A), dev(B), torch.ones_like(dev(m)), 10)[0].cpu() - torch.from_numpy(A).float()).abs().max().item() <= 2e-3
+    assert (iu.laplacian_blend(dev(A), dev(B), torch.zeros_like(dev(m)), 10)[0].cpu() - torch.from_numpy(B).float()).abs().max().item() <= 2e-3
+    assert iu.laplacian_blend(dev(A)[:0], dev(B)[:0], dev(m)[:0], 10).shape == (0, 512, 512, 3)
+    with pytest.raises(ValueError):
+        iu.laplacian_blend(dev(A)[:, :500], dev(B)[:, :500], dev(m)[:, :500], 10)       # 500 is not a multiple of 512
