@@ -39,14 +39,44 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src,
   const T* img = src + (size_t)n * H * W * C;
   using Acc = typename std::conditional<std::is_same<T, float>::value, float, int>::type;
   Acc row[5][C];
+  const bool interior = 2 * ox - 2 >= 0 && 2 * ox + 2 < W;     // the five columns are contiguous in memory
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
     const T* p = img + (size_t)ys[r] * W * C;
     Acc v[5][C];
+    bool done = false;
+    if constexpr (std::is_same<T, uint8_t>::value && C == 3) {
+      // 15 contiguous bytes starting at an even offset: seven 16-bit loads + one byte instead of 15 byte loads
+      const uint8_t* q = p + (2 * ox - 2) * 3;
+      if (interior && (reinterpret_cast<uintptr_t>(q) & 1) == 0) {
+        uint32_t b[15];
 #pragma unroll
-    for (int d = 0; d < 5; ++d)
+        for (int k = 0; k < 7; ++k) {
+          const uint32_t hw = *reinterpret_cast<const unsigned short*>(q + 2 * k);
+          b[2 * k] = hw & 0xffu; b[2 * k + 1] = hw >> 8;
+        }
+        b[14] = q[14];
 #pragma unroll
-      for (int c = 0; c < C; ++c) v[d][c] = (Acc)p[xs[d] * C + c];
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[d][c] = (Acc)b[d * 3 + c];
+        done = true;
+      }
+    }
+    if constexpr (std::is_same<T, float>::value && C == 1) {
+      const float* q = p + (2 * ox - 2);
+      if (interior && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {     // two 8-byte loads + one float instead of five loads
+        const float2 a = *reinterpret_cast<const float2*>(q), b2 = *reinterpret_cast<const float2*>(q + 2);
+        v[0][0] = a.x; v[1][0] = a.y; v[2][0] = b2.x; v[3][0] = b2.y; v[4][0] = q[4];
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[d][c] = (Acc)p[xs[d] * C + c];
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) row[r][c] = v[2][c] * 6 + (v[1][c] + v[3][c]) * 4 + v[0][c] + v[4][c];
   }
@@ -59,41 +89,54 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src,
   }
 }
 
-// pyrUp sample at fine position (y, x) of a coarse [h, w, C] image; U8: the coarse image is uint8
+// 3 x 3 coarse neighbourhood of coarse pixel (cy, cx) with pyrUp's border rule (index -1 -> 1, index n -> n-1), as float
 template <typename T, int C>
-__device__ __forceinline__ void pyrup_at(const T* __restrict__ img, int h, int w, int y, int x, float* out) {
-  const int cy = y >> 1, cx = x >> 1;
-  // per axis: even -> taps (i-1, i, i+1) weights (1, 6, 1); odd -> taps (i, i+1) weights (4, 4); total weight 8
-  int yi[3], xi[3];
-  float wy[3], wx[3];
-  if (y & 1) { yi[0] = cy; yi[1] = min(cy + 1, h - 1); yi[2] = cy; wy[0] = 4.f; wy[1] = 4.f; wy[2] = 0.f; }
-  else { yi[0] = cy > 0 ? cy - 1 : min(1, h - 1); yi[1] = cy; yi[2] = min(cy + 1, h - 1); wy[0] = 1.f; wy[1] = 6.f; wy[2] = 1.f; }
-  if (x & 1) { xi[0] = cx; xi[1] = min(cx + 1, w - 1); xi[2] = cx; wx[0] = 4.f; wx[1] = 4.f; wx[2] = 0.f; }
-  else { xi[0] = cx > 0 ? cx - 1 : min(1, w - 1); xi[1] = cx; xi[2] = min(cx + 1, w - 1); wx[0] = 1.f; wx[1] = 6.f; wx[2] = 1.f; }
-  float acc[C];
+__device__ __forceinline__ void load_nbhd(const T* __restrict__ img, int h, int w, int cy, int cx, float (&v)[3][3][C]) {
+  const int ys[3] = {cy > 0 ? cy - 1 : min(1, h - 1), cy, min(cy + 1, h - 1)};
+  const int xs[3] = {cx > 0 ? cx - 1 : min(1, w - 1), cx, min(cx + 1, w - 1)};
 #pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    if (wy[r] == 0.f) continue;
-    const T* p = img + (size_t)yi[r] * w * C;
-    float rs[C];
+    for (int d = 0; d < 3; ++d)
 #pragma unroll
-    for (int c = 0; c < C; ++c) rs[c] = 0.f;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (wx[d] == 0.f) continue;
-#pragma unroll
-      for (int c = 0; c < C; ++c) rs[c] = fmaf(wx[d], (float)p[xi[d] * C + c], rs[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = fmaf(wy[r], rs[c], acc[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < C; ++c) out[c] = acc[c] * (1.f / 64.f);
+      for (int c = 0; c < C; ++c) v[r][d][c] = (float)img[((size_t)ys[r] * w + xs[d]) * C + c];
 }
 
-// thread = one fine pixel.  coarse == nullptr: coarsest level, out = A * m + B * (1 - m).
+// pyrUp values of the 2 x 2 fine pixels under coarse pixel (cy, cx): per axis even = (x[-1] + 6 x[0] + x[+1]) / 8,
+// odd = (x[0] + x[+1]) / 2; rows first, then columns (same order for every output: deterministic)
+template <int C>
+__device__ __forceinline__ void pyrup_quad(const float (&v)[3][3][C], float (&q)[2][2][C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float e[3], o[3];                 // horizontal pass per coarse row: even / odd fine column
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      e[r] = fmaf(6.f, v[r][1][c], v[r][0][c] + v[r][2][c]);
+      o[r] = 4.f * (v[r][1][c] + v[r][2][c]);
+    }
+    q[0][0][c] = fmaf(6.f, e[1], e[0] + e[2]) * (1.f / 64.f);
+    q[0][1][c] = fmaf(6.f, o[1], o[0] + o[2]) * (1.f / 64.f);
+    q[1][0][c] = 4.f * (e[1] + e[2]) * (1.f / 64.f);
+    q[1][1][c] = 4.f * (o[1] + o[2]) * (1.f / 64.f);
+  }
+}
+
+// coarsest level: thread = one pixel, out = A * m + B * (1 - m)
+template <int C>
+__global__ void __launch_bounds__(256) blend_top_kernel(const uint8_t* __restrict__ a_f, const uint8_t* __restrict__ b_f,
+                                                        const float* __restrict__ m_f, long long total, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const float gm = m_f[pix], gi = 1.0f - gm;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    out[pix * C + c] = __fadd_rn(__fmul_rn((float)a_f[pix * C + c], gm), __fmul_rn((float)b_f[pix * C + c], gi));
+}
+
+// thread = one COARSE pixel = a 2 x 2 quad of fine pixels: the 3 x 3 coarse neighbourhoods of A, B and the running
+// reconstruction are loaded once and serve all four outputs (9 instead of 25 coarse loads per array and quad)
 template <int C>
 __global__ void __launch_bounds__(256) blend_level_kernel(const float* __restrict__ coarse, const uint8_t* __restrict__ a_f,
                                                           const uint8_t* __restrict__ b_f, const float* __restrict__ m_f,
@@ -101,26 +144,43 @@ __global__ void __launch_bounds__(256) blend_level_kernel(const float* __restric
                                                           int N, int h, int w, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
+  const int ch = h >> 1, cw = w >> 1;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * h * w) return;
-  const int x = (int)(idx % w), y = (int)((idx / w) % h), n = (int)(idx / ((long long)w * h));
-  const size_t pix = (size_t)n * h * w + (size_t)y * w + x;
-  const float gm = m_f[pix], gi = 1.0f - gm;
-  float la[C], lb[C], up[C];
+  if (idx >= (long long)N * ch * cw) return;
+  const int cx = (int)(idx % cw), cy = (int)((idx / cw) % ch), n = (int)(idx / ((long long)cw * ch));
+  const size_t cimg = (size_t)n * ch * cw * C;
+  float v[3][3][C], ua[2][2][C], ub[2][2][C], up[2][2][C];
+  load_nbhd<uint8_t, C>(a_c + cimg, ch, cw, cy, cx, v);
+  pyrup_quad<C>(v, ua);
+  load_nbhd<uint8_t, C>(b_c + cimg, ch, cw, cy, cx, v);
+  pyrup_quad<C>(v, ub);
+  load_nbhd<float, C>(coarse + cimg, ch, cw, cy, cx, v);
+  pyrup_quad<C>(v, up);
 #pragma unroll
-  for (int c = 0; c < C; ++c) { la[c] = (float)a_f[pix * C + c]; lb[c] = (float)b_f[pix * C + c]; up[c] = 0.f; }
-  if (coarse) {
-    const int ch = h >> 1, cw = w >> 1;
-    float ua[C], ub[C];
-    pyrup_at<uint8_t, C>(a_c + (size_t)n * ch * cw * C, ch, cw, y, x, ua);
-    pyrup_at<uint8_t, C>(b_c + (size_t)n * ch * cw * C, ch, cw, y, x, ub);
-    pyrup_at<float, C>(coarse + (size_t)n * ch * cw * C, ch, cw, y, x, up);
+  for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-    for (int c = 0; c < C; ++c) { la[c] -= ua[c]; lb[c] -= ub[c]; }
+    for (int dx = 0; dx < 2; ++dx) {
+      const size_t pix = (size_t)n * h * w + (size_t)(2 * cy + dy) * w + (2 * cx + dx);
+      const float gm = m_f[pix], gi = 1.0f - gm;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {   // the reference's order: ls = la*gm + lb*(1-gm) (separately rounded), then pyrUp(ls_) + ls
+        const float la = (float)a_f[pix * C + c] - ua[dy][dx][c], lb = (float)b_f[pix * C + c] - ub[dy][dx][c];
+        up[dy][dx][c] = __fadd_rn(up[dy][dx][c], __fadd_rn(__fmul_rn(la, gm), __fmul_rn(lb, gi)));
+      }
+    }
+  // the two pixels of a quad row are adjacent: 2 * C floats per row, 8-byte aligned when C is even or the pixel index is even
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    float* o = out + ((size_t)n * h * w + (size_t)(2 * cy + dy) * w + 2 * cx) * C;
+    if ((reinterpret_cast<uintptr_t>(o) & 7) == 0 && (2 * C) % 2 == 0) {
+      const float* src = &up[dy][0][0];
+#pragma unroll
+      for (int k = 0; k < C; ++k) reinterpret_cast<float2*>(o)[k] = make_float2(src[2 * k], src[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2 * C; ++k) o[k] = (&up[dy][0][0])[k];
+    }
   }
-#pragma unroll
-  for (int c = 0; c < C; ++c)       // the reference's order: ls = la*gm + lb*(1-gm) (separately rounded), then pyrUp(ls_) + ls
-    out[pix * C + c] = __fadd_rn(up[c], __fadd_rn(__fmul_rn(la[c], gm), __fmul_rn(lb[c], gi)));
 }
 
 }  // namespace s2v
@@ -159,13 +219,24 @@ extern "C" int s2v_lap_blend_level(const float* coarse_out, const uint8_t* a_fin
   if (N == 0) return S2V_OK;
   if (!a_fine || !b_fine || !m_fine || !out || N < 0 || h <= 0 || w <= 0) return S2V_EINVAL;
   if (coarse_out && (!a_coarse || !b_coarse || (h & 1) || (w & 1))) return S2V_EINVAL;   // pyrUp doubles: fine = 2 x coarse
-  const int grid = ceil_div((long long)N * h * w, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (C) {
-    case 1: launch_pdl(blend_level_kernel<1>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
-    case 3: launch_pdl(blend_level_kernel<3>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
-    case 4: launch_pdl(blend_level_kernel<4>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
-    default: return S2V_EINVAL;
+  if (!coarse_out) {
+    const long long total = (long long)N * h * w;
+    const int grid = ceil_div(total, 256);
+    switch (C) {
+      case 1: launch_pdl(blend_top_kernel<1>, grid, 256, 0, st, a_fine, b_fine, m_fine, total, out); break;
+      case 3: launch_pdl(blend_top_kernel<3>, grid, 256, 0, st, a_fine, b_fine, m_fine, total, out); break;
+      case 4: launch_pdl(blend_top_kernel<4>, grid, 256, 0, st, a_fine, b_fine, m_fine, total, out); break;
+      default: return S2V_EINVAL;
+    }
+  } else {
+    const int grid = ceil_div((long long)N * (h / 2) * (w / 2), 256);
+    switch (C) {
+      case 1: launch_pdl(blend_level_kernel<1>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
+      case 3: launch_pdl(blend_level_kernel<3>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
+      case 4: launch_pdl(blend_level_kernel<4>, grid, 256, 0, st, coarse_out, a_fine, b_fine, m_fine, a_coarse, b_coarse, N, h, w, out); break;
+      default: return S2V_EINVAL;
+    }
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;
