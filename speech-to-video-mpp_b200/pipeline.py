@@ -113,6 +113,9 @@ def stream_batches(net, batches, depth: int = 3):
         if pending is not None:                     # issue the previous batch's forward AFTER this batch's copy-in was queued
             issue_forward(*pending)
         pending = (slot, out_host)
+        if depth == 1:                              # a single slot cannot be refilled before its forward has been issued
+            issue_forward(*pending)
+            pending = None
         n += 1
     if pending is not None:
         issue_forward(*pending)
