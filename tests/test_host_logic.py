@@ -54,6 +54,15 @@ def test_no_cpu_fallback():
         audio.melspectrogram(np.zeros(1600, np.float32))
     with pytest.raises(L.S2VError):
         flow_util.warp_image(torch.zeros(1, 3, 8, 8), torch.zeros(1, 8, 8, 2))
+    from s2v_b200.futils import inference_utils as iu
+    with pytest.raises(L.S2VError):
+        iu.transform_semantic(np.zeros((30, 262), np.float32), 3)
+    with pytest.raises(L.S2VError):
+        iu.semantic_windows(torch.zeros(30, 262), (0, 4))
+    with pytest.raises(L.S2VError):
+        iu.Laplacian_Pyramid_Blending_with_mask(np.zeros((64, 64, 3), np.uint8), np.zeros((64, 64, 3), np.uint8), np.zeros((64, 64), np.float32))
+    with pytest.raises(L.S2VError):
+        iu.laplacian_blend(torch.zeros(1, 64, 64, 3, dtype=torch.uint8), torch.zeros(1, 64, 64, 3, dtype=torch.uint8), torch.zeros(1, 64, 64))
 
 
 def test_choose_box():
