@@ -22,14 +22,19 @@ def obtain_seq_index(index, num_frames):
     return [min(max(item, 0), num_frames - 1) for item in seq]
 
 
+_EXP, _ANGLE = slice(80, 144), slice(224, 227)          # expression / pose columns of the coefficient table
+
+
 def find_crop_norm_ratio(source_coeff, target_coeffs):
-    """inference_utils.py:93-99 (host, once per clip): ratio of the source crop scale to the crop scale of the target
-    frame closest in expression (weight 0.3) and pose (0.7).  numpy in, numpy [1] out, dtype preserved."""
-    alpha = 0.3
-    exp_diff = np.mean(np.abs(target_coeffs[:, 80:144] - source_coeff[:, 80:144]), 1)
-    angle_diff = np.mean(np.abs(target_coeffs[:, 224:227] - source_coeff[:, 224:227]), 1)
-    index = np.argmin(alpha * exp_diff + (1 - alpha) * angle_diff)
-    return source_coeff[:, -3] / target_coeffs[index:index + 1, -3]
+    """inference_utils.py:93-99 (host, once per clip): the source frame's crop scale divided by the crop scale of the
+    target frame that is closest to it in expression (weight 0.3) and pose (weight 0.7), distances being mean absolute
+    coefficient differences.  numpy in, numpy [1] out, dtype preserved (same operation order as the reference, so the
+    argmin - an index, hence bit-exact - sees the same floats)."""
+    w_exp = 0.3
+    d_exp = np.abs(target_coeffs[:, _EXP] - source_coeff[:, _EXP]).mean(axis=1)
+    d_pose = np.abs(target_coeffs[:, _ANGLE] - source_coeff[:, _ANGLE]).mean(axis=1)
+    best = int(np.argmin(w_exp * d_exp + (1 - w_exp) * d_pose))
+    return source_coeff[:, -3] / target_coeffs[best:best + 1, -3]
 
 
 def _ratio_args(crop_norm_ratio):
