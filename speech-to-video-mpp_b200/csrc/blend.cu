@@ -24,69 +24,82 @@ __device__ __forceinline__ int refl101(int p, int n) {
   return p >= n ? 2 * n - 2 - p : p;
 }
 
-// thread = one output pixel (all C channels)
+// thread = a 2 x 2 quad of output pixels (all C channels): the 7 x 7 input window is loaded once (49 instead of 100 pixel
+// loads per quad) and the horizontal sums of a row serve both output rows that use it
 template <typename T, int C>
 __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src, int N, int H, int W, T* __restrict__ dst) {
   pdl_trigger();
   pdl_wait();
   const int oh = (H + 1) >> 1, ow = (W + 1) >> 1;
+  const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * oh * ow) return;
-  const int ox = (int)(idx % ow), oy = (int)((idx / ow) % oh), n = (int)(idx / ((long long)ow * oh));
-  int xs[5], ys[5];
+  if (idx >= (long long)N * qh * qw) return;
+  const int qx = (int)(idx % qw), qy = (int)((idx / qw) % qh), n = (int)(idx / ((long long)qw * qh));
+  int xs[7], ys[7];
 #pragma unroll
-  for (int d = 0; d < 5; ++d) { xs[d] = refl101(2 * ox + d - 2, W); ys[d] = refl101(2 * oy + d - 2, H); }
+  for (int d = 0; d < 7; ++d) { xs[d] = refl101(4 * qx + d - 2, W); ys[d] = refl101(4 * qy + d - 2, H); }
   const T* img = src + (size_t)n * H * W * C;
   using Acc = typename std::conditional<std::is_same<T, float>::value, float, int>::type;
-  Acc row[5][C];
-  const bool interior = 2 * ox - 2 >= 0 && 2 * ox + 2 < W;     // the five columns are contiguous in memory
+  Acc hs[7][2][C];
+  const bool interior = 4 * qx - 2 >= 0 && 4 * qx + 4 < W;     // the seven columns are contiguous in memory
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
+  for (int r = 0; r < 7; ++r) {
     const T* p = img + (size_t)ys[r] * W * C;
-    Acc v[5][C];
+    Acc v[7][C];
     bool done = false;
     if constexpr (std::is_same<T, uint8_t>::value && C == 3) {
-      // 15 contiguous bytes starting at an even offset: seven 16-bit loads + one byte instead of 15 byte loads
-      const uint8_t* q = p + (2 * ox - 2) * 3;
+      // 21 contiguous bytes starting at an even offset: ten 16-bit loads + one byte instead of 21 byte loads
+      const uint8_t* q = p + (4 * qx - 2) * 3;
       if (interior && (reinterpret_cast<uintptr_t>(q) & 1) == 0) {
-        uint32_t b[15];
+        uint32_t b[21];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
+        for (int k = 0; k < 10; ++k) {
           const uint32_t hw = *reinterpret_cast<const unsigned short*>(q + 2 * k);
           b[2 * k] = hw & 0xffu; b[2 * k + 1] = hw >> 8;
         }
-        b[14] = q[14];
+        b[20] = q[20];
 #pragma unroll
-        for (int d = 0; d < 5; ++d)
+        for (int d = 0; d < 7; ++d)
 #pragma unroll
           for (int c = 0; c < 3; ++c) v[d][c] = (Acc)b[d * 3 + c];
         done = true;
       }
     }
     if constexpr (std::is_same<T, float>::value && C == 1) {
-      const float* q = p + (2 * ox - 2);
-      if (interior && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {     // two 8-byte loads + one float instead of five loads
-        const float2 a = *reinterpret_cast<const float2*>(q), b2 = *reinterpret_cast<const float2*>(q + 2);
-        v[0][0] = a.x; v[1][0] = a.y; v[2][0] = b2.x; v[3][0] = b2.y; v[4][0] = q[4];
+      const float* q = p + (4 * qx - 2);
+      if (interior && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {     // three 8-byte loads + one float instead of seven loads
+        const float2 a = *reinterpret_cast<const float2*>(q), b2 = *reinterpret_cast<const float2*>(q + 2),
+                     c2 = *reinterpret_cast<const float2*>(q + 4);
+        v[0][0] = a.x; v[1][0] = a.y; v[2][0] = b2.x; v[3][0] = b2.y; v[4][0] = c2.x; v[5][0] = c2.y; v[6][0] = q[6];
         done = true;
       }
     }
     if (!done) {
 #pragma unroll
-      for (int d = 0; d < 5; ++d)
+      for (int d = 0; d < 7; ++d)
 #pragma unroll
         for (int c = 0; c < C; ++c) v[d][c] = (Acc)p[xs[d] * C + c];
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) row[r][c] = v[2][c] * 6 + (v[1][c] + v[3][c]) * 4 + v[0][c] + v[4][c];
+    for (int c = 0; c < C; ++c) {
+      hs[r][0][c] = v[2][c] * 6 + (v[1][c] + v[3][c]) * 4 + v[0][c] + v[4][c];
+      hs[r][1][c] = v[4][c] * 6 + (v[3][c] + v[5][c]) * 4 + v[2][c] + v[6][c];
+    }
   }
-  T* o = dst + ((size_t)n * oh * ow + (size_t)oy * ow + ox) * C;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const Acc s = row[2][c] * 6 + (row[1][c] + row[3][c]) * 4 + row[0][c] + row[4][c];
-    if constexpr (std::is_same<T, float>::value) o[c] = s * (1.f / 256.f);
-    else o[c] = (T)((s + 128) >> 8);
-  }
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int oy = 2 * qy + dy, ox = 2 * qx + dx;
+      if (oy >= oh || ox >= ow) continue;
+      T* o = dst + ((size_t)n * oh * ow + (size_t)oy * ow + ox) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const Acc s = hs[2 * dy + 2][dx][c] * 6 + (hs[2 * dy + 1][dx][c] + hs[2 * dy + 3][dx][c]) * 4 + hs[2 * dy][dx][c] + hs[2 * dy + 4][dx][c];
+        if constexpr (std::is_same<T, float>::value) o[c] = s * (1.f / 256.f);
+        else o[c] = (T)((s + 128) >> 8);
+      }
+    }
 }
 
 // 3 x 3 coarse neighbourhood of coarse pixel (cy, cx) with pyrUp's border rule (index -1 -> 1, index n -> n-1), as float
@@ -189,7 +202,8 @@ using namespace s2v;
 
 template <typename T>
 static int launch_pyrdown(const T* src, int N, int H, int W, int C, T* dst, cudaStream_t st) {
-  const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
+  const int oh = (H + 1) / 2, ow = (W + 1) / 2;
+  const long long total = (long long)N * ((oh + 1) / 2) * ((ow + 1) / 2);       // one thread per 2 x 2 output quad
   const int grid = ceil_div(total, 256);
   switch (C) {
     case 1: launch_pdl(pyrdown_kernel<T, 1>, grid, 256, 0, st, src, N, H, W, dst); break;
