@@ -261,7 +261,24 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_seq = world * B / (tms.item() / K * 1e-3)
-    e2e_value = e2e_seq
+    # the same K host batches through the package's batch loop (pipeline.stream_batches = the reference's generation loop,
+    # inference.py:259-267, with copy-in / forward / copy-out on three streams): every step still copies its inputs from pinned
+    # host memory and its frames back inside the timed region; the copies of neighbouring steps overlap the forward
+    from s2v_b200.pipeline import stream_batches
+    gen = lambda k: (((mel_h, face_h), out_h) for _ in range(k))
+    stream_batches(net, gen(3))
+    barrier()
+    e0.record()
+    stream_batches(net, gen(K))
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_pipe = world * B / (tms.item() / K * 1e-3)
+    e2e_value = max(e2e_seq, e2e_pipe)
+    e2e_api = ("s2v_b200.pipeline.stream_batches(LNet, pinned host batches): H2D, LNet.forward, D2H per step on three streams" if e2e_pipe >= e2e_seq
+               else "out_h.copy_(LNet.forward(mel_h.to(dev), face_h.to(dev))) per step, pinned host tensors, one stream")
 
     # ---- per-kernel-class device times --------------------------------------------------------------
     # Every class's launches (in plan order) are captured into their OWN CUDA graph and its replay is timed with CUDA
@@ -376,9 +393,9 @@ def main():
                            "gflop_per_frame": FRAME_GFLOP},
                 "tflops_algorithmic": round(value * FRAME_GFLOP / 1e3, 1),
                 "clocks": clocks,
-                "e2e": {"value": round(e2e_seq, 1), "unit": "frames/s",
+                "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
                         "h2d_bytes_per_step": int(mel.numel() * 4 + face.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
-                        "api": "out_h.copy_(LNet.forward(mel_h.to(dev), face_h.to(dev))) per step, pinned host tensors, one stream"},
+                        "api": e2e_api, "stream_batches_value": round(e2e_pipe, 1), "sequential_loop_value": round(e2e_seq, 1)},
                 "gpu_launches": K * len(ent["plan"]),
                 "launches_per_step": len(ent["plan"]),
                 "roofline": roof, "cpu_baseline": cb, "kernel_classes": table, "other_rows": extras}
