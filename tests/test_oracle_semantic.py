@@ -46,3 +46,25 @@ def test_dropin_host_helpers_match_oracle():
     assert iu._ratio_args(np.array([1.5], np.float32)) == (1.5, 1)
     with pytest.raises(ValueError):
         iu._ratio_args(np.ones(2))
+
+
+def test_transform_semantic_property():
+    """Against the literal per-element definition (inference_utils.py:73-91) for random tables, frame indices and ratios."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(1, 60), idx=st.integers(0, 59), seed=st.integers(0, 1000), use_ratio=st.booleans())
+    def run(n, idx, seed, use_ratio):
+        idx = idx % n
+        t = osem.synth_table(n, seed=seed)
+        ratio = np.array([1.0 + (seed % 7) * 0.125], np.float32) if use_ratio else None
+        got = osem.transform_semantic(t, idx, ratio)
+        cols = list(range(80, 144)) + [224, 225, 226, 254, 255, 256, 259, 260, 261]
+        for j in range(26):
+            row = min(max(idx - 13 + j, 0), n - 1)
+            for r, c in enumerate(cols):
+                v = t[row, c]
+                if use_ratio and r == 70:
+                    v = np.float32(v * ratio[0])
+                assert got[r, j] == np.float32(v)
+    run()
