@@ -138,6 +138,12 @@ int s2v_flow_to_deformation_f32(const float* flow, float* deformation, int B, in
 int s2v_warp_deformation_f32(const float* src, const float* deformation, float* out,
                              int B, int C, int H, int W, int h, int w, void* stream);
 
+/* bilinear resize of an fp16 channels-last tensor, align_corners = False (F.interpolate(mode='bilinear') as used by the
+ * ENet upsampler: models/base_blocks.py:42-46 ResBlock x0.5, :500-503 ModulatedConv2d x2, models/ENet.py:93,104).
+ * x, y: views with equal n and c (c a multiple of 8); any h, w.  chan_scale (nullable): float32 [N][C] multiplied into the
+ * result per (image, channel) - the StyleGAN2 modulation of the following conv's input.  Building block for SURVEY 8f #1. */
+int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, void* stream);
+
 /* ------------------------------------------------------------- layout ---
  * NCHW float32 [N,C,H,W] -> fp16 NHWC view channels [c_off, c_off+C); channels
  * [c_off+C, c_off+c_fill) are zero-filled (channel padding to a multiple of 8).

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "s2v_mel_window_count": (c_i64, [c_i64, c_f64]),
     "s2v_mel_window_starts_host": (C.c_int, [c_i64, c_f64, C.POINTER(c_i32), c_i64]),
     "s2v_mel_windows_f32": (C.c_int, [c_vp, c_i64, c_f64, c_i64, c_i64, c_vp, c_vp]),
+    "s2v_resize_bilinear": (C.c_int, [VP, VP, c_vp, c_vp]),
     "s2v_semantic_windows": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, c_f64, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_u8": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),

@@ -106,3 +106,53 @@ extern "C" int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, flo
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
+
+// ---- bilinear resize of fp16 channels-last tensors (align_corners = False, PyTorch's F.interpolate semantics:
+// src = scale * (dst + 0.5) - 0.5 clamped at 0, neighbours clamped at the last row / column).  Building block of the
+// ENet upsampler (ResBlock x0.5 / StyleConv x2 / 96 -> 256, models/base_blocks.py:42-46,500-503,
+// models/ENet.py:93,104); optional per-(n, c) input scale = the StyleGAN2 modulation folded into the resize pass.
+namespace s2v {
+
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(View x, View y, const float* __restrict__ chan_scale) {
+  pdl_trigger();
+  pdl_wait();
+  const int C8 = x.c >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)y.n * y.h * y.w * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  const int ox = (int)((idx / C8) % y.w), oy = (int)((idx / ((long long)C8 * y.w)) % y.h), n = (int)(idx / ((long long)C8 * y.w * y.h));
+  const float sch = (float)x.h / (float)y.h, scw = (float)x.w / (float)y.w;
+  const float sy = fmaxf(sch * ((float)oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)ox + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, x.h - 1), x0 = min((int)sx, x.w - 1);
+  const int y1 = y0 + (y0 < x.h - 1 ? 1 : 0), x1 = x0 + (x0 < x.w - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const __half* p = x.p + n * x.sn + c8 * 8;
+  float a[8], b[8], c[8], d[8], o[8];
+  h8_to_f(ld_h8(p + y0 * x.sh + x0 * x.sw), a);
+  h8_to_f(ld_h8(p + y0 * x.sh + x1 * x.sw), b);
+  h8_to_f(ld_h8(p + y1 * x.sh + x0 * x.sw), c);
+  h8_to_f(ld_h8(p + y1 * x.sh + x1 * x.sw), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float top = a[i] + lx * (b[i] - a[i]), bot = c[i] + lx * (d[i] - c[i]);
+    o[i] = top + ly * (bot - top);
+  }
+  if (chan_scale) {
+    const float4 s0 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * x.c + c8 * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * x.c + c8 * 8 + 4);
+    o[0] *= s0.x; o[1] *= s0.y; o[2] *= s0.z; o[3] *= s0.w; o[4] *= s1.x; o[5] *= s1.y; o[6] *= s1.z; o[7] *= s1.w;
+  }
+  st_h8(y.p + n * y.sn + oy * y.sh + ox * y.sw + c8 * 8, f_to_h8(o));
+}
+
+}  // namespace s2v
+
+extern "C" int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, void* stream) {
+  if (!view_ok(x) || !view_ok(y) || x->n != y->n || x->c != y->c) return S2V_EINVAL;
+  if (y->n == 0) return S2V_OK;
+  const long long total = (long long)y->n * y->h * y->w * (x->c >> 3);
+  launch_pdl(resize_bilinear_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(x), mk(y), chan_scale);
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}

@@ -428,3 +428,23 @@ def test_laplacian_blend_vs_reference_golden_and_oracle(G):
     assert iu.laplacian_blend(dev(A)[:0], dev(B)[:0], dev(m)[:0], 10).shape == (0, 512, 512, 3)
     with pytest.raises(ValueError):
         iu.laplacian_blend(dev(A)[:, :500], dev(B)[:, :500], dev(m)[:, :500], 10)       # 500 is not a multiple of 512
+
+
+@pytest.mark.parametrize("n,c,h,w,oh,ow", [(2, 64, 24, 24, 48, 48), (3, 8, 17, 9, 8, 4), (1, 256, 100, 100, 200, 200), (2, 8, 96, 96, 256, 256), (1, 16, 8, 8, 4, 4)])
+def test_resize_bilinear(G, n, c, h, w, oh, ow):
+    """s2v_resize_bilinear == F.interpolate(mode='bilinear', align_corners=False) on fp16 channels-last tensors, with and
+    without the per-(n, c) scale (ENet building block: models/base_blocks.py:42-46,500-503)."""
+    import ctypes as C
+    lib, L, ops = G.lib(), G.L, G.ops
+    torch.manual_seed(5)
+    x = torch.randn(n, h, w, c, device="cuda").half()
+    scale = torch.rand(n, c, device="cuda") + 0.5
+    for sc in (None, scale):
+        y = torch.full((n, oh, ow, c), float("nan"), device="cuda", dtype=torch.float16)
+        vx, vy = ops.view(x), ops.view(y)
+        L.check(lib.s2v_resize_bilinear(C.byref(vx), C.byref(vy), None if sc is None else sc.data_ptr(), ops.cur_stream()))
+        ref = F.interpolate(x.permute(0, 3, 1, 2).float(), size=(oh, ow), mode="bilinear", align_corners=False)
+        if sc is not None:
+            ref = ref * sc[:, :, None, None]
+        m, rel = G.report("resize %dx%d->%dx%d c%d" % (h, w, oh, ow, c), G.nchw(y), ref)
+        assert rel < 2e-3
