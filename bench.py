@@ -5,8 +5,9 @@
 
 A step = one LNet forward (BASELINE.json configs[1]: batch 128, 96x96 faces, 80x16 mel windows,
 16-bit operands / fp32 accumulation) over a batch of synthetic frames already resident in HBM.
-`value` is whole-job frames/s (all ranks); `e2e` is the same metric through the public drop-in
-module (`LNet.forward`) with pinned HOST inputs, H2D + D2H inside the timed region.
+`value` is whole-job frames/s (all ranks); `e2e` is the same metric with pinned HOST inputs and outputs, every step's
+H2D + D2H inside the timed region, through the package's host batch loop `pipeline.stream_batches(LNet, ...)` (copy-in /
+forward / copy-out on three streams) - the plain one-stream loop around `LNet.forward` is reported beside it.
 N > 1 (torchrun): frames are independent, every rank runs its own batch (weak scaling, no data-path
 collective); time = max over ranks.  --impl reference times the oracle port of the reference's
 PyTorch path on the box's host cores (the reference tree itself cannot travel to the GPU box).
