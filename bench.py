@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the per-frame lip-sync hot path on B200 (contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seconds S]
 
-A step = one LNet forward (BASELINE.json configs[1]: batch 128, 96x96 faces, 80x16 mel windows,
-16-bit operands / fp32 accumulation) over a batch of synthetic frames already resident in HBM.
-`value` is whole-job frames/s (all ranks); `e2e` is the same metric with pinned HOST inputs and outputs, every step's
-H2D + D2H inside the timed region, through the package's host batch loop `pipeline.stream_batches(LNet, ...)` (copy-in /
-forward / copy-out on three streams) - the plain one-stream loop around `LNet.forward` is reported beside it.
-N > 1 (torchrun): frames are independent, every rank runs its own batch (weak scaling, no data-path
-collective); time = max over ranks.  --impl reference times the oracle port of the reference's
-PyTorch path on the box's host cores (the reference tree itself cannot travel to the GPU box).
+The metric is BASELINE.json's: generated frames/s of the FULL per-frame path (mel -> DNet 256x256 -> glue -> LNet 96x96).
+A step = one pass over BASELINE.json configs[3]: a 60 s synthetic clip (960 000 samples -> 4 801 STFT columns -> 1 497
+frames, 25 fps), DNet in batches of <= 64, LNet in batches of <= 128 (`pipeline.LipSyncPipeline`).
+
+* `value`: whole-job frames/s with the clip's inputs (wav, 256x256 sources, 3DMM windows) resident in HBM.  N > 1 (torchrun):
+  STRONG scaling - the same clip is frame-sharded (`parallel.shard_range`: rank r owns a contiguous frame range, full weight
+  replica, whole mel computed locally, no collective on the compute path) and the generated frames are gathered over NVLink
+  with one all_gather (`parallel.gather_frames`) INSIDE the timed region; time = max over ranks.
+* `e2e`: the same step through the same public call with PINNED HOST inputs and outputs: every rank copies its shard's
+  sources / windows / wav to the device and its frames back inside the timed region (copy streams overlap the networks).
+* `roofline`: the dominant kernel class (conv_tc, tcgen05 implicit GEMM) over every plan the step replays, each class timed
+  from its own CUDA graph with CUDA events; `other_rows` carries configs[1] (LNet B=128) and configs[2] (DNet B=64) with their
+  own kernel-class tables, the warp / mel kernels against the HBM roofline and stock PyTorch eager on the same GPU.
+* `--impl reference`: the reference's PyTorch fp32 eager path (oracle port - the reference tree cannot travel to the GPU box)
+  on the box's host cores, same metric, each step a bounded sample of the clip's frames; every declared step really runs.
 """
 from __future__ import annotations
 
@@ -26,8 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FRAME_GFLOP = 56.10            # LNet conv+linear FLOPs per frame (SURVEY A.2 / BASELINE.md section 3)
-METRIC = "generated frames/sec (LNet, 96 px, batch 128)"
+LNET_GFLOP, DNET_GFLOP = 56.10, 101.45          # conv + linear FLOPs per frame
+FRAME_GFLOP = LNET_GFLOP + DNET_GFLOP
+METRIC = "generated frames/sec (LNet+DNet, 96/256 px)"
 
 
 def _peaks():
@@ -73,26 +81,91 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(sample_frames: int, reps: int = 1):
-    """The reference's PyTorch fp32 eager path (oracle port, oracle/nets.py) on the host cores."""
-    import torch
-    from oracle import nets, synth, weights
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = weights.make_state_dict("lnet", 0)
-    mel, face = synth.lnet_inputs(sample_frames, seed=0)
-    with torch.no_grad():
-        nets.lnet_forward(sd, mel[:1], face[:1])          # warm-up (thread pool, allocator)
+# ------------------------------------------------------------------------------------------------ CPU arm
+class CpuPath:
+    """The reference's per-frame path on the host cores (TEST INFRASTRUCTURE used as the baseline): oracle/mel.py (fp64 numpy
+    restatement of futils/audio.py) + oracle/nets.py (functional port of models/DNet.py, models/LNet.py, futils/flow_util.py,
+    fp32 eager) with the reference's own batching: DNet one frame at a time (preprocessing/facing.py:176-194), LNet one
+    frame per forward here (batch 1).  Inputs: the 5 s seeded clip of BASELINE.json configs[0]."""
+
+    def __init__(self):
+        import torch
+        from oracle import mel as omel, nets, synth, weights
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch, self.omel, self.nets = torch, omel, nets
+        self.sd_l, self.sd_d = weights.make_state_dict("lnet", 0), weights.make_state_dict("dnet", 0)
+        self.wav = synth.wav(5.0, seed=0)
+        self.n_clip = len(omel.mel_window_starts(1 + len(self.wav) // 200))      # 122
+        self.src, self.coeff = synth.dnet_inputs(8, seed=1)
+        self.cores = torch.get_num_threads()
         t0 = time.perf_counter()
-        for _ in range(reps):
-            nets.lnet_forward(sd, mel, face)
-        dt = (time.perf_counter() - t0) / reps
-    return {"value": sample_frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle/nets.py lnet_forward fp32 eager, batch %d of the 128-frame step, %d rep(s), %.2f s/rep" % (sample_frames, reps, dt)}
+        self.windows = torch.from_numpy(omel.mel_windows(omel.melspectrogram(self.wav)))
+        self.mel_s = time.perf_counter() - t0                                    # whole-clip mel + window time (122 frames)
+        with torch.no_grad():                                                    # thread pool / allocator warm-up
+            self.frames(1)
+
+    def frames(self, f):
+        """f frames through DNet -> glue -> LNet, one at a time; returns seconds."""
+        torch, nets = self.torch, self.nets
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for i in range(f):
+                j = i % self.src.shape[0]
+                fake = nets.dnet_forward(self.sd_d, self.src[j:j + 1], self.coeff[j:j + 1])["fake_image"]
+                face = nets.glue_dnet_to_lnet(fake)
+                nets.lnet_forward(self.sd_l, self.windows[i % self.n_clip:i % self.n_clip + 1], face)
+        return time.perf_counter() - t0
+
+    def step(self, f):
+        """One bounded sample: the mel of f frames' worth of audio (timed: a fresh melspectrogram of f/122 of the clip,
+        at least 16 columns) + f frames of the networks.  Returns seconds."""
+        n = max(int(len(self.wav) * f / self.n_clip), 16 * 200)
+        t0 = time.perf_counter()
+        self.omel.mel_windows(self.omel.melspectrogram(self.wav[:n]))
+        return (time.perf_counter() - t0) + self.frames(f)
 
 
-def _time(fn, reps, dev):
+def cpu_baseline(sample_frames: int):
+    cp = CpuPath()
+    dt = cp.step(sample_frames)
+    return {"value": sample_frames / dt, "unit": "frames/s", "cores": cp.cores, "kind": "port",
+            "sample": "oracle port (oracle/mel.py + oracle/nets.py, fp32 eager) of mel -> DNet(B=1) -> glue -> LNet(B=1): %d frames of the "
+                      "5 s seeded clip of configs[0] (whole-clip mel %.3f s for 122 frames), %.2f s" % (sample_frames, cp.mel_s, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cp = CpuPath()
+    f = args.ref_frames
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    for _ in range(W):
+        cp.step(f)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        cp.step(f)
+    dt = (time.perf_counter() - t0) / K
+    val = f / dt
+    cb = {"value": val, "unit": "frames/s", "cores": cp.cores, "kind": "port",
+          "sample": "each step = %d frames of the 5 s seeded clip through the oracle port (mel restatement + DNet B=1 -> glue -> LNet B=1, "
+                    "fp32 eager, all host threads); %d warm-up + %d timed steps really run" % (f, W, K)}
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (mel f64)", "data": "synthetic",
+            "config": {"workload": "full per-frame path mel -> DNet 256x256 -> glue -> LNet 96x96 (BASELINE.json configs[3] metric); "
+                                   "bounded sample of %d frames per step on the host cores, reference batching (one frame per forward)" % f,
+                       "frames_per_step": f},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU helpers
+def _time(fn, reps, dev, warm=3):
     import torch
-    for _ in range(3):
+    for _ in range(warm):
         fn()
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -104,92 +177,190 @@ def _time(fn, reps, dev):
     return a.elapsed_time(b) / reps
 
 
-def measure_extras(dev, lnet):
-    """The other rows of the hot path, each timed on the device with inputs resident in
-    HBM: DNet B=64 (configs[2]), the fused warp kernel against the HBM roofline, the mel front end, and
-    the chained full path (configs[3]: 60 s clip, 1497 frames)."""
+def _cls_of(op):
+    return ("conv_tc" if op.name.endswith("[tc]") else "conv_head" if op.name.endswith("[head]")
+            else "conv_simt" if op.name.endswith("[simt]") else op.name)
+
+
+def class_times(dev, ent, reps=3):
+    """Device time of every kernel class of one plan: the class's launches (in plan order) are captured into their OWN CUDA
+    graph and its replay is timed with CUDA events on that stream - pure device time, without the host cost of issuing
+    hundreds of launches one by one.  Returns {class: [ms, launches, alg_flops, alg_bytes, per-layer-roofline ms, hbm-bound launches]}."""
     import torch
-    from oracle import synth, weights
+    peaks = _peaks()
+    classes = {}
+    for op in ent["plan"].ops:
+        classes.setdefault(_cls_of(op), []).append(op)
+    acc = {}
+    side = torch.cuda.Stream(device=dev)
+    for cls, cops in classes.items():
+        with torch.cuda.stream(side):
+            for op in cops:
+                op.run()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for op in cops:
+                    op.run()
+            g.replay()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(side)
+            for _ in range(reps):
+                g.replay()
+            b.record(side)
+            torch.cuda.synchronize(dev)
+        tc_like = cls in ("conv_tc", "conv_head")
+        lay = sum(max(getattr(op, "alg_flops", 0.0) / (peaks["tf_sus"] * 1e12), op.io_bytes / (peaks["hbm"] * 1e9)) * 1e3 for op in cops) if tc_like else 0.0
+        nh = sum(1 for op in cops if op.io_bytes / (peaks["hbm"] * 1e9) > getattr(op, "alg_flops", 0.0) / (peaks["tf_sus"] * 1e12)) if tc_like else 0
+        acc[cls] = [a.elapsed_time(b) / reps, len(cops), sum(getattr(op, "alg_flops", 0.0) for op in cops),
+                    sum(getattr(op, "alg_bytes", 0.0) for op in cops), lay, nh]
+    return acc
+
+
+def class_table(acc_list):
+    """[(acc, uses)] -> (table, totals) summed over plans."""
+    peaks = _peaks()
+    tot = {}
+    for acc, uses in acc_list:
+        for k, v in acc.items():
+            t = tot.setdefault(k, [0.0, 0, 0.0, 0.0, 0.0, 0])
+            for i in range(6):
+                t[i] += v[i] * uses
+    total = sum(v[0] for v in tot.values()) or 1.0
+    table = {}
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0]):
+        row = {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)}
+        if v[3] > 0 and v[0] > 0:          # memory-bound class: algorithmic bytes (each tensor read / written once) vs the measured HBM peak
+            gbs = v[3] / (v[0] * 1e-3) / 1e9
+            row.update({"GBps_algorithmic": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)})
+        if v[2] > 0 and v[0] > 0:
+            tf = v[2] / (v[0] * 1e-3) / 1e12
+            row.update({"TFLOPs_algorithmic": round(tf, 1), "frac_of_tensor_peak": round(tf / peaks["tf_sus"], 3)})
+        table[k] = row
+    return table, tot, total
+
+
+def roofline_of(tot, total, what):
+    peaks = _peaks()
+    tc = tot.get("conv_tc")
+    if not tc or tc[0] <= 0:
+        return None
+    ach = tc[2] / (tc[0] * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 / TMEM / TMA implicit GEMM), %d launches per %s" % (tc[1], what),
+            "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of the class's most frequent shape (LNet 12x12 level, 3x3, K = 9216) from one
+            # ncu --set full capture (profiles/r1c_ncu_full_conv_tc_res2_raw.csv): 56.2 MB read + 1.3 MB written; algorithmic 51.8 MB
+            "traffic": 57.5e6, "traffic_of": "one LNet 3x3 K=9216 launch (ncu --set full, DRAM bytes per launch; algorithmic 51.8e6); other shapes: profiles/",
+            "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+            "alg_gflop": round(tc[2] / 1e9, 1), "kernel_ms": round(tc[0], 3), "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
+            "share_of_step_kernels": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
+            "per_layer_roofline": {"min_ms": round(tc[4], 3), "frac": round(tc[4] / tc[0], 4), "hbm_bound_launches": tc[5],
+                                   "how": "sum over the class's launches of max(flops / tensor peak, min HBM bytes / HBM peak) / measured class time"},
+            "how": "every conv_tc launch of every plan the step replays, replayed from its own CUDA graph, CUDA events on that stream, x uses per step"}
+
+
+def measure_extras(dev, lnet, dnet, args):
+    """configs[1] / configs[2] and the memory-bound kernels, each timed on the device with inputs resident in HBM; plus the
+    stock-PyTorch-eager row (oracle/nets.py on the same GPU: cuDNN / cuBLAS / cuFFT / ATen - SURVEY 2.2's per-kernel bar)."""
+    import torch
+    from oracle import nets, synth, weights
     from s2v_b200.futils import audio, flow_util
-    from s2v_b200.models.DNet import DNet
-    from s2v_b200.pipeline import LipSyncPipeline
     peaks = _peaks()
     out = {}
-    dnet = DNet().to(dev).eval()
-    dnet.load_state_dict(weights.make_state_dict("dnet", 0), strict=True)
+    # ---- configs[1]: LNet B=128 ---------------------------------------------------------------------------------------
+    mel, face = synth.lnet_inputs(128, seed=0)
+    mel, face = mel.to(dev), face.to(dev)
+    leng = lnet.engine()
+    ent = leng.plan_for(128)
+    ent["io"]["mel"].copy_(mel)
+    ent["io"]["face"].copy_(face)
+    ms = _time(lambda: leng._run(ent), 20, dev)
+    table, tot, total = class_table([(class_times(dev, ent), 1)])
+    leng._run(ent)
+    out["lnet_b128"] = {"frames_per_s": round(128 / ms * 1e3, 1), "ms": round(ms, 3), "tflops_algorithmic": round(128 * LNET_GFLOP / ms, 1),
+                        "frac_of_tensor_peak": round(128 * LNET_GFLOP / ms / peaks["tf_sus"], 3), "launches": len(ent["plan"]),
+                        "roofline": roofline_of(tot, total, "forward"), "kernel_classes": table,
+                        "note": "BASELINE.json configs[1]: LNet forward, batch 128, 96x96, graph replay, inputs resident"}
+    # ---- configs[2]: DNet B=64 ----------------------------------------------------------------------------------------
     src, coeff = synth.dnet_inputs(64, seed=0)
     src, coeff = src.to(dev), coeff.to(dev)
-    ms = _time(lambda: dnet(src, coeff), 5, dev)
-    out["dnet_b64"] = {"frames_per_s": round(64 / ms * 1e3, 1), "ms": round(ms, 3),
-                       "tflops_useful": round(64 * 101.45 / ms, 1), "note": "DNet full forward, 256x256, batch 64 (configs[2]); 101.45 useful GFLOP/frame"}
+    deng = dnet.engine()
+    dnet(src, coeff)
+    dent = deng._plans[(64, 26, "full")]
+    ms = _time(lambda: deng._run(dent), 10, dev)
+    table, tot, total = class_table([(class_times(dev, dent), 1)])
+    deng._run(dent)
+    out["dnet_b64"] = {"frames_per_s": round(64 / ms * 1e3, 1), "ms": round(ms, 3), "tflops_useful": round(64 * DNET_GFLOP / ms, 1),
+                       "frac_of_tensor_peak": round(64 * DNET_GFLOP / ms / peaks["tf_sus"], 3), "launches": len(dent["plan"]),
+                       "roofline": roofline_of(tot, total, "forward"), "kernel_classes": table,
+                       "note": "BASELINE.json configs[2]: DNet full forward, 256x256, batch 64; 101.45 useful GFLOP/frame"}
     ms = _time(lambda: dnet(src, coeff, stage="warp"), 5, dev)
     out["dnet_b64_stage_warp"] = {"frames_per_s": round(64 / ms * 1e3, 1), "ms": round(ms, 3)}
-    s, fl = synth.warp_inputs(64, seed=0)
-    s, fl = s.to(dev), fl.to(dev)
+    # ---- the fused warp kernel against the HBM roofline (L2 flushed between launches) -------------------------------------
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def warp_flushed():
-        scratch.zero_()                       # 256 MiB write: evicts the 126 MB L2 between timed launches
-        flow_util.warp_flow(s, fl)
-    ms_both = _time(warp_flushed, 10, dev)
     ms_flush = _time(lambda: scratch.zero_(), 10, dev)
-    ms = max(ms_both - ms_flush, 1e-3)
     gb = 64 * 1605632 / 1e9
-    out["warp_kernel_b64"] = {"us": round(ms * 1e3, 2), "GBps_algorithmic": round(gb / (ms * 1e-3), 1),
-                              "frac_of_hbm_peak": round(gb / (ms * 1e-3) / peaks["hbm"], 3), "hbm_peak_GBps": peaks["hbm"],
-                              "alg_bytes_per_frame": 1605632, "note": "fused flow_to_deformation+resize+grid_sample, fp32, L2 flushed between launches"}
-    wav = torch.from_numpy(synth.wav(60.0, seed=0)).to(dev)
-    ms = _time(lambda: audio.mel_windows(audio.melspectrogram_device(wav)), 10, dev)
-    out["mel_60s_clip"] = {"ms": round(ms, 4), "stft_columns": 4801, "windows": 1497,
-                           "GBps_algorithmic": round((4801 * 1120 + 1497 * 5120) / 1e9 / (ms * 1e-3), 2),
-                           "note": "melspectrogram + 80x16 window gather; launch/latency-bound at this size"}
-    n = 1497
-    srcs, coeffs = synth.dnet_inputs(64, seed=1)
-    srcs = srcs.to(dev).repeat((n + 63) // 64, 1, 1, 1)[:n]
-    coeffs = coeffs.to(dev).repeat((n + 63) // 64, 1, 1)[:n]
-    pipe = LipSyncPipeline(lnet, dnet)
-    for _ in range(2):                        # warm-up: the tail-batch plans (25 / 89 frames) are built and graph-captured here
-        pipe.run(wav, srcs, coeffs)
-    torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    pipe.run(wav, srcs, coeffs)
-    b.record()
-    torch.cuda.synchronize(dev)
-    ms = a.elapsed_time(b)
-    out["full_path_60s_clip"] = {"frames": n, "ms": round(ms, 2), "frames_per_s": round(n / ms * 1e3, 1),
-                                 "note": "mel -> DNet(B=64) -> glue -> LNet(B=128) on one GPU, configs[3] at N=1"}
+    for name, (s, fl) in (("warp_kernel_b64", synth.warp_inputs(64, seed=0)),
+                          ("warp_kernel_b64_dnet_flow", (src.cpu(), dnet(src, coeff, stage="warp")["flow_field"].cpu()))):
+        s, fl = s.to(dev), fl.to(dev)
+
+        def warp_flushed():
+            scratch.zero_()                       # 256 MiB write: evicts the 126 MB L2 between timed launches
+            flow_util.warp_flow(s, fl)
+        ms = max(_time(warp_flushed, 10, dev) - ms_flush, 1e-3)
+        out[name] = {"us": round(ms * 1e3, 2), "GBps_algorithmic": round(gb / (ms * 1e-3), 1),
+                     "frac_of_hbm_peak": round(gb / (ms * 1e-3) / peaks["hbm"], 3), "hbm_peak_GBps": peaks["hbm"], "alg_bytes_per_frame": 1605632,
+                     "note": "fused flow_to_deformation + resize + grid_sample, fp32, " + ("N(0,3^2) synthetic flow (configs[2] iii)" if name == "warp_kernel_b64" else "the flow DNet itself predicts")}
+    # ---- mel front end, 60 s and 600 s clips -----------------------------------------------------------------------------
+    for sec in (60.0, 600.0):
+        wav = torch.from_numpy(synth.wav(sec, seed=0)).to(dev)
+        t_cols = 1 + wav.numel() // 200
+        n_win = audio.mel_window_count(t_cols, 25.0)
+
+        def mel_flushed():
+            scratch.zero_()
+            audio.mel_windows(audio.melspectrogram_device(wav))
+        ms = max(_time(mel_flushed, 10, dev) - ms_flush, 1e-3)
+        gbm = (t_cols * 1120 + n_win * 5120) / 1e9
+        out["mel_%ds_clip" % sec] = {"us": round(ms * 1e3, 2), "stft_columns": t_cols, "windows": n_win, "GBps_algorithmic": round(gbm / (ms * 1e-3), 1),
+                                     "frac_of_hbm_peak": round(gbm / (ms * 1e-3) / peaks["hbm"], 4),
+                                     "note": "melspectrogram + 80x16 window gather (2 launches), L2 flushed; 1120 B per STFT column + 5120 B per window"}
+    # ---- stock PyTorch eager on the same GPU (the oracle port on CUDA) ------------------------------------------------------
+    if not args.no_torch_eager:
+        sdl = {k: v.to(dev) for k, v in weights.make_state_dict("lnet", 0).items()}
+        sdd = {k: v.to(dev) for k, v in weights.make_state_dict("dnet", 0).items()}
+        rows = {}
+        saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ms_l = _time(lambda: nets.lnet_forward(sdl, mel, face), 3, dev, warm=2)
+                ms_d = _time(lambda: nets.dnet_forward(sdd, src, coeff), 3, dev, warm=2)
+            rows[tag] = {"lnet_b128_frames_per_s": round(128 / ms_l * 1e3, 1), "dnet_b64_frames_per_s": round(64 / ms_d * 1e3, 1),
+                         "full_path_frames_per_s": round(1e3 / (ms_l / 128 + ms_d / 64), 1)}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        rows["note"] = ("oracle/nets.py (functional port of the reference modules) in PyTorch eager on this GPU: cuDNN convs, cuBLAS linears, cuFFT, "
+                        "ATen elementwise; full_path = 1 / (LNet B=128 time per frame + DNet B=64 time per frame)")
+        out["torch_eager_b200"] = rows
     return out
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cb = cpu_baseline(args.ref_frames, reps=1)
-    # each "step" = the bounded sample; K steps + W warm-ups would repeat it; one rep is already ~10-30 s of CPU work
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_frames / cb["value"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LNet forward, 96x96, 80x16 mel windows; bounded sample of %d frames per step on host cores" % args.ref_frames},
-            "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128)
-    ap.add_argument("--ref-frames", type=int, default=32)
-    ap.add_argument("--cpu-frames", type=int, default=16)
+    ap.add_argument("--seconds", type=float, default=60.0, help="clip length (60 = configs[3], 600 = configs[4])")
+    ap.add_argument("--lnet-batch", type=int, default=128)
+    ap.add_argument("--dnet-batch", type=int, default=64)
+    ap.add_argument("--ref-frames", type=int, default=2)
+    ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the DNet / warp / mel / full-path side measurements")
-    ap.add_argument("--breakdown", default="", help="write the per-kernel-class time table to this file")
+    ap.add_argument("--no-extras", action="store_true", help="skip the LNet / DNet / warp / mel / torch-eager side measurements")
+    ap.add_argument("--no-torch-eager", action="store_true")
+    ap.add_argument("--no-classes", action="store_true", help="skip the per-kernel-class graphs (no roofline object)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,204 +372,130 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep NCCL's banner ("NCCL version ...", printed to stdout at NCCL_DEBUG >= VERSION) out of the one-line JSON stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("S2V_NCCL_DEBUG", "WARN")
+        # NCCL's init lines (ranks, NVLS / NVLink channels) stay visible, but on stderr: stdout is the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import s2v_b200  # noqa: F401
     from oracle import synth, weights           # synthetic inputs + seeded weights (not on the timed path)
+    from s2v_b200 import parallel
+    from s2v_b200.futils import audio
+    from s2v_b200.models.DNet import DNet
     from s2v_b200.models.LNet import LNet
+    from s2v_b200.pipeline import LipSyncPipeline, balanced_batches
 
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    net = LNet().to(dev).eval()
-    net.load_state_dict(weights.make_state_dict("lnet", 0), strict=True)
-    mel, face = synth.lnet_inputs(B, seed=rank)
-    mel_d, face_d = mel.to(dev), face.to(dev)
-    eng = net.engine()
-    ent = eng.plan_for(B)
-    ent["io"]["mel"].copy_(mel_d)
-    ent["io"]["face"].copy_(face_d)
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    lnet = LNet().to(dev).eval()
+    lnet.load_state_dict(weights.make_state_dict("lnet", 0), strict=True)
+    dnet = DNet().to(dev).eval()
+    dnet.load_state_dict(weights.make_state_dict("dnet", 0), strict=True)
+
+    wav_np = synth.wav(args.seconds, seed=0)
+    total = audio.mel_window_count(1 + len(wav_np) // 200, 25.0)
+    lo, hi = parallel.shard_range(total, rank, world)
+    n = hi - lo
+    # this rank's frames only: frame i uses synthetic source (i mod 64), so shards see the same per-frame inputs as N=1
+    src64, co64 = synth.dnet_inputs(64, seed=1)
+    idx = torch.arange(lo, hi) % 64
+    srcs_h, coeffs_h = src64[idx].contiguous().pin_memory(), co64[idx].contiguous().pin_memory()
+    wav_h = torch.from_numpy(wav_np).pin_memory()
+    out_h = torch.empty(n, 3, 96, 96, dtype=torch.float32).pin_memory()
+    wav, srcs, coeffs = wav_h.to(dev), srcs_h.to(dev), coeffs_h.to(dev)
+    pipe = LipSyncPipeline(lnet, dnet, lnet_batch=args.lnet_batch, dnet_batch=args.dnet_batch)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ------------------------------------------------------------
-    for _ in range(W):
-        eng._run(ent)
-    barrier()
+    def timed(step):
+        for _ in range(W):
+            out = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            out = step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / K, out
+
+    # ---- device-resident throughput (the clip's inputs already in HBM) ------------------------------------------------------
+    def step_dev():
+        return parallel.gather_frames(pipe.run(wav, srcs, coeffs, rank, world), total)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        eng._run(ent)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_step, out = timed(step_dev)
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_step = tms.item() / K
-    value = world * B / (ms_step * 1e-3)
+    assert out.shape[0] == total
+    checksum = float(out.double().sum().item())
+    value = total / (ms_step * 1e-3)
 
-    # ---- end to end through the public API: pinned host -> device -> LNet.forward -> host ---------
-    mel_h, face_h = mel.pin_memory(), face.pin_memory()
-    out_h = torch.empty(B, 3, 96, 96, dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        out_h.copy_(net(mel_h.to(dev, non_blocking=True), face_h.to(dev, non_blocking=True)), non_blocking=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        out_h.copy_(net(mel_h.to(dev, non_blocking=True), face_h.to(dev, non_blocking=True)), non_blocking=True)
-    e1.record()
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    # ---- end to end: pinned host inputs -> device -> path -> pinned host frames, copies inside the timed region ----------------
+    def step_e2e():
+        return parallel.gather_frames(pipe.run(wav_h, srcs_h, coeffs_h, rank, world, out_host=out_h), total)
+    ms_e2e, out2 = timed(step_e2e)
+    e2e_value = total / (ms_e2e * 1e-3)
+    h2d = torch.tensor([float(wav_h.numel() * 4 + srcs_h.numel() * 4 + coeffs_h.numel() * 4)], device=dev)
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_seq = world * B / (tms.item() / K * 1e-3)
-    # the same K host batches through the package's batch loop (pipeline.stream_batches = the reference's generation loop,
-    # inference.py:259-267, with copy-in / forward / copy-out on three streams): every step still copies its inputs from pinned
-    # host memory and its frames back inside the timed region; the copies of neighbouring steps overlap the forward
-    from s2v_b200.pipeline import stream_batches
-    gen = lambda k: (((mel_h, face_h), out_h) for _ in range(k))
-    stream_batches(net, gen(3))
-    barrier()
-    e0.record()
-    stream_batches(net, gen(K))
-    e1.record()
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_pipe = world * B / (tms.item() / K * 1e-3)
-    e2e_value = max(e2e_seq, e2e_pipe)
-    e2e_api = ("s2v_b200.pipeline.stream_batches(LNet, pinned host batches): H2D, LNet.forward, D2H per step on three streams" if e2e_pipe >= e2e_seq
-               else "out_h.copy_(LNet.forward(mel_h.to(dev), face_h.to(dev))) per step, pinned host tensors, one stream")
+        dist.all_reduce(h2d)
+    e2e_ok = bool(torch.equal(out2, out)) and bool(torch.equal(out_h, out[lo:hi].cpu()))
 
-    # ---- per-kernel-class device times --------------------------------------------------------------
-    # Every class's launches (in plan order) are captured into their OWN CUDA graph and its replay is timed with CUDA
-    # events: pure device time of that class's kernels, without the host cost of issuing ~500 launches one by one (an
-    # eager s2v_conv_tc call costs ~12 us of CPU - more than many of the kernels run).  The per-op table of --breakdown
-    # still uses eager events around every launch (host-inflated for short kernels; use it for ranking only).
-    roof, table = None, None
-    if rank == 0:
-        ops_l = ent["plan"].ops
-        cls_of = lambda op: ("conv_tc" if op.name.endswith("[tc]") else "conv_head" if op.name.endswith("[head]")
-                             else "conv_simt" if op.name.endswith("[simt]") else op.name)
-        classes = {}
-        for op in ops_l:
-            classes.setdefault(cls_of(op), []).append(op)
-        acc = {}
-        side = torch.cuda.Stream(device=dev)
-        for cls, cops in classes.items():
-            with torch.cuda.stream(side):
-                for op in cops:
-                    op.run()
-                torch.cuda.synchronize(dev)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    for op in cops:
-                        op.run()
-                g.replay()
-                torch.cuda.synchronize(dev)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 3
-                a.record(side)
-                for _ in range(reps):
-                    g.replay()
-                b.record(side)
-                torch.cuda.synchronize(dev)
-            acc[cls] = [a.elapsed_time(b) / reps, len(cops), sum(getattr(op, "alg_flops", 0.0) for op in cops),
-                        sum(getattr(op, "alg_bytes", 0.0) for op in cops)]
-        total = sum(v[0] for v in acc.values())
-        peaks = _peaks()
-        # per-layer roofline of the tensor-core class: a layer cannot run faster than max(flops / tensor peak, bytes / HBM peak);
-        # many of LNet's layers (1x1 spectral convs, 48x48 / 96x96 levels with 48-128 channels) are HBM-bound by that measure
-        lay_ms = sum(max(op.alg_flops / (peaks["tf_sus"] * 1e12), op.io_bytes / (peaks["hbm"] * 1e9)) * 1e3 for op in classes.get("conv_tc", []))
-        lay_hbm = sum(1 for op in classes.get("conv_tc", []) if op.io_bytes / (peaks["hbm"] * 1e9) > op.alg_flops / (peaks["tf_sus"] * 1e12))
-        table = {}
-        for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0]):
-            table[k] = {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)}
-            if v[3] > 0:       # memory-bound class: algorithmic bytes (each tensor read / written once) against the measured HBM peak
-                gbs = v[3] / (v[0] * 1e-3) / 1e9
-                table[k].update({"GBps_algorithmic": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)})
-        tc = acc.get("conv_tc")
-        if tc:
-            ach = tc[2] / (tc[0] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % tc[1],
-                    "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the step's dominant conv_tc shape (12x12 level, 3x3, K = 9216:
-                    # 36 of the 245 launches, ~23 % of the class time) from profiles/r1c_ncu_full_conv_tc_res2_raw.csv (56.2 MB read +
-                    # 1.3 MB written to DRAM; the 9.4 MB output is still in L2 when the kernel ends); its algorithmic bytes are 51.8 MB
-                    # (37.7 in + 4.7 weights + 9.4 out), the rest is the 148 CTAs' weight tiles missing L2.  Other shapes: profiles/r1c_summary.md
-                    "traffic": 57.5e6, "traffic_of": "one 3x3 K=9216 launch (ncu --set full, DRAM bytes per launch; algorithmic 51.8e6)",
-                    "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                    "alg_gflop_per_step": round(tc[2] / 1e9, 1), "kernel_ms_per_step": round(tc[0], 3),
-                    "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
-                    "share_of_step": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
-                    "per_layer_roofline": {"min_ms_per_step": round(lay_ms, 3), "frac": round(lay_ms / tc[0], 4), "hbm_bound_launches": lay_hbm,
-                                           "how": "sum over the class's launches of max(flops / tensor peak, min HBM bytes / HBM peak) / measured class time"},
-                    "how": "all conv_tc launches of one step replayed from their own CUDA graph, CUDA events on that stream"}
-        if args.breakdown:
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops_l]
-            reps = 3
-            per_op = {}
-            for r in range(reps):
-                torch.cuda.synchronize(dev)
-                for op, (a, b) in zip(ops_l, evs):
-                    a.record()
-                    op.run()
-                    b.record()
-                torch.cuda.synchronize(dev)
-                if r == 0:
-                    continue                      # first eager pass = warm-up
-                for op, (a, b) in zip(ops_l, evs):
-                    po = per_op.setdefault(op.name, [0.0, 0, 0.0])
-                    po[0] += a.elapsed_time(b) / (reps - 1)
-                    po[1] += 1 if r == 1 else 0
-                    po[2] += getattr(op, "alg_flops", 0.0) if r == 1 else 0.0
-            with open(args.breakdown, "w") as f:
-                import re
-                grouped = {}
-                for name, v in per_op.items():          # fold the 9 blocks x 2 convs of a decoder level together
-                    key = re.sub(r"res(\d)\.res\d\.conv\d", r"res\1.*", name)
-                    key = re.sub(r"layers\.\d", "layers.*", key)
-                    key = re.sub(r"audio_encoder\.\d+", "audio_encoder.*", key)
-                    g = grouped.setdefault(key, [0.0, 0, 0.0])
-                    g[0] += v[0]; g[1] += v[1]; g[2] += v[2]
-                rows = [{"op": k, "ms": round(v[0], 4), "launches": v[1], "us_per_launch": round(1e3 * v[0] / max(v[1], 1), 2),
-                         "tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1) if v[2] and v[0] > 0 else None}
-                        for k, v in sorted(grouped.items(), key=lambda kv: -kv[1][0])]
-                json.dump({"per_class": table, "sum_ms": sum(v[0] for v in per_op.values()), "ms_per_step_graph": ms_step, "per_op_group": rows}, f, indent=1)
-        eng._run(ent)                             # leave the workspace in a consistent state again
+    # ---- launches per step + per-kernel-class device times of every plan the step replays ---------------------------------------
+    leng, deng = lnet.engine(), dnet.engine()
+    d_sizes, l_sizes = balanced_batches(n, args.dnet_batch), balanced_batches(n, args.lnet_batch)
+    pad8 = lambda b: b if (b < 8 or b % 8 == 0) else (b + 7) // 8 * 8
+    uses = []                                       # (engine, plan key, uses per step)
+    for b in sorted(set(pad8(x) for x in l_sizes)):
+        uses.append((leng, b, sum(1 for x in l_sizes if pad8(x) == b)))
+    for b in sorted(set(pad8(x) for x in d_sizes)):
+        uses.append((deng, (b, 26, "full"), sum(1 for x in d_sizes if pad8(x) == b)))
+    launches = 2 + len(d_sizes) + sum(len(e._plans[k]["plan"]) * u for e, k, u in uses)      # mel + windows, one glue per DNet batch
+    lt = torch.tensor([float(launches)], device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    roof = table = None
+    if rank == 0 and not args.no_classes:
+        acc_list = [(class_times(dev, e._plans[k]), u) for e, k, u in uses]
+        table, tot, total_ms = class_table(acc_list)
+        roof = roofline_of(tot, total_ms, "step (rank 0's shard)")
+        for e, k, u in uses:                         # leave the workspaces in a consistent state again
+            e._run(e._plans[k])
         torch.cuda.synchronize(dev)
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = measure_extras(dev, net)
+        extras = measure_extras(dev, lnet, dnet, args)
     if rank == 0:
-        cb = None if args.no_cpu_baseline else cpu_baseline(args.cpu_frames)
+        cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_frames)
+        peaks = _peaks()
         line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-                "config": {"workload": "BASELINE.json configs[1]: LNet forward, batch %d per GPU, 96x96 faces, 80x16 mel windows, "
-                                       "seeded random-init weights (oracle/weights.py seed 0)" % B,
-                           "frames_per_step_per_gpu": B, "l2": "per-step working set (>1 GB of activations + 255 MB weights) exceeds the 126 MB L2; no explicit flush",
-                           "parallelism": "frame-sharded x%d, no data-path collective" % world,
-                           "gflop_per_frame": FRAME_GFLOP},
+                "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (mel, warp, statistics f32)", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[3]: full per-frame path mel -> DNet(256x256, batches <= %d) -> glue -> LNet(96x96, batches <= %d) "
+                                       "on a %.0f s synthetic clip (%d frames), seeded random-init weights (oracle/weights.py seed 0)"
+                                       % (args.dnet_batch, args.lnet_batch, args.seconds, total),
+                           "frames_per_step": total, "frames_per_rank": n,
+                           "parallelism": "frame-sharded x%d (contiguous ranges), no data-path collective, one final all_gather of the frames over NVLink inside the timed region" % world,
+                           "l2": "inputs larger than L2: %.2f GB of sources per rank and > 1 GB of activations per batch against the 126 MB L2; no explicit flush" % (srcs.numel() * 4 / 1e9),
+                           "gflop_per_frame": FRAME_GFLOP, "dnet_lnet_overlap": bool(pipe.overlap)},
                 "tflops_algorithmic": round(value * FRAME_GFLOP / 1e3, 1),
+                "frac_of_tensor_peak_whole_step": round(value * FRAME_GFLOP / 1e3 / (peaks["tf_sus"] * world), 4),
                 "clocks": clocks,
-                "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
-                        "h2d_bytes_per_step": int(mel.numel() * 4 + face.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
-                        "api": e2e_api, "stream_batches_value": round(e2e_pipe, 1), "sequential_loop_value": round(e2e_seq, 1)},
-                "gpu_launches": K * len(ent["plan"]),
-                "launches_per_step": len(ent["plan"]),
+                "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
+                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(total * 3 * 96 * 96 * 4),
+                        "api": "s2v_b200.pipeline.LipSyncPipeline.run(pinned host wav / sources / windows, out_host=pinned frames): every rank stages its "
+                               "shard batch by batch on a copy stream and copies its frames back on another; + parallel.gather_frames",
+                        "matches_device_resident_run": e2e_ok},
+                "gpu_launches": int(K * lt.item()), "launches_per_step": int(lt.item()),
+                "frame_checksum": checksum,
                 "roofline": roof, "cpu_baseline": cb, "kernel_classes": table, "other_rows": extras}
         print(json.dumps(line))
     if world > 1:

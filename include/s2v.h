@@ -23,7 +23,8 @@
  *   - activations between kernels are fp16, channels-last ("NHWC") views:
  *     element (n,y,x,c) of a view lives at ptr + n*sN + y*sH + x*sW + c
  *     (strides in ELEMENTS; channel stride is 1; C and strides multiples of 8)
- *   - thread-safe for distinct streams; no mutable global state
+ *   - thread-safe for distinct streams and devices; the only process-wide state is immutable after its first
+ *     use (per-device kernel attributes / SM counts, resolved entry points, S2V_* development knobs)
  */
 #ifndef S2V_H_
 #define S2V_H_
@@ -209,22 +210,6 @@ typedef struct {
    * zero.  The kernel may then run those K chunks as narrower MMAs and keep only the non-zero rows in shared memory
    * (FFC at 48x48: the global half of the input reaches only the 32 local outputs).  0 = no hint.           */
   int32_t narrow_cin_from, narrow_cout;
-  /* s2v_conv_tc with stats_partial: finalize the statistics inside the same launch (replaces a s2v_adain_finalize /
-   * s2v_ln2d_finalize call).  Behind a grid-wide barrier of the (persistent, fully resident) kernel the epilogue groups
-   * compute, for every image and the channels this launch produced,
-   *   fin_mode 1 (AdaIN):       a = rstd_c*(1+gamma[n*gb_stride+c]),  b = beta[n*gb_stride+c] - mean_c*a
-   *   fin_mode 2 (LayerNorm2d): a = rstd*gamma[c],                    b = beta[c] - mean*a   (statistics over C,H,W)
-   * from ALL chunks of stats_partial into fin_a / fin_b [N][stats_c_total] - when several launches fill the partials
-   * (sub-pixel phases of an up-conv) only the last one carries fin_mode.  fin_counter: int32[2], zero before the first
-   * launch (the kernel leaves it zero).  fin_inv_count = 1 / (values per statistic).  fin_launches: reserved.          */
-  int32_t fin_mode, fin_launches;
-  const float* fin_gamma;
-  const float* fin_beta;
-  int64_t fin_gb_stride;
-  float*  fin_a;
-  float*  fin_b;
-  int32_t* fin_counter;
-  float   fin_inv_count, fin_eps;
 } s2v_conv;
 
 /* SIMT direct convolution (small / awkward layers: Cin=3 7x7, Cout=3, audio

@@ -37,3 +37,51 @@ def load():
     from models.DNet import DNet          # noqa
     from futils import flow_util          # noqa
     return LNet, DNet, flow_util
+
+
+def load_audio():
+    """Imports the UNMODIFIED ``/root/reference/futils/audio.py`` with a stub ``librosa`` module.
+
+    librosa (pinned ==0.9.2 in the reference's requirements.txt) is not installable here, so the three librosa entry points
+    the file calls are bound to the oracle's restatements: ``librosa.stft`` -> oracle.mel.stft, ``librosa.filters.mel`` ->
+    oracle.mel.mel_basis, ``librosa.core.load`` -> oracle.resample.load_wav.  Everything else in the file runs as it is:
+    ``preemphasis`` (the real scipy.signal.lfilter), ``_linear_to_mel``, ``_amp_to_db``, ``_normalize``, the order of
+    operations of ``melspectrogram`` and the ``hparams`` binding.  Goldens made through this shim therefore pin rows a1 / a4
+    of SURVEY section 8 and the glue of a2 / a3 to the reference itself; the STFT and mel-basis arithmetic stay
+    "unpinned at librosa".  Returns the imported module."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    sys.dont_write_bytecode = True
+    import numpy as np
+    from . import mel as omel
+
+    def _stft(y=None, n_fft=2048, hop_length=None, win_length=None, **kw):
+        assert (n_fft, hop_length, win_length) == (omel.N_FFT, omel.HOP, omel.WIN) and not kw, "stub covers the reference's call only"
+        return omel.stft(np.asarray(y))
+
+    def _mel(sr=None, n_fft=None, n_mels=128, fmin=0.0, fmax=None, **kw):
+        assert (sr, n_fft, n_mels, fmin, fmax) == (omel.SR, omel.N_FFT, omel.NUM_MELS, omel.FMIN, omel.FMAX) and not kw
+        return omel.mel_basis()
+
+    def _load(path, sr=22050, **kw):
+        from . import resample
+        return resample.load_wav(path, sr), sr
+
+    lib = types.ModuleType("librosa")
+    lib.filters = types.ModuleType("librosa.filters")
+    lib.core = types.ModuleType("librosa.core")
+    lib.stft, lib.filters.mel, lib.core.load, lib.load = _stft, _mel, _load, _load
+    saved = {k: sys.modules.get(k) for k in ("librosa", "librosa.filters", "librosa.core")}
+    sys.modules.update({"librosa": lib, "librosa.filters": lib.filters, "librosa.core": lib.core})
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    try:
+        import importlib
+        mod = importlib.import_module("futils.audio")
+    finally:
+        for k, v in saved.items():          # do not leave the stub visible to anything else (e.g. transformers probing librosa)
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

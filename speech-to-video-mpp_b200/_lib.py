@@ -30,9 +30,7 @@ class Conv(C.Structure):
                 ("x2", View), ("k2h", c_i32), ("k2w", c_i32), ("pad2_h", c_i32), ("pad2_w", c_i32),
                 ("stats_partial", c_vp), ("stats_c_off", c_i32), ("stats_c_total", c_i32),
                 ("stats_chunk_off", c_i32), ("stats_chunks_total", c_i32), ("stats_groups", c_i32), ("stats_gmax", c_i32),
-                ("narrow_cin_from", c_i32), ("narrow_cout", c_i32),
-                ("fin_mode", c_i32), ("fin_launches", c_i32), ("fin_gamma", c_vp), ("fin_beta", c_vp), ("fin_gb_stride", c_i64),
-                ("fin_a", c_vp), ("fin_b", c_vp), ("fin_counter", c_vp), ("fin_inv_count", c_f32), ("fin_eps", c_f32)]
+                ("narrow_cin_from", c_i32), ("narrow_cout", c_i32)]
 
 
 class LinGroup(C.Structure):

@@ -20,5 +20,12 @@ extern "C" int s2v_device_ok(void) {
   return major == 10 ? S2V_OK : S2V_EUNSUPPORTED;
 }
 
-// last CUDA error text of this library's runtime instance (diagnostics for the Python wrapper)
-extern "C" const char* s2v_last_cuda_error(void) { return cudaGetErrorString(cudaPeekAtLastError()); }
+// The cudaError_t behind the calling thread's most recent S2V_ECUDA return.  (S2V_CHECK_LAUNCH consumes the runtime's
+// sticky-free error with cudaGetLastError, so it is kept here; cudaPeekAtLastError alone would read "no error".)
+static thread_local cudaError_t t_last_error = cudaSuccess;
+void s2v::note_cuda_error(cudaError_t e) { t_last_error = e; }
+
+extern "C" const char* s2v_last_cuda_error(void) {
+  const cudaError_t e = t_last_error != cudaSuccess ? t_last_error : cudaPeekAtLastError();
+  return cudaGetErrorString(e);
+}

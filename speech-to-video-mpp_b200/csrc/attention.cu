@@ -208,8 +208,13 @@ extern "C" int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_vie
   if (k->n != q->n || v->n != q->n || o->n != q->n) return S2V_EINVAL;
   if (T == 144 && !getenv("S2V_ATTN_SIMT")) {      // the LNet geometry (12 x 12 tokens): tensor-core path
     const size_t smem_tc = (size_t)3 * 144 * kRowH * sizeof(__half);
-    static bool attr_tc = false;     // idempotent
-    if (!attr_tc) { cudaFuncSetAttribute(attention_mma_kernel<144>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc); attr_tc = true; }
+    static DeviceOnce attr_tc;       // per device, idempotent
+    const int dev = current_device();
+    if (dev < 0) return S2V_ECUDA;
+    if (attr_tc.needed(dev)) {
+      S2V_CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel<144>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      attr_tc.mark(dev);
+    }
     launch_pdl(attention_mma_kernel<144>, q->n * heads, 288, smem_tc, (cudaStream_t)stream, mk(q), mk(k), mk(v), mk(o), heads,
                scale * 1.4426950408889634f);
     S2V_CHECK_LAUNCH();
@@ -218,8 +223,13 @@ extern "C" int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_vie
   const int threads = ((T + 31) / 32) * 32;
   const size_t smem = (size_t)2 * T * kDh * sizeof(__half);
   if (smem > 48 * 1024) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxT * kDh * 2); attr = true; }
+    static DeviceOnce attr;
+    const int dev = current_device();
+    if (dev < 0) return S2V_ECUDA;
+    if (attr.needed(dev)) {
+      S2V_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxT * kDh * 2));
+      attr.mark(dev);
+    }
   }
   launch_pdl(attention_kernel, q->n * heads, threads, smem, (cudaStream_t)stream, mk(q), mk(k), mk(v), mk(o), heads,
                                                                          scale * 1.4426950408889634f);

@@ -7,13 +7,51 @@
 
 #include "../../include/s2v.h"
 
+#include <atomic>
+
+namespace s2v {
+// The failing cudaError_t of the calling thread's last S2V_ECUDA return (api.cu); s2v_last_cuda_error() reports it.
+void note_cuda_error(cudaError_t e);
+}  // namespace s2v
+
 #define S2V_CHECK_LAUNCH()                                   \
   do {                                                       \
     cudaError_t e__ = cudaGetLastError();                    \
-    if (e__ != cudaSuccess) return S2V_ECUDA;                \
+    if (e__ != cudaSuccess) { s2v::note_cuda_error(e__); return S2V_ECUDA; } \
+  } while (0)
+// for runtime calls that return their own status (cudaFuncSetAttribute, cudaLaunchKernelEx, ...)
+#define S2V_CUDA_TRY(expr)                                   \
+  do {                                                       \
+    cudaError_t e__ = (expr);                                \
+    if (e__ != cudaSuccess) { s2v::note_cuda_error(e__); (void)cudaGetLastError(); return S2V_ECUDA; } \
   } while (0)
 
 namespace s2v {
+
+// ---- per-device one-time state ----------------------------------------------------------------------------
+// Function attributes (MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a library
+// used on several GPUs from one process must set / query them once per device.  Lock-free, idempotent (two threads racing
+// on the first call both set the same attribute value).
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return -1;
+  return d;
+}
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool needed(int dev) const { return !(done.load(std::memory_order_acquire) >> dev & 1ull); }
+  void mark(int dev) { done.fetch_or(1ull << dev, std::memory_order_release); }
+};
+static inline int sm_count(int dev) {
+  static std::atomic<int> n_sm[kMaxDevices];
+  int v = n_sm[dev].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return -1;
+    n_sm[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
 // A forward is ~570 small dependent kernels replayed from a CUDA graph.  Every kernel of the library is launched

@@ -313,19 +313,17 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return S2V_ECUDA;
   }
-  static bool attr = false;   // idempotent
-  if (!attr) {
-    if (cudaFuncSetAttribute(conv_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
-    attr = true;
+  static DeviceOnce attr;     // per device, idempotent
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  if (attr.needed(dev)) {
+    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr.mark(dev);
   }
-  static int n_sm = 0;        // immutable after the first call
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
-      return S2V_ECUDA;
-  }
+  const int n_sm = sm_count(dev);
+  if (n_sm <= 0) return S2V_ECUDA;
   const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
-  launch_pdl(conv_head_kernel, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p);
+  S2V_CUDA_TRY(launch_pdl(conv_head_kernel, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -40,16 +40,6 @@ struct TcParams {
   int cin_chunks, cout, bn, stages, tmem_cols, ring_bytes;
   int m_tiles, total_tiles, tmem_buf_cols, stage_out_bytes, use_tma_store, pass_cols, stage_bufs, n_tiles_n, epi_groups;
   int tab;                                                // per-group scale / bias table length (bn rounded up to 32)
-  // in-kernel finalize of the fused statistics (replaces a s2v_adain_finalize / s2v_ln2d_finalize launch): the epilogue
-  // group that contributes the LAST partial of an image turns the partials into the per-(image, channel) scale / shift
-  int fin_mode, fin_needed;                               // 0 none, 1 AdaIN (instance norm), 2 LayerNorm2d
-  const float* fin_gamma;
-  const float* fin_beta;
-  long long fin_gb_stride;
-  float* fin_a;
-  float* fin_b;
-  int* fin_counter;
-  float fin_inv_count, fin_eps;
   int nf_chunk, bn_narrow;                                // segment-0 chunks >= nf_chunk run as N = bn_narrow MMAs (0 = off)
   int m_pairs, total_pair_tiles;                          // CTA-pair mode: the pair (leader, peer) owns M tiles (2*mp, 2*mp+1)
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
@@ -277,64 +267,6 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int cra
   x0 = tw * p.box_w; y0 = th * p.box_h; n0 = tn * p.box_n;
 }
 
-// Statistics partials [N][chunks][C][2] of image n -> scale a / shift b (same arithmetic as norm.cu's finalize kernels:
-// double accumulation in a fixed order, so the result does not depend on which CTA runs it).  Called by the 128 threads
-// of one epilogue group; red = 8 doubles of scratch per group.
-struct FinArgs {           // passed by value: a reference to the kernel's TcParams would force a local-memory copy of it
-  const float* stats; const float* gamma; const float* beta; float* a; float* b;
-  long long gb_stride; int chunks, C, c_off, cout, mode; float inv_count, eps;
-};
-__device__ __noinline__ void finalize_image(const FinArgs p, int n, int et, double* red, uint32_t bar_id) {
-  const int chunks = p.chunks, C = p.C;
-  const float2* base = reinterpret_cast<const float2*>(p.stats) + (size_t)n * chunks * C + p.c_off;
-  if (p.mode == 1) {
-    for (int c = et; c < p.cout; c += 128) {
-      double sd = 0.0, qd = 0.0;
-#pragma unroll 4
-      for (int k = 0; k < chunks; ++k) {
-        const float2 v = __ldcg(base + (size_t)k * C + c);
-        sd += (double)v.x; qd += (double)v.y;
-      }
-      const double mean = sd * (double)p.inv_count;
-      double var = qd * (double)p.inv_count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-      const int cc = p.c_off + c;
-      const float g = p.gamma ? p.gamma[(size_t)n * p.gb_stride + cc] : 0.f;
-      const float be = p.beta ? p.beta[(size_t)n * p.gb_stride + cc] : 0.f;
-      const float av = rstd * (1.f + g);
-      p.a[(size_t)n * C + cc] = av;
-      p.b[(size_t)n * C + cc] = be - (float)mean * av;
-    }
-  } else {
-    double sd = 0.0, qd = 0.0;
-    for (int c = et; c < p.cout; c += 128) {
-#pragma unroll 4
-      for (int k = 0; k < chunks; ++k) {
-        const float2 v = __ldcg(base + (size_t)k * C + c);
-        sd += (double)v.x; qd += (double)v.y;
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(0xffffffffu, sd, o); qd += __shfl_xor_sync(0xffffffffu, qd, o); }
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // scratch free (previous image)
-    if ((et & 31) == 0) { red[(et >> 5) * 2] = sd; red[(et >> 5) * 2 + 1] = qd; }
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    sd = (red[0] + red[2]) + (red[4] + red[6]);
-    qd = (red[1] + red[3]) + (red[5] + red[7]);
-    const double mean = sd * (double)p.inv_count;
-    double var = qd * (double)p.inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    const float fmean = (float)mean;
-    for (int c = et; c < p.cout; c += 128) {
-      const int cc = p.c_off + c;
-      const float av = rstd * p.gamma[cc];
-      p.a[(size_t)n * C + cc] = av;
-      p.b[(size_t)n * C + cc] = p.beta[cc] - fmean * av;
-    }
-  }
-}
-
 // Epilogue warps (4): for every tile of this CTA, TMEM -> registers -> scale/bias/activation ->
 // (fp16 tile staged in smem -> optional column statistics -> coalesced 16-byte stores [+ residual]) or direct
 // stores (fp32 NCHW heads, pre-activation residual).  Runs concurrently with the producer / MMA warps
@@ -356,8 +288,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
   float* const s_scale = sm.s_scale + 2 * p.tab * grp;
   float* const s_bias = s_scale + p.tab;
   uint8_t* const s_valid = sm.s_valid + 128 * grp;
-  uint8_t* const s_flag = sm.s_valid + 256 + 16 * grp;                              // per-image 'this group finalizes' flags
-  double* const s_red = reinterpret_cast<double*>(sm.s_valid + 384) + 8 * grp;       // LayerNorm2d finalize scratch
   const int m = q * 32 + lane;                     // tile row owned in phase 1
   const int ww = m % p.box_w, hh = (m / p.box_w) % p.box_h, nn = m / (p.box_w * p.box_h);
   const bool direct = (p.out_mode == S2V_OUT_F32_NCHW) || (p.r1.p != nullptr);
@@ -629,37 +559,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         }
       }
       if (p.stage_bufs == 2 && p.epi_groups == 1) sb ^= 1u;
-    }
-  }
-  if (p.stats && p.fin_mode) {
-    // In-kernel finalize (replaces a finalize launch).  The kernel is persistent with every CTA resident (grid <= #SMs,
-    // one CTA per SM), so the epilogue groups can meet at a grid-wide barrier once their partials are stored; behind it
-    // the images are dealt round-robin to the groups, each turning [chunks][C] partials into per-channel scale / shift.
-    // (Counting arrivals per image instead makes the slowest CTA the last arriver - and sole finalizer - of every image it
-    // touched; a synchronous atomic per tile sits on the epilogue's critical path.  Both measured 35 % slower.)
-    const int groups_total = (int)gridDim.x * p.epi_groups;
-    __threadfence();                                         // this thread's partial stores are visible device-wide
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    if (et == 0) {
-      atomicAdd(p.fin_counter, 1);
-      unsigned spins = 0;
-      while (*reinterpret_cast<volatile int*>(p.fin_counter) < groups_total) {
-        __nanosleep(64);
-        if (++spins > (kSpinLimit >> 4)) __trap();
-      }
-      __threadfence();
-    }
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    FinArgs fa;
-    fa.stats = p.stats; fa.gamma = p.fin_gamma; fa.beta = p.fin_beta; fa.a = p.fin_a; fa.b = p.fin_b;
-    fa.gb_stride = p.fin_gb_stride; fa.chunks = p.st_chunks_total; fa.C = p.st_c_total; fa.c_off = p.st_c_off;
-    fa.cout = p.cout; fa.mode = p.fin_mode; fa.inv_count = p.fin_inv_count; fa.eps = p.fin_eps;
-    for (int n = (int)blockIdx.x * p.epi_groups + grp; n < p.N; n += groups_total) finalize_image(fa, n, et, s_red, bar_id);
-    // re-arm the counters for the next launch / graph replay: the last group to LEAVE does it (everybody has passed the
-    // wait above by then)
-    if (et == 0 && atomicAdd(p.fin_counter + 1, 1) == groups_total - 1) {
-      p.fin_counter[0] = 0;
-      p.fin_counter[1] = 0;
     }
   }
 }
@@ -1193,18 +1092,13 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.st_c_off = d->stats_c_off; p.st_c_total = d->stats_c_total;
   p.st_chunk_off = d->stats_chunk_off; p.st_chunks_total = d->stats_chunks_total;
   p.st_groups = d->stats_groups; p.st_gmax = d->stats_gmax;
-  p.fin_mode = d->fin_mode; p.fin_gamma = d->fin_gamma; p.fin_beta = d->fin_beta; p.fin_gb_stride = d->fin_gb_stride;
-  p.fin_a = d->fin_a; p.fin_b = d->fin_b; p.fin_counter = d->fin_counter; p.fin_inv_count = d->fin_inv_count; p.fin_eps = d->fin_eps;
-  if (p.fin_mode && (!p.stats || p.fin_mode < 0 || p.fin_mode > 2 || !p.fin_a || !p.fin_b || !p.fin_counter ||
-                     (p.fin_mode == 2 && (!p.fin_gamma || !p.fin_beta)) || box_n > 16))
-    return S2V_EINVAL;
   // fused statistics: one partial per (image, spatial tile, channel); every <=128-column epilogue pass must be 32, 64 or
   // 128 columns wide (the lanes sharing a 16-byte chunk form a power-of-two group inside a warp)
   const bool st_bn_ok = bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256;
   if (p.stats && p.st_gmax == 0) {
-    // LayerNorm2d totals: [N][chunks][4][2], one N tile only (a tile's channels are summed by one thread), no in-kernel finalize
+    // LayerNorm2d totals: [N][chunks][4][2], one N tile only (a tile's channels are summed by one thread)
     if (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_groups != 4 || p.st_c_total != 4 || p.st_c_off != 0 ||
-        p.n_tiles_n != 1 || p.fin_mode || p.st_chunks_total <= 0 || p.st_chunk_off + p.tiles_w * p.tiles_h > p.st_chunks_total)
+        p.n_tiles_n != 1 || p.st_chunks_total <= 0 || p.st_chunk_off + p.tiles_w * p.tiles_h > p.st_chunks_total)
       return S2V_EINVAL;
   } else
   if (p.stats && (d->out_mode != S2V_OUT_F16_NHWC || d->res1.ptr || d->res2.ptr || p.st_c_total <= 0 || p.st_chunks_total <= 0 ||
@@ -1291,22 +1185,17 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     case S2V_ACT_GELU: act_idx = 5; break;
     default: return S2V_EINVAL;
   }
-  static bool attr = false;   // idempotent
-  if (!attr) {
+  static DeviceOnce attr;     // function attributes are per device; idempotent
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  if (attr.needed(dev)) {
     for (int i = 0; i < 2; ++i)
       for (int k = 0; k < 6; ++k)
-        if (cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2V_ECUDA;
-    attr = true;
+        S2V_CUDA_TRY(cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr.mark(dev);
   }
-  static int n_sm = 0;        // immutable after the first call
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
-      return S2V_ECUDA;
-  }
-  {
-    p.fin_needed = 0;
-  }
+  const int n_sm = sm_count(dev);
+  if (n_sm <= 0) return S2V_ECUDA;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("S2V_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   if (dbg)
@@ -1329,11 +1218,11 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, tmBn, p) != cudaSuccess) return S2V_ECUDA;
+    S2V_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernels[1][act_idx], tmA, tmB, tmA2, tmY, tmBn, p));
   } else {
     p.m_pairs = 0; p.total_pair_tiles = 0;
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;      // persistent: one CTA per SM
-    launch_pdl(kernels[0][act_idx], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, tmA2, tmY, tmBn, p);
+    S2V_CUDA_TRY(launch_pdl(kernels[0][act_idx], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, tmA2, tmY, tmBn, p));
   }
   S2V_CHECK_LAUNCH();
   return S2V_OK;

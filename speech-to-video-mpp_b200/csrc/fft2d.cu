@@ -164,8 +164,10 @@ template <int S, int CB>
 static int launch_rfft2(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
   constexpr int K = S / 2 + 1;
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
-  static bool attr = false;   // idempotent attribute set (same value every time)
-  if (!attr) { cudaFuncSetAttribute(rfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static DeviceOnce attr;     // per device; idempotent attribute set (same value every time)
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  if (attr.needed(dev)) { S2V_CUDA_TRY(cudaFuncSetAttribute(rfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr.mark(dev); }
   launch_pdl(rfft2_kernel<S, CB>, dim3(x->c / CB, x->n), K * CB, smem, st, mk(x), mk(sp), fft_rev());
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }
@@ -173,8 +175,10 @@ template <int S, int CB>
 static int launch_irfft2(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
   constexpr int K = S / 2 + 1;
   const size_t smem = (size_t)S * K * CB * sizeof(float2);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(irfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static DeviceOnce attr;
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  if (attr.needed(dev)) { S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_kernel<S, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr.mark(dev); }
   launch_pdl(irfft2_kernel<S, CB>, dim3(y->c / CB, y->n), K * CB, smem, st, mk(sp), mk(add && add->ptr ? add : nullptr), mk(y), fft_rev());
   return cudaGetLastError() == cudaSuccess ? S2V_OK : S2V_ECUDA;
 }

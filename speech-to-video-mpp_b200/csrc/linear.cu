@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(kLinTile) grouped_linear_kernel(const __half* 
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[kLinRows][kLinMaxK];
-  const s2v_lin_group g = groups[tile2group[2 * blockIdx.x]];
+  s2v_lin_group g = groups[tile2group[2 * blockIdx.x]];
+  if (g.k > kLinMaxK) g.k = kLinMaxK;        // never past the staging buffer; the host wrapper rejects k > 512 (ops.pack_lin_groups)
   const int j = tile2group[2 * blockIdx.x + 1] + threadIdx.x;
   const int b0 = blockIdx.y * kLinRows;
   for (int i = threadIdx.x; i < kLinRows * g.k; i += kLinTile) {

@@ -585,8 +585,13 @@ extern "C" int s2v_adain_fused(const s2v_view* x, const float* gamma, const floa
   const dim3 grid(x->c / cg, x->n);
 #define S2V_FUSED(CGV, A)                                                                                          \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) { cudaFuncSetAttribute(adain_fused_kernel<CGV, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    static DeviceOnce attr;                                                                                        \
+    const int dev = current_device();                                                                              \
+    if (dev < 0) return S2V_ECUDA;                                                                                 \
+    if (attr.needed(dev)) {                                                                                        \
+      S2V_CUDA_TRY(cudaFuncSetAttribute(adain_fused_kernel<CGV, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+      attr.mark(dev);                                                                                              \
+    }                                                                                                              \
     launch_pdl(adain_fused_kernel<CGV, A>, grid, kFusedThreads, smem, st, vx, gamma, beta, gb_stride, eps, act_param, vr, vy, reflect1); \
   } while (0)
   if (cg == 64) {

@@ -6,13 +6,17 @@ weights + per-batch plans live in the Python-side engine object registered under
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import pipeline as _pipeline
 from .futils import audio as _audio
 from .futils import flow_util as _flow
 
-_ENGINES: dict[int, object] = {}
+# handle -> engine, held WEAKLY: the nn.Module owns its engine (packed weights, plans, workspaces); when the module is
+# deleted or rebuilt the engine and its device memory go with it
+_ENGINES: "weakref.WeakValueDictionary[int, object]" = weakref.WeakValueDictionary()
 _NEXT = [1]
 
 

@@ -41,12 +41,16 @@ def convT_phase_weights(w):
     return out
 
 
+_IO_OF = {"flow_field": "flow", "warp_image": "warp", "fake_image": "fake"}
+
+
 class DNetEngine(EngineBase):
     def __init__(self, sd, device, conv_impl="tc", use_graph=True):
         super().__init__(device, conv_impl, use_graph)
         assert conv_impl == "tc", "DNet engine is built on the tcgen05 conv path"
-        sd = {k: v.detach().to(device) for k, v in sd.items()}
+        sd = {k: v.detach().to(self.fold_dev) for k, v in sd.items()}
         self._pack(sd)
+        self.finish_pack()
 
     def _pack(self, sd):
         f32 = lambda t: t.float().contiguous()
@@ -272,22 +276,36 @@ class DNetEngine(EngineBase):
 
         return builder
 
-    def forward(self, img, coeff, stage=None):
+    def forward(self, img, coeff, stage=None, only=None):
+        """``only``: return just that output as a VIEW of the plan's I/O buffer (valid until this engine's next forward; the
+        caller consumes it on the same stream) instead of fresh copies of all outputs."""
         B, T = img.shape[0], coeff.shape[2]
         if B == 0:                                  # empty batch: empty outputs with the reference's shapes
             out = {"flow_field": img.new_empty(0, 2, 64, 64), "warp_image": img.new_empty(0, 3, 256, 256)}
             if stage != "warp":
                 out["fake_image"] = img.new_empty(0, 3, 256, 256)
             return out
-        key = (B, T, "warp" if stage == "warp" else "full")
-        ent = self._get_plan(key, self._build(B, T, key[2]))
-        io = ent["io"]
-        io["img"].copy_(img, non_blocking=True)
-        io["coeff"].copy_(coeff.reshape(B, 73, 1, T), non_blocking=True)
-        self._run(ent)
-        out = {"flow_field": io["flow"].clone(), "warp_image": io["warp"].clone()}
-        if "fake" in io:
-            out["fake_image"] = io["fake"].clone()
+        # Batches that are not a multiple of 8 run on the next multiple's plan (frames are independent, the zeroed padding rows
+        # cannot influence the first B outputs): a bounded set of plan sizes for clips of any length, as in LNetEngine.forward.
+        Bp = B if (B < 8 or B % 8 == 0) else (B + 7) // 8 * 8
+        key = (Bp, T, "warp" if stage == "warp" else "full")
+        with self._lock, torch.cuda.device(self.dev):
+            self.begin_forward()
+            ent = self._get_plan(key, self._build(Bp, T, key[2]))
+            io = ent["io"]
+            io["img"][:B].copy_(img, non_blocking=True)
+            io["coeff"][:B].copy_(coeff.reshape(B, 73, 1, T), non_blocking=True)
+            if Bp != B:
+                io["img"][B:].zero_()
+                io["coeff"][B:].zero_()
+            self._run(ent)
+            if only is not None:                    # the pipeline needs a single output and no copies of the others
+                out = {only: io[_IO_OF[only]][:B]}
+            else:
+                out = {"flow_field": io["flow"][:B].clone(), "warp_image": io["warp"][:B].clone()}
+                if "fake" in io:
+                    out["fake_image"] = io["fake"][:B].clone()
+            self.end_forward()
         return out
 
 

@@ -34,12 +34,13 @@ class LNetEngine(EngineBase):
         super().__init__(device, conv_impl, use_graph)
         self.layer, self.base_nc, self.max_nc, self.nblk, self.dnc = layer, base_nc, max_nc, num_res_blocks, descriptor_nc
         assert layer == 3 and base_nc == 64 and max_nc == 512, "kernels are specialised for the default LNet geometry"
-        sd = {k: v.detach().to(device) for k, v in sd.items()}
+        sd = {k: v.detach().to(self.fold_dev) for k, v in sd.items()}
         # decoder levels (by channel count) whose spatial FFC runs as ONE GEMM with N = C (see _pack)
         self.merge_levels = tuple(int(v) for v in os.environ.get("S2V_MERGE", "128").split(",") if v)
         # {channels of the decoder level: frames per L2-resident sub-batch}, e.g. S2V_SUB="128:32,256:64"
         self.sub_batch = {int(k): int(v) for k, v in (kv.split(":") for kv in os.environ.get("S2V_SUB", "").split(",") if kv)}
         self._pack(sd)
+        self.finish_pack()
 
     # ------------------------------------------------------------------ weights
     def _pack(self, sd):
@@ -301,8 +302,8 @@ class LNetEngine(EngineBase):
                           "out": ("out", (b, 3, 96, 96), torch.float32)}
         return self._get_plan(B, self._build(B), builder_of=self._build, batch=B, io_spec=spec)
 
-    def forward(self, mel, face):
-        """mel [B,1,80,16], face [B,6,96,96] float32 CUDA -> [B,3,96,96] float32 (a fresh tensor)."""
+    def forward(self, mel, face, out=None):
+        """mel [B,1,80,16], face [B,6,96,96] float32 CUDA -> [B,3,96,96] float32 (a fresh tensor, or ``out`` filled in place)."""
         B = mel.shape[0]
         if B == 0:                                  # empty batch: the reference returns an empty tensor
             return torch.empty(0, 3, 96, 96, dtype=torch.float32, device=mel.device)
@@ -311,15 +312,19 @@ class LNetEngine(EngineBase):
         # and clipped boxes in ~150 launches (measured on B200: B = 89 16.0 ms vs B = 96 11.2 ms; B = 25 7.5 vs B = 32 6.4).
         # Frames are independent, so the (zeroed) padding rows cannot influence the first B outputs.
         Bp = B if (B < 8 or B % 8 == 0) else (B + 7) // 8 * 8
-        ent = self.plan_for(Bp)
-        io = ent["io"]
-        io["mel"][:B].copy_(mel, non_blocking=True)
-        io["face"][:B].copy_(face, non_blocking=True)
-        if Bp != B:
-            io["mel"][B:].zero_()
-            io["face"][B:].zero_()
-        self._run(ent)
-        return io["out"][:B].clone()
+        with self._lock, torch.cuda.device(self.dev):
+            self.begin_forward()
+            ent = self.plan_for(Bp)
+            io = ent["io"]
+            io["mel"][:B].copy_(mel, non_blocking=True)
+            io["face"][:B].copy_(face, non_blocking=True)
+            if Bp != B:
+                io["mel"][B:].zero_()
+                io["face"][B:].zero_()
+            self._run(ent)
+            res = io["out"][:B].clone() if out is None else out.copy_(io["out"][:B])
+            self.end_forward()
+        return res
 
 
 class LNet(nn.Module):

@@ -3,8 +3,10 @@ helpers, CUDA-graph capture.  Everything here only *orders* C-ABI calls; all ari
 path happens in libs2v's kernels."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -57,8 +59,22 @@ class EngineBase:
         self.lib = L.require_device(device.index) if device.type == "cuda" else L.load_library()
         self.impl = conv_impl
         self.use_graph = use_graph
+        # Weight folding / packing (spectral norm, BatchNorm, phase weights, K-major fp16 packing) runs once per engine on the
+        # HOST by default - a few hundred MB of one-time numpy-style work instead of ~1000 tiny ATen launches in front of the
+        # first forward; the packed tensors are uploaded by finish_pack().  S2V_FOLD_DEVICE=1 folds on the GPU instead.
+        self.fold_dev = device if os.environ.get("S2V_FOLD_DEVICE", "0") == "1" else torch.device("cpu")
         self.W = {}
-        self._plans = {}
+        # per-batch-size plans, least recently used first.  Every plan owns a private workspace (dozens of activation
+        # buffers) and a captured CUDA graph, so the cache is bounded: at most S2V_MAX_PLANS plans and S2V_PLAN_CACHE_GB of
+        # workspace; the least recently used plan is dropped first (its buffers go back to torch's caching allocator).
+        self._plans = collections.OrderedDict()
+        self.max_plans = int(os.environ.get("S2V_MAX_PLANS", "8"))
+        self.max_plan_bytes = int(float(os.environ.get("S2V_PLAN_CACHE_GB", "96")) * (1 << 30))
+        # One forward at a time per engine: a plan's I/O and workspace buffers are shared by every call that uses it.
+        # The lock serialises host-side issue; _last_done orders a forward issued on a DIFFERENT stream behind the previous one.
+        self._lock = threading.RLock()
+        self._last_done = None
+        self._last_stream = None
 
     # ---- workspace ---------------------------------------------------------------------
     def buf(self, ws, name, shape, dtype=torch.float16, zero=False):
@@ -69,6 +85,16 @@ class EngineBase:
         t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
         ws[name] = t
         return t
+
+    def finish_pack(self):
+        """Uploads everything _pack produced (packed weights, epilogue vectors, norm parameters) to the engine's device."""
+        mv = lambda t: t.to(self.dev) if isinstance(t, torch.Tensor) else t
+        for ent in self.W.values():
+            for k in list(ent):
+                if k != "w_f32":                    # kept on the folding device for the lazy head packing
+                    ent[k] = mv(ent[k])
+        if hasattr(self, "P"):
+            self.P = {k: mv(v) for k, v in self.P.items()}
 
     # ---- conv helpers ------------------------------------------------------------------
     def pack_conv(self, name, w, bias=None, scale=None, impl=None, cin_pad=None, rowtaps=False):
@@ -101,7 +127,7 @@ class EngineBase:
         n, co, oh, ow = y_f32.shape
         if e["impl"] == "tc" and e["k"] == (7, 7) and co <= 8 and x.shape[3] % 64 == 0 and os.environ.get("S2V_HEAD", "1") == "1":
             if "w_head" not in e:
-                e["w_head"] = ops.pack_w_head(e["w_f32"])
+                e["w_head"] = ops.pack_w_head(e["w_f32"]).to(self.dev)
             return plan.add(ops.op_conv_head(self.lib, x, e["w_head"], y_f32, bias=e["bias"], act=act, act_param=act_param, name=name))
         return self.conv(plan, name, x, None, pad=(3, 3), act=act, act_param=act_param, y_f32=y_f32, out_shape=(n, co, oh, ow))
 
@@ -128,9 +154,9 @@ class EngineBase:
 
     def conv_stats(self, plan, ws, name, x, y, *, tag=None, c_total=None, c_off=0, phase=0, phases=1, fuse=True, fin=None, **kw):
         """conv whose epilogue also emits the per-(image, spatial tile, channel) sum / sum of squares of its fp16 output
-        (tc path) - this replaces the separate full-tensor chan_stats pass.  With ``fin`` = ("adain", gamma, beta, gb_stride)
-        or ("ln", gamma, beta) the same launch also FINALIZES them (last contributing CTA per image) into the scale / shift
-        the apply kernel consumes, so no finalize launch is needed either.
+        (tc path) - this replaces the separate full-tensor chan_stats pass.  ``fin`` names the consumer of the statistics:
+        ("ln", gamma, beta) = a LayerNorm2d over (C,H,W), for which the conv only emits per-tile TOTALS from its accumulator
+        registers; ("adain", ...) or None = per-channel partials.
         Returns a dict for layernorm2d/adain(stats=...), or None when the statistics cannot be fused (simt path, odd tile
         widths, S2V_FUSED_STATS=0): the caller then falls back to a chan_stats pass."""
         n, h, w, c = y.shape
@@ -144,30 +170,14 @@ class EngineBase:
         # LayerNorm2d consumer (fin = ("ln", ...)): the conv only emits totals over all channels, from its accumulator
         # registers - no shared-memory statistics pass in the epilogue and a 4-entry-per-tile partial list to finalize
         totals = (fin is not None and fin[0] == "ln" and c_off == 0 and ct == c and c <= 256 and self.lib.s2v_conv_tc_tile_n(c) >= c
-                  and os.environ.get("S2V_LN_TOTALS", "1") == "1" and os.environ.get("S2V_FUSED_FINALIZE", "0") != "1")
+                  and os.environ.get("S2V_LN_TOTALS", "1") == "1")
         if totals:
             partial = self.buf(ws, t + ".epi_totals", (n, tiles * phases, 4, 2), torch.float32, zero=True)
             self.conv(plan, name, x, y, stats=(partial, 0, phase * tiles, "totals"), **kw)
             return dict(partial=partial, chunks=tiles * phases, done=False, totals=True)
         partial = self.buf(ws, t + ".epi_partial", (n, tiles * phases, ct, 2), torch.float32, zero=True)
-        st = dict(partial=partial, chunks=tiles * phases, done=False)
-        f = None
-        # In-kernel finalize: opt-in.  Measured on B200 (LNet B=128): 435 instead of 503 launches but 14.49 vs 14.03 ms/step -
-        # the grid-wide barrier + finalize at the conv's tail costs more than the tiny finalize kernel it removes (which
-        # overlaps its launch with the conv's drain through PDL).  Never with two full-size kernels racing for the SMs.
-        if fin is not None and os.environ.get("S2V_FUSED_FINALIZE", "0") == "1" and self.streams == 1:
-            a = self.buf(ws, t + ".a", (n, ct), torch.float32)
-            b = self.buf(ws, t + ".b", (n, ct), torch.float32)
-            st.update(a=a, b=b, done=True)
-            if phase == phases - 1:         # the launch that completes the partials finalizes them (stream order)
-                counter = self.buf(ws, f"{name}.fin_counter", (2,), torch.int32, zero=True)
-                if fin[0] == "adain":
-                    f = dict(mode="adain", gamma=fin[1], beta=fin[2], gb_stride=fin[3], count=h * w * phases)
-                else:
-                    f = dict(mode="ln", gamma=fin[1], beta=fin[2], count=h * w * phases * ct)
-                f.update(a=a, b=b, counter=counter)
-        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), fin=f, **kw)
-        return st
+        self.conv(plan, name, x, y, stats=(partial, c_off, phase * tiles), **kw)
+        return dict(partial=partial, chunks=tiles * phases, done=False)
 
     # ---- norm helpers ------------------------------------------------------------------
     def _stats(self, plan, ws, tag, x):
@@ -226,7 +236,9 @@ class EngineBase:
         arr = (L.LinGroup * len(groups))()
         tiles, keep = [], []
         for i, (wt, bias, in_off, out_off) in enumerate(groups):
-            wt, bias = wt.float().contiguous(), bias.float().contiguous()
+            wt, bias = wt.float().contiguous().to(self.dev), bias.float().contiguous().to(self.dev)
+            if wt.shape[0] > 512:               # kLinMaxK of csrc/linear.cu: the hidden vector is staged in a fixed smem buffer
+                raise ValueError("s2v_grouped_linear supports hidden widths up to 512, got %d" % wt.shape[0])
             keep += [wt, bias]
             arr[i] = L.LinGroup(wt.data_ptr(), bias.data_ptr(), in_off, wt.shape[0], out_off, wt.shape[1])
             tiles += [(i, j) for j in range(0, wt.shape[1], 128)]
@@ -243,7 +255,10 @@ class EngineBase:
     def _get_plan(self, key, builder, builder_of=None, batch=None, io_spec=None):
         """builder(plan, ws) -> io dict.  With builder_of(B) / io_spec(B) -> {io name: (workspace name, shape, dtype)} given,
         a batch of `batch` frames is split over `self.streams` parallel sub-plans."""
-        if key not in self._plans:
+        if key in self._plans:
+            self._plans.move_to_end(key)
+        else:
+            self._evict(reserve=1)
             B = batch or 0
             parts_n = self.streams if (builder_of and io_spec and self.streams > 1 and B % self.streams == 0 and B // self.streams >= 8) else 1
             if parts_n == 1:
@@ -263,7 +278,35 @@ class EngineBase:
                     parts.append(dict(plan=plan, ws=ws, stream=torch.cuda.Stream(device=self.dev)))
                     allp.main_ops.extend(plan.ops)
                 self._plans[key] = dict(plan=allp, ws=None, io=io, graph=None, warm=0, parts=parts)
+            self._plans[key]["bytes"] = self._plan_bytes(self._plans[key])
+            self._evict()
         return self._plans[key]
+
+    @staticmethod
+    def _plan_bytes(ent):
+        seen, total = set(), 0
+        wss = [ent["ws"]] if ent["ws"] is not None else [pt["ws"] for pt in ent["parts"]]
+        for ws in wss + [ent["io"]]:
+            for t in ws.values():
+                st = t.untyped_storage()
+                if st.data_ptr() not in seen:
+                    seen.add(st.data_ptr())
+                    total += st.nbytes()
+        return total
+
+    def _evict(self, reserve=0):
+        """Drops least-recently-used plans until the cache holds at most max_plans - reserve plans and max_plan_bytes of
+        workspace (the newest plan always stays).  The dropped plan's graph and buffers are released once the work already
+        queued on them has run (stream-ordered free of torch's caching allocator)."""
+        while len(self._plans) > 1 and (len(self._plans) > self.max_plans - reserve or
+                                        sum(e.get("bytes", 0) for e in self._plans.values()) > self.max_plan_bytes):
+            _, old = self._plans.popitem(last=False)
+            if self._last_done is not None:
+                self._last_done.synchronize()          # a captured graph must not be destroyed while a replay is in flight
+            old.clear()
+
+    def plan_cache_info(self):
+        return {"plans": len(self._plans), "bytes": sum(e.get("bytes", 0) for e in self._plans.values()), "keys": list(self._plans)}
 
     def _run_plan(self, ent):
         if not ent["parts"]:
@@ -278,6 +321,20 @@ class EngineBase:
             done = torch.cuda.Event()
             done.record(pt["stream"])
             main.wait_event(done)
+
+    def begin_forward(self):
+        """Called (under self._lock, inside torch.cuda.device(self.dev)) before a forward touches a plan's buffers: if the
+        previous forward of this engine was issued on another stream, the current stream waits for it."""
+        cur = torch.cuda.current_stream(self.dev)
+        if self._last_done is not None and self._last_stream != cur.cuda_stream:
+            cur.wait_event(self._last_done)
+
+    def end_forward(self):
+        cur = torch.cuda.current_stream(self.dev)
+        if self._last_done is None:
+            self._last_done = torch.cuda.Event()
+        self._last_done.record(cur)
+        self._last_stream = cur.cuda_stream
 
     def _run(self, ent):
         """Runs the plan on the current stream; the first call runs the op list eagerly (one-time kernel attribute

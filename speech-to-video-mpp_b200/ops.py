@@ -155,7 +155,7 @@ def choose_box(h: int, w: int, n: int) -> tuple[int, int, int]:
 def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pad_mode=L.PAD_ZERO, up2=0,
             scale=None, bias=None, res1=None, res2=None, act=L.ACT_NONE, act_param=0.0, y_f32=None,
             out_shape=None, impl="tc", box=None, name="conv", cin_true=None, alg_scale=1.0,
-            x2=None, k2=(1, 1), pad2=(0, 0), stats=None, alg_flops=None, narrow=None, fin=None) -> Op:
+            x2=None, k2=(1, 1), pad2=(0, 0), stats=None, alg_flops=None, narrow=None) -> Op:
     """x: fp16 NHWC tensor; y: fp16 NHWC tensor (or None with y_f32 [N,Cout,OH,OW] float32)."""
     d = L.Conv()
     d.x = view(x)
@@ -194,17 +194,7 @@ def op_conv(lib, x, w, y, *, k=(1, 1), stride=(1, 1), pad=(0, 0), dil=(1, 1), pa
     if narrow is not None:      # (cin_from, cout): input channels >= cin_from only feed the first `cout` outputs (zero weight block)
         d.narrow_cin_from, d.narrow_cout = narrow
         assert impl == "tc" and narrow[0] % 64 == 0 and narrow[1] % 32 == 0
-    if fin is not None:         # in-kernel finalize of the fused statistics, see s2v.h
-        assert stats is not None
-        d.fin_mode = {"adain": 1, "ln": 2}[fin["mode"]]
-        d.fin_launches = fin.get("launches", 1)
-        d.fin_gamma = None if fin.get("gamma") is None else fin["gamma"].data_ptr()
-        d.fin_beta = None if fin.get("beta") is None else fin["beta"].data_ptr()
-        d.fin_gb_stride = fin.get("gb_stride", 0)
-        d.fin_a, d.fin_b, d.fin_counter = fin["a"].data_ptr(), fin["b"].data_ptr(), fin["counter"].data_ptr()
-        d.fin_inv_count, d.fin_eps = 1.0 / fin["count"], fin.get("eps", 1e-5)
-        assert fin["counter"].dtype == torch.int32 and fin["a"].dtype == torch.float32
-    keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2, stats, fin)
+    keep = (d, x, w, y, scale, bias, res1, res2, y_f32, x2, stats)
     cout, taps = d.y.c, k[0] * k[1]
     for t in (scale, bias):
         assert t is None or (t.dtype == torch.float32 and t.numel() == cout), (name, cout)

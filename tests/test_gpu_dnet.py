@@ -83,3 +83,37 @@ def test_dnet_errors(env):
     G, sd, net = env
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 256, 256, device="cuda"), torch.zeros(1, 73, 20, device="cuda"))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_dnet_bench_config_b64_vs_oracle(seed):
+    """BASELINE.json configs[2] as benchmarked: batch 64 at 256 x 256, weight seeds 0 and 1, against the fp32 oracle on the
+    GPU with TF32 off.  Gate: PSNR >= 45 dB (peak 2) on warp_image / fake_image, flow_field relative to its own peak."""
+    import gpu_util as G
+    from oracle import nets, synth, weights
+    from s2v_b200.models.DNet import DNet
+    G.lib()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = weights.make_state_dict("dnet", seed)
+        net = DNet().cuda().eval()
+        net.load_state_dict(sd, strict=True)
+        src, coeff = synth.dnet_inputs(64, seed=200 + seed)
+        src, coeff = src.cuda(), coeff.cuda()
+        out = net(src, coeff)
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        refs = [nets.dnet_forward(sdc, src[i:i + 16], coeff[i:i + 16]) for i in range(0, 64, 16)]
+        ref = {k: torch.cat([r[k] for r in refs]) for k in refs[0]}
+        fl = ref["flow_field"]
+        tag = "B=64 weight seed %d" % seed
+        _check(G, "DNet flow_field vs oracle " + tag, out["flow_field"], fl, float(fl.abs().max()), 45.0)
+        _check(G, "DNet warp_image vs oracle " + tag, out["warp_image"], ref["warp_image"], 2.0, 45.0)
+        _check(G, "DNet fake_image vs oracle " + tag, out["fake_image"], ref["fake_image"], 2.0, 45.0)
+        worst = min(G.psnr(out["fake_image"][i], ref["fake_image"][i], 2.0) for i in range(64))
+        print("worst single frame %.2f dB" % worst)
+        assert worst >= 45.0
+        one = net(src[17:18], coeff[17:18])
+        assert torch.equal(one["fake_image"], out["fake_image"][17:18])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32

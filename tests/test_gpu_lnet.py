@@ -109,3 +109,34 @@ def test_lnet_errors(env):
     from s2v_b200.models.LNet import LNet
     with pytest.raises(L.S2VError):
         LNet().eval()(torch.zeros(1, 1, 80, 16), torch.zeros(1, 6, 96, 96))     # CPU module: no fallback
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_lnet_bench_config_b128_vs_oracle(seed):
+    """BASELINE.json configs[1] as benchmarked: batch 128 (full 8-image boxes at 12 x 12, CTA pairs / resident plans keyed on
+    the tile count), weight seeds 0 and 1, against the fp32 oracle on the GPU with TF32 off.  Gate: PSNR >= 45 dB, max-abs printed."""
+    import gpu_util as G
+    from oracle import nets, synth, weights
+    from s2v_b200.models.LNet import LNet
+    G.lib()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = weights.make_state_dict("lnet", seed)
+        net = LNet().cuda().eval()
+        net.load_state_dict(sd, strict=True)
+        mel, face = synth.lnet_inputs(128, seed=100 + seed)
+        mel, face = mel.cuda(), face.cuda()
+        out = net(mel, face)
+        out2 = net(mel, face)                              # graph replay
+        assert torch.equal(out, out2)
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        ref = torch.cat([nets.lnet_forward(sdc, mel[i:i + 32], face[i:i + 32]) for i in range(0, 128, 32)])
+        p = _check(G, "LNet tc vs oracle B=128 weight seed %d" % seed, out, ref)
+        worst = min(G.psnr(out[i], ref[i], 1.0) for i in range(128))
+        print("worst single frame %.2f dB" % worst)
+        assert worst >= 45.0
+        # the frames of the big batch equal the same frames computed in a small batch, bit for bit
+        assert torch.equal(net(mel[40:48], face[40:48]), out[40:48])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32

@@ -93,3 +93,59 @@ def test_mel_windows_layout():
     assert w.dtype == np.float32 and w.shape[1:] == (1, 80, 16)
     s = omel.mel_window_starts(m.shape[1])
     np.testing.assert_array_equal(w[3, 0], m[:, s[3]:s[3] + 16].astype(np.float32))
+
+
+# ---- goldens produced by the UNMODIFIED reference futils/audio.py (oracle/make_golden_mel.py; stub librosa) ------------------
+def _ref_golden():
+    return np.load(os.path.join(GOLDEN, "mel_ref_golden.npz"))
+
+
+def test_oracle_vs_reference_audio_py_goldens():
+    """a1 / a4 + the glue of a2 / a3 pinned to the reference's own file (STFT / mel basis stay unpinned at librosa)."""
+    from oracle import resample
+    g = _ref_golden()
+    np.testing.assert_allclose(omel.preemphasis(synth.wav(1.0, seed=0)), g["preemph_synth"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(omel.melspectrogram(synth.wav(1.0, seed=0)), g["mel_synth_seed0_1s"], rtol=0, atol=1e-12)
+    speech = resample.pcm_to_float_mono(g["speech_pcm"])
+    m = omel.melspectrogram(speech)
+    assert m.shape == g["mel_speech"].shape == (80, 321)
+    np.testing.assert_allclose(m, g["mel_speech"], rtol=0, atol=1e-12)
+    assert (g["mel_speech"] <= -4).mean() > 0.1          # real speech reaches the lower clip rail (white noise never does)
+
+
+def test_reference_audio_py_importable_with_stub_librosa():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree only exists in the build container")
+    a = ref_shim.load_audio()
+    w = synth.wav(0.5, seed=5)
+    np.testing.assert_array_equal(a.melspectrogram(w), omel.melspectrogram(w))
+    assert a.get_hop_size() == 200 and a.hp.num_mels == 80
+    import sys
+    assert "librosa" not in sys.modules or not hasattr(sys.modules["librosa"], "_s2v_stub")
+
+
+# ---- load_wav restatement (oracle/resample.py; parity unpinned: librosa / resampy absent) ---------------------------------------
+def test_resample_identity_and_length_rule():
+    from oracle import resample as R
+    x = synth.wav(0.5, seed=2)
+    np.testing.assert_array_equal(R.load_array(x, 16000, 16000), x)                     # equal rates: no resampling at all
+    for sr0, n in ((44100, 4410), (48000, 4801), (22050, 2207), (8000, 801)):
+        y = R.load_array(x[:n], sr0, 16000)
+        assert y.dtype == np.float32 and y.shape[0] == int(np.ceil(n * 16000.0 / sr0))   # librosa.resample: fix_length(ceil(n * ratio))
+
+
+def test_resample_reconstructs_band_limited_sine():
+    from oracle import resample as R
+    for sr0, tol in ((8000, 1e-6), (22050, 1e-3), (44100, 4e-3), (48000, 4e-3)):        # int(index_step) truncation = resampy's known gain error when down-sampling
+        t = np.arange(sr0 // 2) / sr0
+        y = R.resample(np.sin(2 * np.pi * 440 * t), sr0, 16000).astype(np.float64)
+        ref = np.sin(2 * np.pi * 440 * np.arange(len(y)) / 16000)
+        assert np.abs(y - ref)[1000:-1000].max() < tol
+
+
+def test_pcm_decode():
+    from oracle import resample as R
+    pcm = np.array([[-32768, 32767], [0, 16384]], dtype=np.int16)
+    np.testing.assert_array_equal(R.pcm_to_float_mono(pcm), np.array([(-1.0 + 32767 / 32768) / 2, 0.25], dtype=np.float32))
+    np.testing.assert_array_equal(R.pcm_to_float_mono(np.array([0, 128, 255], dtype=np.uint8)), np.array([-1, 0, 127 / 128], dtype=np.float32))
