@@ -21,7 +21,9 @@ namespace s2v {
 __device__ __forceinline__ int refl101(int p, int n) {
   if (n == 1) return 0;
   p = p < 0 ? -p : p;
-  return p >= n ? 2 * n - 2 - p : p;
+  p = p >= n ? 2 * n - 2 - p : p;
+  // window taps more than one reflection away (n = 2, 3) only feed outputs outside the image; keep their address in range
+  return min(max(p, 0), n - 1);
 }
 
 // thread = a 2 x 2 quad of output pixels (all C channels): the 7 x 7 input window is loaded once (49 instead of 100 pixel

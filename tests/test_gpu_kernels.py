@@ -448,3 +448,41 @@ def test_resize_bilinear(G, n, c, h, w, oh, ow):
             ref = ref * sc[:, :, None, None]
         m, rel = G.report("resize %dx%d->%dx%d c%d" % (h, w, oh, ow, c), G.nchw(y), ref)
         assert rel < 2e-3
+
+
+def test_mel_vs_reference_audio_py_goldens(G):
+    """CUDA mel against outputs of the UNMODIFIED reference futils/audio.py (oracle/make_golden_mel.py, stub librosa): the seeded
+    synthetic wav and 4 s of the reference's own speech sample, whose pauses sit on the -4 clip rail.  Gate: 1e-4 * max(|b|, 1)."""
+    import os
+    from oracle import resample, synth
+    from s2v_b200.futils import audio
+    g = np.load(os.path.join(GOLDEN, "mel_ref_golden.npz"))
+    for name, wav, ref in (("synthetic 1 s", synth.wav(1.0, seed=0), g["mel_synth_seed0_1s"]),
+                           ("speech 4 s", resample.pcm_to_float_mono(g["speech_pcm"]), g["mel_speech"])):
+        got = audio.melspectrogram(wav)
+        assert got.shape == ref.shape and got.dtype == np.float64
+        d = np.abs(got - ref)
+        tol = 1e-4 * np.maximum(np.abs(ref), 1.0)
+        bad = int((d > tol).sum())
+        print("mel vs reference audio.py, %s: max_abs=%.3e, %d of %d bins above tolerance, on the -4 rail: ref %.3f got %.3f"
+              % (name, d.max(), bad, d.size, (ref <= -4).mean(), (got <= -4).mean()))
+        with open("gpurun_out/parity_report.txt", "a") as f:
+            f.write("mel vs reference audio.py goldens (%s): max_abs %.3e, %d / %d bins above 1e-4*max(|b|,1)\n" % (name, d.max(), bad, d.size))
+        assert bad == 0
+
+
+def test_two_devices_in_one_process(G):
+    """Kernel attributes (opt-in shared memory > 48 KB) and the SM count are per-device state: the same process must be able to
+    run the large-smem kernels on a second GPU (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from oracle import synth, weights
+    from s2v_b200.models.LNet import LNet
+    sd = weights.make_state_dict("lnet", 0)
+    mel, face = synth.lnet_inputs(8, seed=0)
+    outs = []
+    for d in (0, 1):
+        net = LNet().to("cuda:%d" % d).eval()
+        net.load_state_dict(sd, strict=True)
+        outs.append(net(mel.to("cuda:%d" % d), face.to("cuda:%d" % d)).cpu())      # current device stays cuda:0 throughout
+    assert torch.equal(outs[0], outs[1])

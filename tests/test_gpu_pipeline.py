@@ -111,3 +111,59 @@ def test_stream_batches_matches_direct_forward():
         for o, r in zip(outs, refs):
             assert torch.equal(o, r), depth
     assert stream_batches(lnet, iter(())) == 0
+
+
+def test_clip_batch_structure_vs_oracle_sample():
+    """The benchmarked configuration: the 60 s clip of BASELINE.json configs[3] (1 497 frames) through LipSyncPipeline with
+    its real batch structure (24 DNet batches of 63 / 62 on the B=64 plan, 12 LNet batches of 125 / 124 on the B=128 plan,
+    DNet and LNet overlapped on two streams), checked on a strided sample of frames against the oracle chain (fp32, TF32
+    off); overlapped == single-stream bit-for-bit; rank 3 of 8 == its slice of the unsharded run."""
+    import gpu_util as G
+    from oracle import mel as omel, nets, synth, weights
+    from s2v_b200 import parallel
+    from s2v_b200.models.DNet import DNet
+    from s2v_b200.models.LNet import LNet
+    from s2v_b200.pipeline import LipSyncPipeline
+    G.lib()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd_l, sd_d = weights.make_state_dict("lnet", 0), weights.make_state_dict("dnet", 0)
+        lnet, dnet = LNet().cuda().eval(), DNet().cuda().eval()
+        lnet.load_state_dict(sd_l, strict=True)
+        dnet.load_state_dict(sd_d, strict=True)
+        wav_np = synth.wav(60.0, seed=0)
+        n = len(omel.mel_window_starts(1 + len(wav_np) // 200))
+        assert n == 1497
+        src64, co64 = synth.dnet_inputs(64, seed=1)
+        idx = torch.arange(n) % 64
+        src, coeff = src64[idx].cuda(), co64[idx].cuda()
+        wav = torch.from_numpy(wav_np).cuda()
+        pipe = LipSyncPipeline(lnet, dnet)
+        frames = pipe.run(wav, src, coeff)
+        assert frames.shape == (n, 3, 96, 96)
+        assert torch.equal(LipSyncPipeline(lnet, dnet, overlap=False).run(wav, src, coeff), frames)
+        # pinned-host inputs / outputs (bench.py's e2e form) give the same frames
+        out_h = torch.empty(n, 3, 96, 96).pin_memory()
+        f2 = pipe.run(torch.from_numpy(wav_np).pin_memory(), src.cpu().pin_memory(), coeff.cpu().pin_memory(), out_host=out_h)
+        assert torch.equal(f2, frames) and torch.equal(out_h, frames.cpu())
+        # strided sample (covers first / last frames, batch seams 62|63, 124|125 and the tail window) vs the oracle chain
+        sample = sorted(set(list(range(0, n, 97)) + [61, 62, 63, 124, 125, 126, n - 2, n - 1]))
+        sidx = torch.tensor(sample)
+        win = torch.from_numpy(omel.mel_windows(omel.melspectrogram(wav_np)))[sidx].cuda()
+        sdd, sdl = {k: v.cuda() for k, v in sd_d.items()}, {k: v.cuda() for k, v in sd_l.items()}
+        fake = nets.dnet_forward(sdd, src[sidx.cuda()], coeff[sidx.cuda()])["fake_image"]
+        ref = nets.lnet_forward(sdl, win, nets.glue_dnet_to_lnet(fake))
+        got = frames[sidx.cuda()]
+        m, _ = G.report("60 s clip, %d sampled frames vs oracle" % len(sample), got, ref)
+        p = G.psnr(got, ref, 1.0)
+        worst = min(G.psnr(got[i], ref[i], 1.0) for i in range(len(sample)))
+        with open("gpurun_out/parity_report.txt", "a") as f:
+            f.write("60 s clip real batch structure: PSNR %.2f dB (worst frame %.2f) max_abs %.5f\n" % (p, worst, m))
+        assert p >= 45.0 and worst >= 45.0
+        lo, hi = parallel.shard_range(n, 3, 8)
+        assert torch.equal(pipe.run(wav, src[lo:hi], coeff[lo:hi], rank=3, world=8), frames[lo:hi])
+        info = dnet.engine().plan_cache_info()
+        assert info["plans"] <= dnet.engine().max_plans
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
