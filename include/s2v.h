@@ -87,6 +87,19 @@ int s2v_melspectrogram_f32(const float* wav, int64_t n_samples, const float* bas
 /* uploads the constant DFT-25 twiddle table; call once per device before the first mel call */
 int s2v_mel_init(void);
 
+/* ------------------------------------------------------------- load_wav ---
+ * replaces futils/audio.py:9-10 (librosa.core.load(path, sr)[0]) behind the file read: PCM decode to float32 mono
+ * (soundfile: int16 / 2^15, int32 / 2^31, uint8 (x-128)/2^7; librosa.to_mono = mean over channels) and librosa 0.9.2's
+ * default resampler, resampy 'kaiser_best' (band-limited sinc interpolation with a 64-zero-crossing Kaiser window sampled
+ * 512 times per crossing; the host builds the half window `win` [nwin] and its forward differences `delta`, float64).
+ *   kind: 0 int16, 1 int32, 2 uint8, 3 float32; pcm interleaved [n_frames][channels]
+ *   s2v_resample_out_len = int(n_in * sr_new / sr_orig) samples; the caller (librosa.resample) pads / trims the result to
+ *   ceil(n_in * sr_new / sr_orig).  float64 accumulation in resampy's order.                                                */
+int64_t s2v_resample_out_len(int64_t n_in, int sr_orig, int sr_new);
+int s2v_resample_f32(const float* x, int64_t n_in, int sr_orig, int sr_new, const double* win, const double* delta,
+                     int nwin, int num_table, float* y, int64_t n_out, void* stream);
+int s2v_pcm_to_mono_f32(const void* pcm, int kind, int channels, int64_t n_frames, float* out, void* stream);
+
 /* replaces the loop of inference.py:209-216 (+ layout of :399/:261):
  * number of 80x16 windows for T mel columns at `fps` (bit-exact int(i*80./fps)) */
 int64_t s2v_mel_window_count(int64_t n_cols, double fps);
@@ -142,8 +155,32 @@ int s2v_warp_deformation_f32(const float* src, const float* deformation, float* 
 /* bilinear resize of an fp16 channels-last tensor, align_corners = False (F.interpolate(mode='bilinear') as used by the
  * ENet upsampler: models/base_blocks.py:42-46 ResBlock x0.5, :500-503 ModulatedConv2d x2, models/ENet.py:93,104).
  * x, y: views with equal n and c (c a multiple of 8); any h, w.  chan_scale (nullable): float32 [N][C] multiplied into the
- * result per (image, channel) - the StyleGAN2 modulation of the following conv's input.  Building block for SURVEY 8f #1. */
-int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, void* stream);
+ * result per (image, channel) - the StyleGAN2 modulation of the following conv's input; rows of stride scale_stride
+ * floats (0 = C; a multiple of 4, 16-byte aligned base).
+ * s2v_resize_planes_f32: the same interpolation on float32 planes (models/ENet.py:93,104: the reference frame to 256 x 256,
+ * the LNet input to 96 x 96): plane p of image n at src + n*src_sn + p*src_sp (a channel window of an NCHW tensor).        */
+int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, int64_t scale_stride, void* stream);
+int s2v_resize_planes_f32(const float* src, int64_t src_sn, int64_t src_sp, int N, int P, int H, int W,
+                          float* dst, int64_t dst_sn, int64_t dst_sp, int OH, int OW, void* stream);
+
+/* ------------------------------------------------------------------ ENet ---
+ * The memory-bound pieces of the 96 -> 384 upsampler (models/ENet.py:82-139) around the s2v_conv_tc GEMMs.  The per-sample
+ * modulated conv (models/base_blocks.py:487-508, a grouped conv over B x Cout x Cin x k x k weights) runs as ONE shared-weight
+ * conv:  conv(x, W*s[n,ci]*d[n,co]) == d[n,co] * conv(x*s[n,ci], W).
+ *   s2v_style_demod     d[n][co] = gain * rsqrt(sum_ci w2[co][ci] * s[n][ci]^2 + eps)   (:494-496; w2 = sum over taps of W^2)
+ *   s2v_style_epilogue  y = lrelu(x*a[n][c] + bias[c] + noise_w[0]*noise[n][h][w], slope) * post[n][c]      (StyleConv :524-536:
+ *                       demodulation * sqrt2, noise injection, bias, LeakyReLU(0.2); `post` = the NEXT conv's modulation)
+ *                       a, bias, noise, post nullable; a [N][C], post rows of stride post_stride, noise float32 [N][H][W]
+ *   s2v_to_rgb          ToRGB :539-553: out[n][k] = sum_c x[..c]*w[k][c]*s[n][c] + bias[k] + bilinear_x2(skip)[n][k], float32 NCHW,
+ *                       cropped by `crop` pixels on every side (ENet.py:131); skip float32 NCHW [N][3][H/2][W/2] or NULL
+ *   s2v_reflect_pad_nchw_f32   F.pad(x, (p,p,p,p), 'reflect') of `planes` float32 H x W planes (ENet.py:118-119)          */
+int s2v_style_demod(const float* w2, const float* s, int64_t s_stride, int N, int cin, int cout, float eps, float gain,
+                    float* out, void* stream);
+int s2v_style_epilogue(const s2v_view* x, const float* a, const float* bias, const float* noise, const float* noise_w,
+                       float slope, const float* post, int64_t post_stride, const s2v_view* y, void* stream);
+int s2v_to_rgb(const s2v_view* x, const float* w, const float* s, int64_t s_stride, const float* bias, const float* skip,
+               float* out, int crop, void* stream);
+int s2v_reflect_pad_nchw_f32(const float* src, int planes, int H, int W, int pad, float* dst, void* stream);
 
 /* ------------------------------------------------------------- layout ---
  * NCHW float32 [N,C,H,W] -> fp16 NHWC view channels [c_off, c_off+C); channels

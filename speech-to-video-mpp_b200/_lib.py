@@ -51,10 +51,18 @@ _SIGNATURES = {
     "s2v_mel_num_frames": (C.c_int, [c_i64]),
     "s2v_melspectrogram_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "s2v_mel_init": (C.c_int, []),
+    "s2v_resample_out_len": (c_i64, [c_i64, C.c_int, C.c_int]),
+    "s2v_resample_f32": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_i64, c_vp]),
+    "s2v_pcm_to_mono_f32": (C.c_int, [c_vp, C.c_int, C.c_int, c_i64, c_vp, c_vp]),
     "s2v_mel_window_count": (c_i64, [c_i64, c_f64]),
     "s2v_mel_window_starts_host": (C.c_int, [c_i64, c_f64, C.POINTER(c_i32), c_i64]),
     "s2v_mel_windows_f32": (C.c_int, [c_vp, c_i64, c_f64, c_i64, c_i64, c_vp, c_vp]),
-    "s2v_resize_bilinear": (C.c_int, [VP, VP, c_vp, c_vp]),
+    "s2v_resize_bilinear": (C.c_int, [VP, VP, c_vp, c_i64, c_vp]),
+    "s2v_resize_planes_f32": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
+    "s2v_style_demod": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_f32, c_f32, c_vp, c_vp]),
+    "s2v_style_epilogue": (C.c_int, [VP, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, VP, c_vp]),
+    "s2v_to_rgb": (C.c_int, [VP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp]),
+    "s2v_reflect_pad_nchw_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "s2v_semantic_windows": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, c_f64, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_u8": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),

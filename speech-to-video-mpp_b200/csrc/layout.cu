@@ -113,7 +113,7 @@ extern "C" int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, flo
 // models/ENet.py:93,104); optional per-(n, c) input scale = the StyleGAN2 modulation folded into the resize pass.
 namespace s2v {
 
-__global__ void __launch_bounds__(256) resize_bilinear_kernel(View x, View y, const float* __restrict__ chan_scale) {
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(View x, View y, const float* __restrict__ chan_scale, long long scale_stride) {
   pdl_trigger();
   pdl_wait();
   const int C8 = x.c >> 3;
@@ -139,20 +139,57 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(View x, View y, co
     o[i] = top + ly * (bot - top);
   }
   if (chan_scale) {
-    const float4 s0 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * x.c + c8 * 8);
-    const float4 s1 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * x.c + c8 * 8 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * scale_stride + c8 * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(chan_scale + (size_t)n * scale_stride + c8 * 8 + 4);
     o[0] *= s0.x; o[1] *= s0.y; o[2] *= s0.z; o[3] *= s0.w; o[4] *= s1.x; o[5] *= s1.y; o[6] *= s1.z; o[7] *= s1.w;
   }
   st_h8(y.p + n * y.sn + oy * y.sh + ox * y.sw + c8 * 8, f_to_h8(o));
 }
 
+// F.interpolate(mode='bilinear', align_corners=False) of float32 planes: src plane p of image n at src + n*src_sn + p*src_sp
+// (a channel window of a contiguous NCHW tensor), dst contiguous [N][P][OH][OW] window with the same addressing
+__global__ void __launch_bounds__(256) resize_planes_f32_kernel(const float* __restrict__ src, long long src_sn, long long src_sp, int P, int H, int W,
+                                                               float* __restrict__ dst, long long dst_sn, long long dst_sp, int OH, int OW, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % OW), oy = (int)((idx / OW) % OH);
+  const long long np = idx / ((long long)OW * OH);
+  const int p = (int)(np % P);
+  const long long n = np / P;
+  const float sch = (float)H / (float)OH, scw = (float)W / (float)OW;
+  const float sy = fmaxf(sch * ((float)oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)ox + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float* sp = src + n * src_sn + p * src_sp;
+  // same operation order as ATen's upsample_bilinear2d: hy*(hx*a + lx*b) + ly*(hx*c + lx*d)
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float v = hy * (hx * sp[(size_t)y0 * W + x0] + lx * sp[(size_t)y0 * W + x1]) + ly * (hx * sp[(size_t)y1 * W + x0] + lx * sp[(size_t)y1 * W + x1]);
+  dst[n * dst_sn + p * dst_sp + (size_t)oy * OW + ox] = v;
+}
+
 }  // namespace s2v
 
-extern "C" int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, void* stream) {
+extern "C" int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const float* chan_scale, int64_t scale_stride, void* stream) {
   if (!view_ok(x) || !view_ok(y) || x->n != y->n || x->c != y->c) return S2V_EINVAL;
   if (y->n == 0) return S2V_OK;
+  if (chan_scale && ((((uintptr_t)chan_scale) & 15) || (scale_stride & 3) || scale_stride < 0)) return S2V_EINVAL;
   const long long total = (long long)y->n * y->h * y->w * (x->c >> 3);
-  launch_pdl(resize_bilinear_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(x), mk(y), chan_scale);
+  S2V_CUDA_TRY(launch_pdl(resize_bilinear_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(x), mk(y), chan_scale,
+                          (long long)(scale_stride ? scale_stride : x->c)));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+extern "C" int s2v_resize_planes_f32(const float* src, int64_t src_sn, int64_t src_sp, int N, int P, int H, int W, float* dst, int64_t dst_sn,
+                                     int64_t dst_sp, int OH, int OW, void* stream) {
+  if (N == 0 || P == 0) return S2V_OK;
+  if (!src || !dst || N < 0 || P < 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return S2V_EINVAL;
+  const long long total = (long long)N * P * OH * OW;
+  S2V_CUDA_TRY(launch_pdl(resize_planes_f32_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, src, (long long)src_sn, (long long)src_sp, P, H, W,
+                          dst, (long long)dst_sn, (long long)dst_sp, OH, OW, total));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -1,5 +1,6 @@
-"""Drop-in for the reference's futils/audio.py mel front end, backed by libs2v's fused CUDA kernel.
+"""Drop-in for the reference's futils/audio.py front end, backed by libs2v's CUDA kernels.
 
+    load_wav(path, sr)  -> float32 numpy [n]                          (futils/audio.py:9-10, librosa.core.load)
     melspectrogram(wav) -> float64 numpy [80, 1 + len(wav)//200]      (futils/audio.py:45-51)
 
 plus the window rule of inference.py:209-216 as functions (``mel_window_starts``, ``mel_windows``).
@@ -16,6 +17,85 @@ from .. import _lib as L
 from .hparams import hparams as hp
 
 _basis_cache: dict = {}
+
+
+# ---- load_wav: PCM decode + librosa's default resampler (resampy 'kaiser_best') -------------------------------------------------
+_KAISER_BEST = dict(num_zeros=64, precision=9, rolloff=0.9475937167399596, beta=14.769656459379492)   # resampy/filters.py
+_filter_cache: dict = {}
+_PCM_KIND = {np.dtype(np.int16): 0, np.dtype(np.int32): 1, np.dtype(np.uint8): 2, np.dtype(np.float32): 3}
+
+
+def _kaiser_best_table(device: torch.device, ratio: float):
+    """resampy.filters.sinc_window for 'kaiser_best' (right half of a Kaiser-windowed sinc, 512 samples per zero crossing),
+    scaled by the ratio when down-sampling, plus its forward differences - float64 device tensors."""
+    key = (device.index, ratio if ratio < 1 else 1.0)
+    if key not in _filter_cache:
+        k = _KAISER_BEST
+        num_bits = 2 ** k["precision"]
+        n = num_bits * k["num_zeros"]
+        win = k["rolloff"] * np.sinc(k["rolloff"] * np.linspace(0, k["num_zeros"], num=n + 1, endpoint=True)) * np.kaiser(2 * n + 1, k["beta"])[n:]
+        if ratio < 1:
+            win = win * ratio
+        delta = np.zeros_like(win)
+        delta[:-1] = np.diff(win)
+        _filter_cache[key] = (torch.from_numpy(win).to(device), torch.from_numpy(delta).to(device), num_bits)
+    return _filter_cache[key]
+
+
+def resample_device(y: torch.Tensor, orig_sr: int, target_sr: int) -> torch.Tensor:
+    """librosa.resample(y, orig_sr, target_sr) with its default res_type='kaiser_best' (what librosa.load calls) on a 1-D float32
+    CUDA tensor: resampy's int(n * ratio) samples, padded / trimmed to ceil(n * ratio) (util.fix_length)."""
+    if not (y.is_cuda and y.dim() == 1):
+        raise ValueError("y must be a 1-D CUDA tensor")
+    y = y.contiguous().float()
+    if orig_sr == target_sr:
+        return y
+    lib = L.require_device(y.device.index)
+    ratio = float(target_sr) / float(orig_sr)
+    n_res = int(lib.s2v_resample_out_len(y.numel(), int(orig_sr), int(target_sr)))
+    if n_res < 1:
+        raise ValueError("Input signal length=%d is too small to resample from %d->%d" % (y.numel(), orig_sr, target_sr))
+    n_out = int(np.ceil(y.numel() * ratio))
+    win, delta, num_table = _kaiser_best_table(y.device, ratio)
+    out = torch.zeros(n_out, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        L.check(lib.s2v_resample_f32(y.data_ptr(), y.numel(), int(orig_sr), int(target_sr), win.data_ptr(), delta.data_ptr(), win.numel(),
+                                     num_table, out.data_ptr(), min(n_res, n_out), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "s2v_resample_f32")
+    return out
+
+
+def load_array_device(data, sr_native: int, sr: int, device=None) -> torch.Tensor:
+    """librosa.load behind the file read: PCM samples [n] or [n, channels] (int16 / int32 / uint8 / float32 numpy) at
+    ``sr_native`` -> float32 mono CUDA tensor at ``sr``."""
+    data = np.ascontiguousarray(data)
+    if data.dtype == np.float64:
+        data = data.astype(np.float32)
+    if data.dtype not in _PCM_KIND:
+        raise TypeError("unsupported PCM dtype %s" % data.dtype)
+    if not torch.cuda.is_available():
+        raise L.S2VError("a CUDA device is required: this package has no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = L.require_device(dev.index)
+    n = data.shape[0]
+    ch = data.shape[1] if data.ndim == 2 else 1
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        # torch has no uint16/etc. issue here: the bytes are shipped as they are and decoded on the device
+        raw = torch.from_numpy(data.reshape(-1).view(np.uint8)).to(dev)
+        with torch.cuda.device(dev):
+            L.check(lib.s2v_pcm_to_mono_f32(raw.data_ptr(), _PCM_KIND[data.dtype], ch, n, out.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "s2v_pcm_to_mono_f32")
+    return resample_device(out, int(sr_native), int(sr))
+
+
+def load_wav(path, sr):
+    """futils/audio.py:9-10: ``librosa.core.load(path, sr=sr)[0]`` - float32 numpy, mono, resampled to ``sr``.  The file is read on
+    the host (scipy.io.wavfile; the reference hands every non-wav input to ffmpeg first, inference.py:200-203); decode, channel
+    mix and the resampler run on the GPU."""
+    from scipy.io import wavfile
+    sr_native, data = wavfile.read(path)
+    return load_array_device(data, int(sr_native), int(sr)).cpu().numpy()
 
 
 def get_hop_size():

@@ -1,4 +1,4 @@
-"""Drop-in mirrors of the reference's models package for the hot path (LNet, DNet).
+"""Drop-in mirrors of the reference's models package for the hot path (LNet, DNet, ENet).
 
 ``load_checkpoint`` / ``load_network`` / ``load_DNet`` keep the behaviour of the reference's
 models/__init__.py:12-56 (strip ``module.``, drop ``low_res`` keys, strict=False; DNet from
@@ -21,6 +21,19 @@ def load_checkpoint(path, model):
         new_s[k.replace("module.", "")] = v
     model.load_state_dict(new_s, strict=False)
     return model
+
+
+def load_network(args):
+    """models/__init__.py:29-35 of the reference: LNet from ``args.LNet_path``, wrapped by ENet from ``args.ENet_path`` (whose
+    ``low_res.*`` keys are skipped by load_checkpoint, so the LNet weights stay the ones just loaded); returns ``model.eval()``
+    on the CPU like the reference - the caller moves it to the GPU (inference.py:250)."""
+    from .ENet import ENet
+    from .LNet import LNet
+    L_net = LNet()
+    L_net = load_checkpoint(args.LNet_path, L_net)
+    E_net = ENet(lnet=L_net)
+    model = load_checkpoint(args.ENet_path, E_net)
+    return model.eval()
 
 
 def load_DNet(args):

@@ -287,7 +287,10 @@ class EngineBase:
         seen, total = set(), 0
         wss = [ent["ws"]] if ent["ws"] is not None else [pt["ws"] for pt in ent["parts"]]
         for ws in wss + [ent["io"]]:
+            flat = []
             for t in ws.values():
+                flat += list(t) if isinstance(t, (list, tuple)) else [t]
+            for t in flat:
                 st = t.untyped_storage()
                 if st.data_ptr() not in seen:
                     seen.add(st.data_ptr())

@@ -149,6 +149,33 @@ def dnet_spec():
     return s
 
 
+def enet_spec(num_style_feat=512):
+    """ENet's own 64 tensors (models/ENet.py:8-80; ``low_res.*`` = the wrapped LNet, registered first)."""
+    ch = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128}
+    s = _conv("conv_body_first", 3, ch[128], 1)
+    cin = ch[128]
+    for j, i in enumerate(range(8, 2, -1)):
+        cout = ch[2 ** (i - 1)]
+        p = f"conv_body_down.{j}"
+        s += _conv(p + ".conv1", cin, cin, 3) + _conv(p + ".conv2", cin, cout, 3) + _conv(p + ".skip", cin, cout, 1, bias=False)
+        cin = cout
+    s += _linear("final_linear", ch[4] * 16, num_style_feat) + _conv("final_conv", cin, ch[4], 3)
+    cin, convs = 3, []
+    for i in (7, 8):
+        cout = ch[2 ** i]
+        convs += [(cin, cout), (cout, cout)]
+        cin = cout
+    for j, (ci, co) in enumerate(convs):
+        p = f"style_convs.{j}"
+        s += [(p + ".weight", (1,), P), (p + ".bias", (1, co, 1, 1), P), (p + ".modulated_conv.weight", (1, co, ci, 3, 3), P)]
+        s += _linear(p + ".modulated_conv.modulation", num_style_feat, ci)
+    for j, ci in enumerate((ch[128], ch[256])):
+        p = f"to_rgbs.{j}"
+        s += [(p + ".bias", (1, 3, 1, 1), P), (p + ".modulated_conv.weight", (1, 3, ci, 1, 1), P)]
+        s += _linear(p + ".modulated_conv.modulation", num_style_feat, ci)
+    return s
+
+
 def build_param_tree(root: nn.Module, spec, seed: int = 0) -> None:
     """Registers every tensor of ``spec`` under nested container modules of ``root`` and
     gives it a PyTorch-default-like init (spectral-norm u/v from a short power iteration,

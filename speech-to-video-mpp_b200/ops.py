@@ -369,6 +369,57 @@ def op_grouped_linear(lib, hidden, groups_dev, tile2group_dev, n_tiles, out) -> 
               (hidden, h2, groups_dev, tile2group_dev, out))
 
 
+def op_resize(lib, x, y, chan_scale=None) -> Op:
+    """bilinear resize (align_corners=False) of an fp16 NHWC tensor, optional per-(n, c) float32 scale [N, C]."""
+    vx, vy = view(x), view(y)
+    assert chan_scale is None or (chan_scale.dtype == torch.float32 and tuple(chan_scale.shape) == (x.shape[0], x.shape[3]) and chan_scale.stride(1) == 1)
+    op = Op("resize_bilinear", lib.s2v_resize_bilinear,
+            (C.byref(vx), C.byref(vy), _ptr(chan_scale), 0 if chan_scale is None else chan_scale.stride(0)), (vx, vy, x, y, chan_scale))
+    op.alg_bytes = 2.0 * (x.numel() + y.numel())
+    return op
+
+
+def op_resize_planes(lib, src, dst) -> Op:
+    """src [N,P,H,W] float32 (a channel window of a contiguous NCHW tensor) -> dst [N,P,OH,OW], bilinear, align_corners=False."""
+    n, p, h, w = src.shape
+    assert src.dtype == dst.dtype == torch.float32 and src.stride(3) == 1 and src.stride(2) == w and dst.stride(3) == 1 and dst.stride(2) == dst.shape[3]
+    assert tuple(dst.shape[:2]) == (n, p)
+    return Op("resize_planes", lib.s2v_resize_planes_f32,
+              (_ptr(src), src.stride(0), src.stride(1), n, p, h, w, _ptr(dst), dst.stride(0), dst.stride(1), dst.shape[2], dst.shape[3]), (src, dst))
+
+
+def op_style_demod(lib, w2, s, cin, cout, gain, out, eps=1e-8) -> Op:
+    """s: float32 rows (a column window of the modulation table) [N, >= cin]; out float32 [N, cout]."""
+    assert w2.dtype == torch.float32 and tuple(w2.shape) == (cout, cin) and s.stride(1) == 1 and out.is_contiguous()
+    return Op("style_demod", lib.s2v_style_demod, (_ptr(w2), _ptr(s), s.stride(0), s.shape[0], cin, cout, float(eps), float(gain), _ptr(out)),
+              (w2, s, out))
+
+
+def op_style_epilogue(lib, x, y, *, a=None, bias=None, noise=None, noise_w=None, slope=0.2, post=None) -> Op:
+    vx, vy = view(x), view(y)
+    assert post is None or post.stride(1) == 1
+    op = Op("style_epilogue", lib.s2v_style_epilogue,
+            (C.byref(vx), _ptr(a), _ptr(bias), _ptr(noise), _ptr(noise_w), float(slope), _ptr(post), 0 if post is None else post.stride(0), C.byref(vy)),
+            (vx, vy, x, y, a, bias, noise, noise_w, post))
+    op.alg_bytes = 2.0 * (x.numel() + y.numel()) + (4.0 * noise.numel() if noise is not None else 0.0)
+    return op
+
+
+def op_to_rgb(lib, x, w, s, bias, skip, out, crop=0) -> Op:
+    vx = view(x)
+    assert w.dtype == torch.float32 and tuple(w.shape) == (3, x.shape[3]) and s.stride(1) == 1 and out.is_contiguous()
+    op = Op("to_rgb", lib.s2v_to_rgb, (C.byref(vx), _ptr(w), _ptr(s), s.stride(0), _ptr(bias), _ptr(skip), _ptr(out), int(crop)),
+            (vx, x, w, s, bias, skip, out))
+    op.alg_bytes = 2.0 * x.numel() + 4.0 * out.numel() + (4.0 * skip.numel() if skip is not None else 0.0)
+    return op
+
+
+def op_reflect_pad_nchw(lib, src, pad, dst) -> Op:
+    n, c, h, w = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and tuple(dst.shape) == (n, c, h + 2 * pad, w + 2 * pad)
+    return Op("reflect_pad_nchw", lib.s2v_reflect_pad_nchw_f32, (_ptr(src), n * c, h, w, pad, _ptr(dst)), (src, dst))
+
+
 def op_mean_over_w(lib, x, y) -> Op:
     vx, vy = view(x), view(y)
     return Op("mean_over_w", lib.s2v_mean_over_w, (C.byref(vx), C.byref(vy)), (vx, vy, x, y))

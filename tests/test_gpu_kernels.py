@@ -442,7 +442,7 @@ def test_resize_bilinear(G, n, c, h, w, oh, ow):
     for sc in (None, scale):
         y = torch.full((n, oh, ow, c), float("nan"), device="cuda", dtype=torch.float16)
         vx, vy = ops.view(x), ops.view(y)
-        L.check(lib.s2v_resize_bilinear(C.byref(vx), C.byref(vy), None if sc is None else sc.data_ptr(), ops.cur_stream()))
+        L.check(lib.s2v_resize_bilinear(C.byref(vx), C.byref(vy), None if sc is None else sc.data_ptr(), 0, ops.cur_stream()))
         ref = F.interpolate(x.permute(0, 3, 1, 2).float(), size=(oh, ow), mode="bilinear", align_corners=False)
         if sc is not None:
             ref = ref * sc[:, :, None, None]
@@ -486,3 +486,39 @@ def test_two_devices_in_one_process(G):
         net.load_state_dict(sd, strict=True)
         outs.append(net(mel.to("cuda:%d" % d), face.to("cuda:%d" % d)).cpu())      # current device stays cuda:0 throughout
     assert torch.equal(outs[0], outs[1])
+
+
+def test_load_wav_decode_and_resampler_vs_oracle(G):
+    """load_wav (futils/audio.py:9-10) behind the file read: PCM decode + mono mix bit-exact, the kaiser_best resampler against the
+    numpy restatement of resampy (oracle/resample.py; float64 accumulation in the same order: bit-exact), librosa's length rule,
+    and the reference's own sample read from a real wav file."""
+    import os
+    from oracle import resample as R
+    from s2v_b200.futils import audio
+    g = np.load(os.path.join(GOLDEN, "mel_ref_golden.npz"))
+    pcm = g["speech_pcm"]                                                  # int16 mono, 16 kHz
+    got = audio.load_array_device(pcm, 16000, 16000).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, R.pcm_to_float_mono(pcm))
+    rng = np.random.default_rng(0)
+    stereo = rng.integers(-32768, 32767, size=(5000, 2), dtype=np.int16)
+    assert np.array_equal(audio.load_array_device(stereo, 16000, 16000).cpu().numpy(), R.pcm_to_float_mono(stereo))
+    u8 = rng.integers(0, 255, size=3000, dtype=np.uint8)
+    assert np.array_equal(audio.load_array_device(u8, 16000, 16000).cpu().numpy(), R.pcm_to_float_mono(u8))
+    for sr0 in (44100, 48000, 22050, 8000, 11025):
+        x = pcm[: sr0 // 2 + 7]                                           # treat the samples as if recorded at sr0
+        ref = R.load_array(x, sr0, 16000)
+        got = audio.load_array_device(x, sr0, 16000).cpu().numpy()
+        assert got.shape == ref.shape == (int(np.ceil(len(x) * 16000.0 / sr0)),)
+        d = np.abs(got - ref).max()
+        print("resample %d -> 16000: max_abs %.3e" % (sr0, d))
+        assert d <= 1e-7
+    with pytest.raises(ValueError):
+        audio.resample_device(torch.zeros(1, device="cuda"), 48000, 16000)
+    # through a file, like the reference's call
+    import tempfile
+    from scipy.io import wavfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "a.wav")
+        wavfile.write(path, 22050, stereo)
+        w = audio.load_wav(path, 16000)
+        assert w.dtype == np.float32 and np.abs(w - R.load_array(stereo, 22050, 16000)).max() <= 1e-7
