@@ -137,6 +137,32 @@ int s2v_lap_blend_level(const float* coarse_out, const uint8_t* a_fine, const ui
                         const uint8_t* a_coarse, const uint8_t* b_coarse, int N, int h, int w, int C, float* out,
                         void* stream);
 
+/* ------------------------------------------------ per-frame image glue ---
+ * The numpy / OpenCV lines either side of the networks, batched over frames (uint8 images channels-last [N,H,W,3] as cv2
+ * holds them, float network tensors NCHW):
+ *   s2v_resize_linear_u8   cv2.resize(x, (OW, OH)) (INTER_LINEAR) of 8-bit images, BIT-EXACT (OpenCV's 11-bit fixed-point
+ *                          bilinear; an exact 2x down-scale is INTER_AREA): inference.py:292 (generated face -> its box), :308
+ *                          (frames -> 512 x 512), :392-393 (crops -> img_size).  dst: image n at dst + n*dst_sn, rows dst_sh bytes
+ *                          apart.  boxes_dev (nullable): int32 [N][4] = (y1, y2, x1, x2) per frame - frame n is resized to
+ *                          (y2-y1) x (x2-x1) and written INTO that window of dst image n, i.e. the paste of inference.py:295-297
+ *                          (dst = a copy of the full frames); max_box_pixels >= the largest box area.  C = 1 or 3.
+ *   s2v_resize_linear_f32  the float32 form (the mask at :308; the blended image back to the frame size at :313 with the
+ *                          np.clip(x, 0, 255) before (clip_in) and the np.uint8 truncation after (out_u8: dst is uint8) fused in).
+ *                          Taps in double precision = what cv2.resize returns through its IPP path (within 1e-4 on 0..255).
+ *   s2v_fake_to_bgr_u8     preprocessing/facing.py:190-192: fake [N,3,H,W] -> np.uint8((clamp(x,-1,1) + 1) / 2. * 255), RGB -> BGR
+ *   s2v_face_batch         inference.py:394-399 + :260-262: oface / face uint8 [N,S,S,3] (already at img_size) -> img_batch float32
+ *                          [N,6,S,S] (rows >= S/2 of the face zeroed | reference, / 255.) and img_original float32 [N,3,S,S]
+ *   s2v_compose_pred_u8    inference.py:267, :282-288, :290: clamp(pred,0,1) [mixed with img_original where the masked input is
+ *                          non-zero] * 255 -> uint8 [N,S,S,3].  All bit-exact against the reference's lines.                      */
+int s2v_resize_linear_u8(const uint8_t* src, int N, int H, int W, int C, uint8_t* dst, int64_t dst_sn, int64_t dst_sh,
+                         const int32_t* boxes_dev, int OH, int OW, int max_box_pixels, void* stream);
+int s2v_resize_linear_f32(const float* src, int N, int H, int W, int C, void* dst, int OH, int OW, int clip_in, int out_u8,
+                          void* stream);
+int s2v_fake_to_bgr_u8(const float* fake, int N, int H, int W, uint8_t* out, void* stream);
+int s2v_face_batch(const uint8_t* oface, const uint8_t* face, int N, int S, float* img_batch, float* img_original, void* stream);
+int s2v_compose_pred_u8(const float* pred, const float* img_batch, const float* img_original, int N, int S, int compose,
+                        uint8_t* out, void* stream);
+
 /* ----------------------------------------------------------- flow warp ---
  * replaces futils/flow_util.py:3-15 + :41-56 (convert_flow_to_deformation,
  * bilinear resize of the grid, F.grid_sample bilinear/zeros/align_corners=False)

@@ -63,6 +63,11 @@ _SIGNATURES = {
     "s2v_style_epilogue": (C.c_int, [VP, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, VP, c_vp]),
     "s2v_to_rgb": (C.c_int, [VP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "s2v_reflect_pad_nchw_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "s2v_resize_linear_u8": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_i64, c_i64, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
+    "s2v_resize_linear_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    "s2v_fake_to_bgr_u8": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "s2v_face_batch": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "s2v_compose_pred_u8": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "s2v_semantic_windows": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, c_f64, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_u8": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "s2v_pyrdown_f32": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),

@@ -522,3 +522,51 @@ def test_load_wav_decode_and_resampler_vs_oracle(G):
         wavfile.write(path, 22050, stereo)
         w = audio.load_wav(path, 16000)
         assert w.dtype == np.float32 and np.abs(w - R.load_array(stereo, 22050, 16000)).max() <= 1e-7
+
+
+def test_frame_io_vs_reference_lines(G):
+    """The per-frame image glue (frame_io.py) against the reference's own lines executed with the real cv2
+    (tests/golden/imageops_golden.npz): bit-exact 8-bit resize / paste / batch formation / uint8 conversion; the float resize and
+    the blend round trip within one uint8 LSB."""
+    import os
+    from oracle import imageops as oio
+    from s2v_b200 import frame_io as fio
+    gold = np.load(os.path.join(GOLDEN, "imageops_golden.npz"))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    i = 0
+    while f"rs_u8_{i}_in" in gold:
+        ref = gold[f"rs_u8_{i}"]
+        oh, ow = ref.shape[:2]
+        assert np.array_equal(fio.resize_u8(dev(gold[f"rs_u8_{i}_in"])[None], oh, ow)[0].cpu().numpy(), ref), i
+        f = gold[f"rs_f32_{i}_in"]
+        assert np.abs(fio.resize_f32(dev(f)[None], oh, ow)[0].cpu().numpy() - gold[f"rs_f32_{i}"]).max() <= 1e-4, i
+        assert np.abs(fio.resize_f32(dev(f[:, :, :1])[None], oh, ow)[0, :, :, 0].cpu().numpy() - gold[f"rs_f32c1_{i}"]).max() <= 1e-4, i
+        i += 1
+    # full-size shapes of the path, against the oracle (itself bit-exact against cv2)
+    rng = np.random.default_rng(2)
+    big = rng.integers(0, 256, (2, 384, 384, 3), dtype=np.uint8)
+    for oh, ow in ((211, 187), (192, 192), (512, 512)):
+        got = fio.resize_u8(dev(big), oh, ow).cpu().numpy()
+        assert all(np.array_equal(got[k], oio.resize_linear_u8(big[k], oh, ow)) for k in range(2))
+    assert np.array_equal(fio.fake_to_bgr_u8(dev(gold["fake_in"]))[0].cpu().numpy(), gold["fake_bgr"])
+    of = torch.stack([fio.resize_u8(dev(gold[f"oface_{k}"])[None], 48, 48)[0] for k in range(3)])
+    fa = torch.stack([fio.resize_u8(dev(gold[f"face_{k}"])[None], 48, 48)[0] for k in range(3)])
+    ib, orig = fio.face_batch(of, fa)
+    assert np.array_equal(ib.cpu().numpy(), gold["img_batch"]) and np.array_equal(orig.cpu().numpy(), gold["img_original"])
+    pc = fio.compose_pred_u8(dev(gold["pred_in"]), ib, orig)
+    assert np.array_equal(pc.cpu().numpy(), gold["pred_u8_composed"])
+    assert np.array_equal(fio.compose_pred_u8(dev(gold["pred_in"])).cpu().numpy(), gold["pred_u8_plain"])
+    # paste: three frames, three different boxes, one launch
+    frame = gold["frame_in"]
+    boxes = [tuple(int(v) for v in gold["box"]), (0, 90, 0, 120), (5, 29, 100, 118)]
+    ff = fio.paste_faces(pc, dev(np.stack([frame] * 3)), boxes).cpu().numpy()
+    assert np.array_equal(ff[0], gold["frame_pasted"])
+    for k in (1, 2):
+        assert np.array_equal(ff[k], oio.paste_resized(gold["pred_u8_composed"][k], frame, boxes[k]))
+    with pytest.raises(ValueError):
+        fio.paste_faces(pc, dev(np.stack([frame] * 3)), [(0, 91, 0, 10)] * 3)
+    # inference.py:308-313
+    pp = fio.blend_paste_back(dev(gold["restored_in"])[None], dev(gold["frame_pasted"])[None], dev(gold["mouse_mask_in"])[None], 10)[0].cpu().numpy()
+    d = np.abs(pp.astype(np.int32) - gold["blend_back"].astype(np.int32))
+    print("blend_paste_back vs reference lines: max |diff| %d LSB, %.4f %% of the bytes differ" % (d.max(), 100 * (d > 0).mean()))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
