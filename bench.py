@@ -371,11 +371,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line (the JSON): everything else any library prints at the C level (NCCL's version banner and its
+    # NCCL_DEBUG=INFO init lines go to stdout by default) is sent to stderr by pointing fd 1 at fd 2 for the whole run; the JSON
+    # line is written to the saved descriptor at the end.  NCCL's init lines therefore stay visible (ranks, NVLS, channels).
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's init lines (ranks, NVLS / NVLink channels) stay visible, but on stderr: stdout is the one JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import s2v_b200  # noqa: F401
@@ -497,7 +501,8 @@ def main():
                 "gpu_launches": int(K * lt.item()), "launches_per_step": int(lt.item()),
                 "frame_checksum": checksum,
                 "roofline": roof, "cpu_baseline": cb, "kernel_classes": table, "other_rows": extras}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -353,7 +353,11 @@ class EngineBase:
             if ent["warm"] >= 1 and not torch.cuda.is_current_stream_capturing():
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # an explicit capture stream on THIS engine's device: torch's default capture stream is created once, on
+                # whichever device was current first, and launching device-1 kernels into a device-0 stream fails
+                if getattr(self, "_capture_stream", None) is None:
+                    self._capture_stream = torch.cuda.Stream(device=self.dev)
+                with torch.cuda.graph(g, stream=self._capture_stream):
                     self._run_plan(ent)
                 ent["graph"] = g
             return

@@ -11,11 +11,11 @@ B = int(os.environ.get("MB_B", "128"))
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 
 
-def bench(name, x, w, y, reps=20, **kw):
+def bench(name, x, w, y, reps=int(os.environ.get('MB_REPS', '20')), **kw):
     if only and only not in name:
         return
     op = ops.op_conv(lib, x, w, y, name=name, **kw)
-    for _ in range(3):
+    for _ in range(int(os.environ.get('MB_WARM', '3'))):
         op.run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
