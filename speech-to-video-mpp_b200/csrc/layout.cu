@@ -113,15 +113,15 @@ extern "C" int s2v_unpack_to_nchw_f32(const s2v_view* src, int c_off, int C, flo
 // models/ENet.py:93,104); optional per-(n, c) input scale = the StyleGAN2 modulation folded into the resize pass.
 namespace s2v {
 
+// grid (x-chunk blocks, OH, N): row taps are block-uniform, column taps per thread; 32-bit index arithmetic only
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(View x, View y, const float* __restrict__ chan_scale, long long scale_stride) {
   pdl_trigger();
   pdl_wait();
   const int C8 = x.c >> 3;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)y.n * y.h * y.w * C8;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  const int ox = (int)((idx / C8) % y.w), oy = (int)((idx / ((long long)C8 * y.w)) % y.h), n = (int)(idx / ((long long)C8 * y.w * y.h));
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;         // (ox, c8) of this output row
+  if (idx >= y.w * C8) return;
+  const int ox = idx / C8, c8 = idx - ox * C8;
+  const int oy = blockIdx.y, n = blockIdx.z;
   const float sch = (float)x.h / (float)y.h, scw = (float)x.w / (float)y.w;
   const float sy = fmaxf(sch * ((float)oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)ox + 0.5f) - 0.5f, 0.f);
   const int y0 = min((int)sy, x.h - 1), x0 = min((int)sx, x.w - 1);
@@ -176,9 +176,9 @@ extern "C" int s2v_resize_bilinear(const s2v_view* x, const s2v_view* y, const f
   if (!view_ok(x) || !view_ok(y) || x->n != y->n || x->c != y->c) return S2V_EINVAL;
   if (y->n == 0) return S2V_OK;
   if (chan_scale && ((((uintptr_t)chan_scale) & 15) || (scale_stride & 3) || scale_stride < 0)) return S2V_EINVAL;
-  const long long total = (long long)y->n * y->h * y->w * (x->c >> 3);
-  S2V_CUDA_TRY(launch_pdl(resize_bilinear_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, mk(x), mk(y), chan_scale,
-                          (long long)(scale_stride ? scale_stride : x->c)));
+  if (y->h > 65535 || y->n > 65535) return S2V_EINVAL;
+  S2V_CUDA_TRY(launch_pdl(resize_bilinear_kernel, dim3(ceil_div((long long)y->w * (x->c >> 3), 256), y->h, y->n), 256, 0, (cudaStream_t)stream,
+                          mk(x), mk(y), chan_scale, (long long)(scale_stride ? scale_stride : x->c)));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
