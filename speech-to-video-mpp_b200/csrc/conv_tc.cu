@@ -44,7 +44,7 @@ struct TcParams {
   int m_pairs, total_pair_tiles;                          // CTA-pair mode: the pair (leader, peer) owns M tiles (2*mp, 2*mp+1)
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
-  int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident;
+  int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident, pf_dist;
   float* stats;                                           // fused per-(image, tile, channel) sum / sumsq
   int st_c_off, st_c_total, st_chunk_off, st_chunks_total, st_groups, st_gmax;
   View y, r1, r2;
@@ -88,6 +88,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a patch a few tiles ahead: the A-patch slots are few (2 when the weights are resident next to a 128-column
+// staging tile), so a load's latency is only partly hidden by the previous chunk's MMAs; pulling the NEXT tiles' patches into
+// L2 while the slots are busy turns the slot loads into L2 hits
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -686,6 +693,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
         for (int tile = w_first; tile < w_total; tile += w_step) {
           int ntile, n0, y0, x0, tile_sp;
+          if (p.pf_dist) {                            // this CTA's tile pf_dist rounds ahead -> L2
+            const int pt = tile + p.pf_dist * w_step;
+            if (pt < w_total) {
+              tile_coords<C2>(p, pt, crank, ntile, n0, y0, x0, tile_sp);
+              for (int c = 0; c < p.cin_chunks; ++c) tma_prefetch_4d(&tmA, c * kChunkK, x0 - p.pad_w, y0 - p.pad_h, n0);
+              for (int c = 0; c < chunks2; ++c) tma_prefetch_4d(&tmA2, c * kChunkK, x0 - p.pad2_w, y0 - p.pad2_h, n0);
+            }
+          }
           tile_coords<C2>(p, tile, crank, ntile, n0, y0, x0, tile_sp);
           int kcol = 0;
           for (int seg = 0; seg < 2; ++seg) {
@@ -1078,6 +1093,10 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.b_resident = sp.resident ? 1 : 0;
   p.bn_narrow = sp.resident ? narrow_n : 0;
   p.nf_chunk = nf_chunk;
+  // L2 prefetch distance in tiles.  Measured on B200 (LNet B=128 / DNet B=64 plans): 0 / 1 / 2 / 4 -> 13.69 / 13.88 / 13.82 / 13.88 ms
+  // and 9.29 / 9.52 / 9.41 / 9.39 ms - the patch loads already hit L2 (the producer kernel just wrote the tensor), so it stays off.
+  static const int pf_env = [] { const char* e = getenv("S2V_PF"); return e ? atoi(e) : 0; }();      // development knob
+  p.pf_dist = (sp.halo && p.n_tiles_n == 1) ? pf_env : 0;
   p.a_slots = sp.halo ? sp.a_slots : 0;
   p.a_slot_bytes = sp.halo ? a_slot_bytes : 0;
   p.ring_bytes = sp.ring_bytes;
