@@ -249,9 +249,11 @@ def roofline_of(tot, total, what):
     ach = tc[2] / (tc[0] * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 / TMEM / TMA implicit GEMM), %d launches per %s" % (tc[1], what),
             "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum of the class's most frequent shape (LNet 12x12 level, 3x3, K = 9216) from one
-            # ncu --set full capture (profiles/r1c_ncu_full_conv_tc_res2_raw.csv): 56.2 MB read + 1.3 MB written; algorithmic 51.8 MB
-            "traffic": 57.5e6, "traffic_of": "one LNet 3x3 K=9216 launch (ncu --set full, DRAM bytes per launch; algorithmic 51.8e6); other shapes: profiles/",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the class's largest launch on this metric (DNet editing_net.encoder.down0,
+            # 256 x 256, 64 -> 128, 3x3, batch 64: 5.8 % of the class time) from one ncu --set full capture
+            # (profiles/r2_ncu_full_conv_tc_dnet_down0_raw.csv): 537.1 MB read + 1016.4 MB written; algorithmic 1610.8 MB
+            # (536.9 in + 0.15 weights + 1073.7 out) - no re-reads.  LNet 12x12 3x3 K=9216: 57.5 MB vs 51.8 (profiles/r1c_*)
+            "traffic": 1553.5e6, "traffic_of": "one DNet down0 launch (256x256, 64->128, 3x3, B=64; ncu --set full, DRAM bytes per launch; algorithmic 1610.8e6); other shapes: profiles/",
             "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
             "alg_gflop": round(tc[2] / 1e9, 1), "kernel_ms": round(tc[0], 3), "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
             "share_of_step_kernels": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
