@@ -4,6 +4,8 @@
 // per query row keeps q and the output row in registers and runs an online softmax over keys
 // in chunks of 8 (exp2 with the scale folded into q).  This SIMT kernel is the general-shape path; the 144-token
 // LNet geometry runs on the tensor-core kernel below.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace s2v {
@@ -195,6 +197,215 @@ __global__ void __launch_bounds__(T * 2) attention_mma_kernel(View q, View k, Vi
   }
 }
 
+
+// ---- tcgen05 / TMEM / TMA path (the default for the 144-token LNet geometry) ---------------------------------------------
+// One CTA (128 threads) per (frame, head).  Q, K, V of the head ([144 tokens][64 dims] fp16 = channel window h*64 .. of the
+// channels-last token tensors) arrive by three tiled TMA loads in the K-major SWIZZLE_128B layout tcgen05.mma reads.
+// For each of the two 128-row query tiles (rows 0-127, 128-143 + 112 don't-care rows):
+//   S[128 x 144]  = Q_tile K^T      4 x tcgen05.mma (M 128, N 144, K 16), accumulator in TMEM columns [0, 144)
+//   softmax       thread = query row: two passes over its TMEM row (max, then exp2 / sum); P (fp16) is written to shared
+//                 memory as the K-major A operand of the second GEMM (three 64-column panels, SWIZZLE_128B)
+//   O[128 x 64]   = P V             9 x tcgen05.mma (M 128, N 64, K 16): V stays as loaded ([token][dim]) and is read as an
+//                 MN-MAJOR B operand (N = dims contiguous, K = tokens: one 16-row step = 2 048 bytes; verified layout of
+//                 tools/probe_colsum_umma.cu), accumulator in TMEM columns [160, 224)
+//   epilogue      tcgen05.ld of the row, * 1 / sum, fp16, 128-byte row store
+// 102 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM.
+namespace attn_tc {
+constexpr int kT = 144, kRowsBytes = kT * 128;                  // 18 432 B per operand tile
+constexpr int kOffQ = 0, kOffK = kRowsBytes, kOffV = 2 * kRowsBytes, kOffP = 3 * kRowsBytes, kPBytes = 3 * 128 * 128;
+constexpr int kSmem = kOffP + kPBytes + 64 + 1024;              // + barriers / tmem pointer + 1024-byte alignment slack
+constexpr unsigned kSpin = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (++spins > kSpin) __trap();
+  }
+}
+// shared-memory matrix descriptor, SWIZZLE_128B: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | swizzle 2 << 61
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(128, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, View o, int heads, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  pdl_trigger();
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  uint8_t* al = raw + (base - smem_u32(raw));
+  const uint32_t sQ = base + kOffQ, sK = base + kOffK, sV = base + kOffV, sP = base + kOffP;
+  const uint32_t bar_tma = sP + kPBytes, bar_mma = bar_tma + 8, tptr = bar_tma + 16;
+  volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(al + kOffP + kPBytes + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / heads, h = blockIdx.x - n * heads;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_tma) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_mma) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tptr) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tptr_gen;
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_tma), "r"(3u * kRowsBytes) : "memory");
+    const int c0 = h * kDh;
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(sQ), "l"(&tmQ), "r"(bar_tma), "r"(c0), "r"(0), "r"(0), "r"(n) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(sK), "l"(&tmK), "r"(bar_tma), "r"(c0), "r"(0), "r"(0), "r"(n) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(sV), "l"(&tmV), "r"(bar_tma), "r"(c0), "r"(0), "r"(0), "r"(n) : "memory");
+  }
+  mbar_wait(bar_tma, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // instruction descriptors: D fp32 (bit 4), A / B fp16, N >> 3 at bit 17, M >> 4 at bit 24; bit 16 = B is MN-major
+  const uint32_t idesc_s = (1u << 4) | ((uint32_t)(kT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(kDh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t tS = tmem, tO = tmem + 160;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const int rl = warp * 32 + lane;                         // row of the 128-row tile this thread owns
+  uint32_t phase = 0;
+  for (int mt = 0; mt < 2; ++mt) {
+    // ---- S = Q_tile K^T: the second tile starts 128 rows (16 KB) into Q; its rows past token 143 read whatever follows
+    //      (K's bytes - finite fp16 values) and are never used
+    if (threadIdx.x == 0) {
+      const uint64_t da = desc(sQ + (uint32_t)mt * 16384u, 16, 1024), db = desc(sK, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma(tS, da + 2u * k, db + 2u * k, idesc_s, k ? 1u : 0u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma) : "memory");
+    }
+    mbar_wait(bar_mma, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int tok = mt * 128 + rl;
+    const bool valid = tok < kT;
+    // tcgen05.ld is warp-collective: every lane walks its TMEM row (the don't-care rows of the second tile too); only the
+    // shared-memory / global stores are predicated
+    float l = 0.f;
+    {
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kT; c += 16) {
+        float v[16];
+        tmem_ld16(tS + lane_sel + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+      }
+      const float mb = mx * scale_log2e;
+#pragma unroll 1
+      for (int c = 0; c < kT; c += 16) {
+        float v[16];
+        tmem_ld16(tS + lane_sel + (uint32_t)c, v);
+        H8 p8[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 pp = __floats2half2_rn(exp2f(fmaf(v[2 * i], scale_log2e, -mb)), exp2f(fmaf(v[2 * i + 1], scale_log2e, -mb)));
+          const float2 pf = __half22float2(pp);             // the sum uses the rounded values: rows are exactly normalised
+          l += pf.x + pf.y;
+          p8[i >> 2].v[i & 3] = pp;
+        }
+        // K-major SWIZZLE_128B A tile: panel = 64 key columns, row = 128 B, 16-byte chunk j stored at j ^ (row & 7)
+        const int panel = c >> 6, chunk = (c & 63) >> 3;
+        uint8_t* rowp = al + kOffP + panel * 16384 + rl * 128;
+        if (valid) {
+          *reinterpret_cast<H8*>(rowp + (((chunk) ^ (rl & 7)) << 4)) = p8[0];
+          *reinterpret_cast<H8*>(rowp + (((chunk + 1) ^ (rl & 7)) << 4)) = p8[1];
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes of P -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- O = P V
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int ks = 0; ks < kT / 16; ++ks) {
+        const uint64_t da = desc(sP + (uint32_t)(ks >> 2) * 16384u, 16, 1024) + 2u * (ks & 3);
+        const uint64_t db = desc(sV + (uint32_t)ks * 2048u, 16384, 1024);   // MN-major: 16 token rows per K step
+        mma(tO, da, db, idesc_o, ks ? 1u : 0u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma) : "memory");
+    }
+    mbar_wait(bar_mma, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      const float inv = 1.f / l;
+      __half* op = o.p + n * o.sn + (valid ? tok : 0) * o.sw + h * kDh;
+#pragma unroll
+      for (int c = 0; c < kDh; c += 16) {
+        float v[16];
+        tmem_ld16(tO + lane_sel + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= inv;
+        if (valid) {
+          st_h8(op + c, f_to_h8(v));
+          st_h8(op + c + 8, f_to_h8(v + 8));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // TMEM reads done before the next tile's MMAs overwrite S / O
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;     // resolved once; immutable afterwards
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+// the head's [144 tokens][64 dims] window of a [N,1,144,C] token tensor as a 4-D tiled map {c, token, 1, n}
+static bool make_map(EncodeTiledFn enc, const s2v_view* t, CUtensorMap* tm) {
+  cuuint64_t gdim[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, 1, (cuuint64_t)t->n};
+  cuuint64_t gstr[3] = {(cuuint64_t)t->sw * 2, (cuuint64_t)t->sh * 2, (cuuint64_t)t->sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kDh, (cuuint32_t)kT, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t->ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace attn_tc
+
 }  // namespace s2v
 
 using namespace s2v;
@@ -206,7 +417,26 @@ extern "C" int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_vie
   if (q->h != 1 || k->h != 1 || v->h != 1 || o->h != 1 || T > kMaxT || k->w != T || v->w != T || o->w != T) return S2V_EINVAL;
   if (q->c < heads * kDh || k->c < heads * kDh || v->c < heads * kDh || o->c < heads * kDh) return S2V_EINVAL;
   if (k->n != q->n || v->n != q->n || o->n != q->n) return S2V_EINVAL;
-  if (T == 144 && !getenv("S2V_ATTN_SIMT")) {      // the LNet geometry (12 x 12 tokens): tensor-core path
+  static const int path = [] { const char* e = getenv("S2V_ATTN"); return e ? atoi(e) : 0; }();   // development knob: 0 tcgen05, 1 mma.sync, 2 SIMT
+  if (T == 144 && path == 0 && (q->sw & 7) == 0 && (k->sw & 7) == 0 && (v->sw & 7) == 0) {
+    // the LNet geometry (12 x 12 tokens): tcgen05 / TMEM / TMA path
+    attn_tc::EncodeTiledFn enc = attn_tc::get_encode();
+    if (!enc) return S2V_EUNSUPPORTED;
+    CUtensorMap tq, tk, tv;
+    if (!attn_tc::make_map(enc, q, &tq) || !attn_tc::make_map(enc, k, &tk) || !attn_tc::make_map(enc, v, &tv)) return S2V_ECUDA;
+    static DeviceOnce attr_t5;
+    const int dev = current_device();
+    if (dev < 0) return S2V_ECUDA;
+    if (attr_t5.needed(dev)) {
+      S2V_CUDA_TRY(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::kSmem));
+      attr_t5.mark(dev);
+    }
+    S2V_CUDA_TRY(launch_pdl(attn_tc::attention_tc_kernel, q->n * heads, 128, (size_t)attn_tc::kSmem, (cudaStream_t)stream, tq, tk, tv, mk(o), heads,
+                            scale * 1.4426950408889634f));
+    S2V_CHECK_LAUNCH();
+    return S2V_OK;
+  }
+  if (T == 144 && path <= 1) {      // mma.sync path (kept as a cross-check of the tcgen05 kernel)
     const size_t smem_tc = (size_t)3 * 144 * kRowH * sizeof(__half);
     static DeviceOnce attr_tc;       // per device, idempotent
     const int dev = current_device();
