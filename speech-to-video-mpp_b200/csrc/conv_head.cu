@@ -24,15 +24,19 @@
 namespace s2v {
 namespace head {
 
-constexpr int kK = 7, kPW = 32, kRows = 4, kOW = kPW - (kK - 1), kPH = kRows + kK - 1;   // 26 output columns, 10 patch rows
-constexpr int kPatchBytes = kPW * kPH * 128;            // 40 KB: one 64-channel chunk of the patch
+constexpr int kK = 7, kPW = 32, kRows = 4, kOW = kPW - (kK - 1);   // 26 output columns, 4 output rows per 128-position M tile
+// SUB vertically stacked M tiles share ONE patch of SUB * 4 + 6 rows (SUB = 2: 14 rows = 56 KB for 8 x 26 outputs instead of two
+// 10-row patches = 80 KB): 30 % less patch traffic and twice the MMA work behind every patch load.  SUB = 2 needs the weights
+// resident (Cin = 64: the FinalBlock2d heads); the streaming-weights head (flow_out, Cin = 256) keeps SUB = 1.
+__host__ __device__ constexpr int patch_rows(int sub) { return sub * kRows + kK - 1; }
+__host__ __device__ constexpr int patch_bytes(int sub) { return kPW * patch_rows(sub) * 128; }
 constexpr int kBTile = 64 * 128;                         // 8 KB: (kx, co) x 64 channels of one (chunk, ky)
 constexpr int kASlots = 2, kBRing = 8, kThreads = 320;   // producer, MMA, 2 x 4 epilogue warps (the epilogue is the longer stage)
 constexpr int kStageBytes = 56 * 128 * 4;               // fp32 accumulator parked column-major, one buffer per epilogue group
 constexpr unsigned kSpin = 1u << 26;
 
 struct Params {
-  int N, H, W, cout, chunks, tiles_x, tiles_y, total_tiles, b_resident, act;
+  int N, H, W, cout, chunks, tiles_x, tiles_y, total_tiles, b_resident, act, rows_per_tile;
   float ap;
   const float* bias;
   float* out;
@@ -89,12 +93,14 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& n, i
   n = tile / per_img;
   const int t = tile - n * per_img;
   const int ty = t / p.tiles_x;
-  y0 = ty * kRows;
+  y0 = ty * p.rows_per_tile;
   x0 = (t - ty * p.tiles_x) * kOW;
 }
 
+template <int SUB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  constexpr int kPatchBytes = patch_bytes(SUB);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_trigger();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -112,12 +118,12 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < kASlots; ++i) { mbar_init(afull + 8u * i, 1); mbar_init(aempty + 8u * i, 1); }
     for (int i = 0; i < kBRing; ++i) { mbar_init(bfull + 8u * i, 1); mbar_init(bempty + 8u * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8u * i, 1); mbar_init(tempty + 8u * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8u * i, 1); mbar_init(tempty + 8u * i, 4 * SUB); }
     mbar_init(ball, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tptr) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(128u * SUB) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -164,7 +170,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t buf = (uint32_t)j & 1u;
         mbar_wait(tempty + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem + buf * 64u;
+        const uint32_t d_tmem = tmem + buf * (64u * SUB);                              // SUB accumulators of 64 columns per buffer
         uint32_t accum = 0;
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(afull + 8u * a, aph);
@@ -180,12 +186,14 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               bdesc = umma_desc(b0 + s * kBTile);
             }
-            const uint64_t adesc = adesc0 + (uint64_t)((ky * kPW * 128) >> 4);       // ky patch rows further down
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                                             // +32 B = 16 channels along K
-              umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
-              accum = 1u;
+            for (int sub = 0; sub < SUB; ++sub) {                                       // the stacked M tiles read the same weight tile
+              const uint64_t adesc = adesc0 + (uint64_t)(((ky + sub * kRows) * kPW * 128) >> 4);   // (ky + 4 sub) patch rows further down
+#pragma unroll
+              for (int k = 0; k < 4; ++k)                                               // +32 B = 16 channels along K
+                umma_f16(d_tmem + 64u * sub, adesc + 2u * k, bdesc + 2u * k, idesc, accum | (uint32_t)(k > 0));
             }
+            accum = 1u;
             if (!p.b_resident) {
               umma_commit(bempty + 8u * s);
               if (++s == kBRing) { s = 0; sph ^= 1u; }
@@ -207,14 +215,17 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int oy = et >> 5, ox = et & 31;
     float* stage = stage0 + grp * (kStageBytes / 4);
     const uint32_t bar_id = 1u + (uint32_t)grp;
-    const uint32_t buf = (uint32_t)grp;                       // tile j -> group j & 1 -> accumulator buffer j & 1
+    // SUB = 1: tile j -> group j & 1 -> accumulator buffer j & 1 (a group drains every other tile).
+    // SUB = 2: group g drains stacked tile g of EVERY tile (accumulator g of buffer j & 1).
     int jj = 0;                                               // tiles this group has drained
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, ++jj) {
+    for (int tile = blockIdx.x + (SUB == 1 ? grp : 0) * gridDim.x; tile < p.total_tiles; tile += (SUB == 1 ? 2 : 1) * gridDim.x, ++jj) {
       int n, y0, x0;
       tile_coords(p, tile, n, y0, x0);
-      mbar_wait(tfull + 8u * buf, (uint32_t)jj & 1u);
+      const uint32_t buf = SUB == 1 ? (uint32_t)grp : ((uint32_t)jj & 1u);
+      if (SUB == 2) y0 += grp * kRows;
+      mbar_wait(tfull + 8u * buf, SUB == 1 ? ((uint32_t)jj & 1u) : (((uint32_t)jj >> 1) & 1u));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * 64u;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (64u * SUB) + (SUB == 2 ? 64u * grp : 0u);
       float v[64];
       tmem_ld16(trow, v); tmem_ld16(trow + 16u, v + 16); tmem_ld16(trow + 32u, v + 32); tmem_ld16(trow + 48u, v + 48);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -244,7 +255,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u * SUB) : "memory");
   }
 }
 
@@ -285,19 +296,24 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   if (!enc) return S2V_EUNSUPPORTED;
   Params p;
   p.N = N; p.H = H; p.W = W; p.cout = cout; p.chunks = d->x.c / 64;
-  p.tiles_x = ceil_div(W, kOW); p.tiles_y = ceil_div(H, kRows);
+  // two stacked M tiles per patch when the weights of the single chunk stay resident next to two 14-row patches (Cin = 64)
+  static const int sub_env = [] { const char* e = getenv("S2V_HEAD_SUB"); return e ? atoi(e) : 2; }();      // development knob
+  const int fixed = 2 * kStageBytes + 256 + 1024;
+  const int sub = (sub_env == 2 && (long long)p.chunks * kK * kBTile + kASlots * patch_bytes(2) + fixed <= 227 * 1024) ? 2 : 1;
+  p.rows_per_tile = sub * kRows;
+  p.tiles_x = ceil_div(W, kOW); p.tiles_y = ceil_div(H, p.rows_per_tile);
   const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
   if (tiles <= 0 || tiles > 0x7fffffff) return S2V_EINVAL;
   p.total_tiles = (int)tiles;
   p.act = d->act; p.ap = d->act_param; p.bias = d->bias; p.out = d->y_f32;
-  const int fixed = 2 * kStageBytes + 256 + 1024;
-  p.b_resident = ((long long)p.chunks * kK * kBTile + kASlots * kPatchBytes + fixed <= 224 * 1024) ? 1 : 0;
+  const int kPatchBytes = patch_bytes(sub);
+  p.b_resident = (sub == 2 || (long long)p.chunks * kK * kBTile + kASlots * kPatchBytes + fixed <= 224 * 1024) ? 1 : 0;
   const size_t smem = (size_t)kASlots * kPatchBytes + (size_t)(p.b_resident ? p.chunks * kK : kBRing) * kBTile + fixed;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)d->x.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)d->x.sw * 2, (cuuint64_t)d->x.sh * 2, (cuuint64_t)d->x.sn * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)kPW, (cuuint32_t)kPH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)kPW, (cuuint32_t)patch_rows(sub), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->x.ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -317,13 +333,16 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   const int dev = current_device();
   if (dev < 0) return S2V_ECUDA;
   if (attr.needed(dev)) {
-    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr.mark(dev);
   }
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
-  S2V_CUDA_TRY(launch_pdl(conv_head_kernel, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
+  if (smem > 227 * 1024) return S2V_EINVAL;
+  if (sub == 2) S2V_CUDA_TRY(launch_pdl(conv_head_kernel<2>, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
+  else S2V_CUDA_TRY(launch_pdl(conv_head_kernel<1>, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
