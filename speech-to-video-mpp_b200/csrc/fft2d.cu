@@ -155,6 +155,19 @@ __global__ void __launch_bounds__((S / 2 + 1) * CB) irfft2_kernel(View sp, View 
   }
 }
 
+// Channels per block.  The fp16 channels-last rows are read / written 2 bytes per thread, so a block touches CB * 2 contiguous
+// bytes per pixel: 16 channels = one full 32-byte sector (8 channels use half of every sector they fetch).  Measured on B200, LNet
+// B = 128: 48 x 48 with CB 8 -> 16 (one 400-thread block per SM instead of two 200-thread ones): irfft2 45.8 -> 36.7 us, rfft2
+// 24.8 -> 23.3 us; 24 x 24 with CB 16 -> 32: irfft2 12.1 -> 11.1 us.  (Rejected: an fp16 exchange buffer + 96 registers for three
+// 48 x 48 blocks per SM - the spills cost more than the occupancy gives, 24.9 -> 29.1 / 45.7 -> 49.3 us.)
+static int fft48_cb16() {
+  static const int v = [] { const char* e = getenv("S2V_FFT48_CB16"); return e ? atoi(e) : 1; }();     // development knob
+  return v;
+}
+static int fft24_cb32() {
+  static const int v = [] { const char* e = getenv("S2V_FFT24_CB32"); return e ? atoi(e) : 1; }();     // development knob
+  return v;
+}
 static int fft_rev() {
   static const int rev = [] { const char* e = getenv("S2V_FFT_REV"); return e ? atoi(e) : 0; }();
   return rev;
@@ -208,8 +221,10 @@ extern "C" int s2v_rfft2(const s2v_view* x, const s2v_view* spec, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   if (x->h == 12 && x->c % 32 == 0) return launch_rfft2<12, 32>(x, spec, st);
   if (x->h == 12 && x->c % 8 == 0) return launch_rfft2<12, 8>(x, spec, st);
+  if (x->h == 24 && x->c % 32 == 0 && fft24_cb32()) return launch_rfft2<24, 32>(x, spec, st);
   if (x->h == 24 && x->c % 16 == 0) return launch_rfft2<24, 16>(x, spec, st);
   if (x->h == 24 && x->c % 8 == 0) return launch_rfft2<24, 8>(x, spec, st);
+  if (x->h == 48 && x->c % 16 == 0 && fft48_cb16()) return launch_rfft2<48, 16>(x, spec, st);
   if (x->h == 48 && x->c % 8 == 0) return launch_rfft2<48, 8>(x, spec, st);
   return S2V_EINVAL;
 }
@@ -220,8 +235,10 @@ extern "C" int s2v_irfft2(const s2v_view* spec, const s2v_view* add, const s2v_v
   cudaStream_t st = (cudaStream_t)stream;
   if (y->h == 12 && y->c % 32 == 0) return launch_irfft2<12, 32>(spec, add, y, st);
   if (y->h == 12 && y->c % 8 == 0) return launch_irfft2<12, 8>(spec, add, y, st);
+  if (y->h == 24 && y->c % 32 == 0 && fft24_cb32()) return launch_irfft2<24, 32>(spec, add, y, st);
   if (y->h == 24 && y->c % 16 == 0) return launch_irfft2<24, 16>(spec, add, y, st);
   if (y->h == 24 && y->c % 8 == 0) return launch_irfft2<24, 8>(spec, add, y, st);
+  if (y->h == 48 && y->c % 16 == 0 && fft48_cb16()) return launch_irfft2<48, 16>(spec, add, y, st);
   if (y->h == 48 && y->c % 8 == 0) return launch_irfft2<48, 8>(spec, add, y, st);
   return S2V_EINVAL;
 }
