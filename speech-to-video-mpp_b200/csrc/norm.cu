@@ -424,9 +424,13 @@ __global__ void __launch_bounds__(256) token_ln_kernel(View x, const float* __re
   for (int k = 0; k < 4; ++k) {
     const int c8 = lane + 32 * k;
     if (c8 < C8) {
-      float o[8];
+      float o[8], g[8], be[8];
+      *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(gamma + c8 * 8);        // 16-byte parameter loads (32 scalar
+      *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(gamma + c8 * 8 + 4);  // loads per lane made the kernel
+      *reinterpret_cast<float4*>(be) = *reinterpret_cast<const float4*>(beta + c8 * 8);         // instruction bound: 0.22 of HBM)
+      *reinterpret_cast<float4*>(be + 4) = *reinterpret_cast<const float4*>(beta + c8 * 8 + 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * gamma[c8 * 8 + i] + beta[c8 * 8 + i];
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * g[i] + be[i];
       st_h8(py + c8 * 8, f_to_h8(o));
     }
   }
@@ -619,6 +623,7 @@ extern "C" int s2v_reflect_border(const s2v_view* interior, void* stream) {
 extern "C" int s2v_token_layernorm(const s2v_view* x, const float* gamma, const float* beta, float eps,
                                    const s2v_view* y, void* stream) {
   if (!view_ok(x) || !view_ok(y) || !gamma || !beta || x->c > 1024) return S2V_EINVAL;
+  if ((((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) return S2V_EINVAL;        // 16-byte parameter loads
   if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return S2V_EINVAL;
   const long long total = (long long)x->n * x->h * x->w;
   launch_pdl(token_ln_kernel, ceil_div(total, 8), 256, 0, (cudaStream_t)stream, mk(x), gamma, beta, eps, mk(y));
