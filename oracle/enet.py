@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY - functional PyTorch restatement of the reference's ENet (the 96 -> 384
-upsampler that wraps LNet and is the object inference.py:266 really calls).  GROUNDWORK for the next round: the CUDA path
-for ENet is not built yet; this module, the schema and the golden output pin what it will be checked against.
+upsampler that wraps LNet and is the object inference.py:266 really calls).  The CUDA path (s2v_b200.models.ENet) is checked
+against this module and against the golden output of the unmodified reference in tests/test_gpu_enet.py.
 
 Follows /root/reference models/ENet.py:82-139 (forward) and models/base_blocks.py:29-49 (ResBlock), :460-508
 (ModulatedConv2d), :515-536 (StyleConv), :539-553 (ToRGB).  Pinned: tests/test_oracle_enet.py compares it with the unmodified

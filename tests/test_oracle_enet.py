@@ -1,6 +1,6 @@
-"""CPU: groundwork for SURVEY 8f #1 (ENet): the functional restatement (oracle/enet.py) against the golden output of the
-unmodified reference ENet (tests/golden/enet_seed0_b1_out.npz, oracle/make_golden_enet.py) and, when /root/reference is
-present, against the imported reference itself.  No CUDA path exists for ENet yet."""
+"""CPU: SURVEY 8f #1 (ENet): the functional restatement (oracle/enet.py) against the golden output of the unmodified
+reference ENet (tests/golden/enet_seed0_b1_out.npz, oracle/make_golden_enet.py) and, when /root/reference is present,
+against the imported reference itself.  The CUDA ENet is checked against both in tests/test_gpu_enet.py."""
 import os
 
 import numpy as np
