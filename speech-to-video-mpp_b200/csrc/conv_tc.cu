@@ -974,7 +974,19 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.str_h = d->stride_h; p.str_w = d->stride_w;
   p.cin_chunks = ceil_div(d->x.c, kChunkK);
   p.cout = cout;
-  const int bn = s2v_conv_tc_tile_n(cout);
+  int bn = s2v_conv_tc_tile_n(cout);
+  {
+    // Tiny feature maps (<= 64 output pixels per image: the 8 x 8 level of DNet's hourglass, MappingNet, the tail of the audio
+    // encoder, the AdaIN / style MLPs): even at batch 64 there are only a few M tiles, and with one wide N tile only that many
+    // CTAs run and EACH streams the whole weight matrix through its own L2 port (1.2 MB for a 3x3 256 -> 256 layer: ~20 us for
+    // ~1 us of MMAs).  N tiles of 64 spread the weight stream over 2-4 x more SMs (decoder4 phase convs 24 -> 12 us, MappingNet
+    // 25 -> 13 us).  The rule depends on the LAYER geometry only, never on the batch: the tile shape a frame is computed with must
+    // not change with the batch it sits in (sharded == unsharded bit for bit).  Not with LayerNorm2d totals (one thread sums a
+    // tile's channels) or the narrow hint (both need a single N tile).
+    static const int split_env = [] { const char* e = getenv("S2V_SPLIT_N"); return e ? atoi(e) : 1; }();      // development knob
+    const bool single_only = (d->stats_partial && d->stats_gmax == 0) || d->narrow_cout > 0;
+    if (split_env && !single_only && OH * OW <= 64 && cout >= 128 && cout % 64 == 0) bn = 64;
+  }
   p.bn = bn;
   // two accumulator buffers (epilogue of tile j overlaps the main loop of tile j+1)
   p.tmem_buf_cols = bn <= 16 ? 16 : bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
