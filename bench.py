@@ -5,7 +5,7 @@
 
 The metric is BASELINE.json's: generated frames/s of the FULL per-frame path (mel -> DNet 256x256 -> glue -> LNet 96x96).
 A step = one pass over BASELINE.json configs[3]: a 60 s synthetic clip (960 000 samples -> 4 801 STFT columns -> 1 497
-frames, 25 fps), DNet in batches of <= 64, LNet in batches of <= 256 (`pipeline.LipSyncPipeline`).
+frames, 25 fps), DNet in batches of <= 192, LNet in batches of <= 256 (`pipeline.LipSyncPipeline`).
 
 * `value`: whole-job frames/s with the clip's inputs (wav, 256x256 sources, 3DMM windows) resident in HBM.  N > 1 (torchrun):
   STRONG scaling - the same clip is frame-sharded (`parallel.shard_range`: rank r owns a contiguous frame range, full weight
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=60.0, help="clip length (60 = configs[3], 600 = configs[4])")
     ap.add_argument("--lnet-batch", type=int, default=256)
-    ap.add_argument("--dnet-batch", type=int, default=64)
+    ap.add_argument("--dnet-batch", type=int, default=192)
     ap.add_argument("--ref-frames", type=int, default=2)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -65,9 +65,10 @@ class LipSyncPipeline:
     end-to-end number uses.
     Batch caps (measured on B200, 600 s clip on 8 GPUs, gather timed): LNet 64 / 128 / 256 / 512 -> 27.5 / 29.4 / 29.8 / 29.7 k
     frames/s; a rank of the 60 s clip at N = 8 owns 188 frames: one batch of 192 instead of 128 + 64 is 29.3 k vs 28.0 k frames/s.
-    DNet's per-frame time is flat from 64 to 256 frames per batch, so it stays at BASELINE.json's 64."""
+    DNet (1.3 ms fixed + 125 us per frame): caps 64 / 128 / 192 -> 3 790 / 3 851 / 3 876 frames/s on the 60 s clip at N = 1
+    (plan workspaces 9.7 / 19.5 / 29 GB); 192 also makes a rank's 188 frames at N = 8 a single DNet batch."""
 
-    def __init__(self, lnet, dnet, lnet_batch: int = 256, dnet_batch: int = 64, fps: float = 25.0, overlap: bool | None = None):
+    def __init__(self, lnet, dnet, lnet_batch: int = 256, dnet_batch: int = 192, fps: float = 25.0, overlap: bool | None = None):
         self.lnet, self.dnet, self.lb, self.db, self.fps = lnet, dnet, lnet_batch, dnet_batch, fps
         self.overlap = (os.environ.get("S2V_PIPE_OVERLAP", "1") == "1") if overlap is None else overlap
         self._stage = {}

@@ -115,8 +115,8 @@ def test_stream_batches_matches_direct_forward():
 
 def test_clip_batch_structure_vs_oracle_sample():
     """The benchmarked configuration: the 60 s clip of BASELINE.json configs[3] (1 497 frames) through LipSyncPipeline with
-    its real batch structure (24 DNet batches of 63 / 62 on the B=64 plan, 12 LNet batches of 125 / 124 on the B=128 plan,
-    DNet and LNet overlapped on two streams), checked on a strided sample of frames against the oracle chain (fp32, TF32
+    its real batch structure (DNet 7 x 192 + a tail of 153 on the B=160 plan, LNet 5 x 256 + a tail of 217 on the B=224 plan,
+    DNet and LNet on two streams), checked on a strided sample of frames against the oracle chain (fp32, TF32
     off); overlapped == single-stream bit-for-bit; rank 3 of 8 == its slice of the unsharded run."""
     import gpu_util as G
     from oracle import mel as omel, nets, synth, weights
@@ -147,8 +147,9 @@ def test_clip_batch_structure_vs_oracle_sample():
         out_h = torch.empty(n, 3, 96, 96).pin_memory()
         f2 = pipe.run(torch.from_numpy(wav_np).pin_memory(), src.cpu().pin_memory(), coeff.cpu().pin_memory(), out_host=out_h)
         assert torch.equal(f2, frames) and torch.equal(out_h, frames.cpu())
-        # strided sample (covers first / last frames, batch seams 62|63, 124|125 and the tail window) vs the oracle chain
-        sample = sorted(set(list(range(0, n, 97)) + [61, 62, 63, 124, 125, 126, n - 2, n - 1]))
+        # strided sample (covers first / last frames, the batch seams 191|192, 255|256, the tail batches from 1344 / 1280 and the
+        # tail mel window) vs the oracle chain
+        sample = sorted(set(list(range(0, n, 97)) + [63, 64, 191, 192, 255, 256, 1279, 1280, 1343, 1344, n - 2, n - 1]))
         sidx = torch.tensor(sample)
         win = torch.from_numpy(omel.mel_windows(omel.melspectrogram(wav_np)))[sidx].cuda()
         sdd, sdl = {k: v.cuda() for k, v in sd_d.items()}, {k: v.cuda() for k, v in sd_l.items()}
