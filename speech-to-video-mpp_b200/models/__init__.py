@@ -13,13 +13,17 @@ def _load(checkpoint_path):
 def load_checkpoint(path, model):
     print("Load checkpoint from: {}".format(path))
     checkpoint = _load(path)
-    s = checkpoint["state_dict"] if "arcface" not in path else checkpoint
-    new_s = {}
-    for k, v in s.items():
-        if "low_res" in k:
-            continue
-        new_s[k.replace("module.", "")] = v
-    model.load_state_dict(new_s, strict=False)
+    try:
+        s = checkpoint["state_dict"] if "arcface" not in path else checkpoint
+        new_s = {}
+        for k, v in s.items():
+            if "low_res" in k:
+                continue
+            new_s[k.replace("module.", "")] = v
+        model.load_state_dict(new_s, strict=False)
+    except (KeyError, AttributeError, TypeError, RuntimeError):
+        # the reference's fallback (models/__init__.py:24-26, a bare ``except``): the file holds a plain state_dict
+        model.load_state_dict(checkpoint)
     return model
 
 

@@ -145,3 +145,56 @@ def test_convT_and_up2_phase_weights_match_torch():
     for (p, q), w4 in up2_phase_weights(w3).items():
         out[:, :, p::2, q::2] = F.conv2d(F.pad(x, (1 - q, q, 1 - p, p)), w4)
     assert (out - ref).abs().max() < 1e-12
+
+
+def test_enet_module_schema_and_loaders(tmp_path):
+    """models.ENet keeps the reference's 1 785-tensor schema (low_res.* first); load_checkpoint strips `module.`, skips `low_res`
+    keys and falls back to a plain state_dict file (models/__init__.py:12-27); load_network wires LNet into ENet (:29-35)."""
+    import types
+    from s2v_b200 import models
+    from s2v_b200.models.ENet import ENet
+    from s2v_b200.models.LNet import LNet
+    with open(os.path.join(GOLDEN, "enet_schema.json")) as f:
+        own = json.load(f)
+    with open(os.path.join(GOLDEN, "lnet_schema.json")) as f:
+        lnet_schema = json.load(f)
+    net = ENet(lnet=LNet())
+    sd = net.state_dict()
+    assert list(sd)[:len(lnet_schema)] == ["low_res." + k for k in lnet_schema]
+    assert list(sd)[len(lnet_schema):] == list(own) and all(list(sd[k].shape) == own[k] for k in own)
+    with pytest.raises(L.S2VError):
+        ENet(lnet=LNet(), concat=True)
+    with pytest.raises(TypeError):
+        ENet()
+    # checkpoints: wrapped ({"state_dict": {"module.x": ...}}) and plain
+    lsd = {k: torch.randn_like(v) if v.is_floating_point() else v for k, v in LNet().state_dict().items()}
+    torch.save({"state_dict": {"module." + k: v for k, v in lsd.items()}}, tmp_path / "l.pth")
+    esd = {k: torch.randn_like(v) for k, v in sd.items() if not k.startswith("low_res.")}
+    stale = {"module.low_res." + k: torch.zeros_like(v) for k, v in lsd.items()}
+    torch.save({"state_dict": {**stale, **{"module." + k: v for k, v in esd.items()}}}, tmp_path / "e.pth")
+    model = models.load_network(types.SimpleNamespace(LNet_path=str(tmp_path / "l.pth"), ENet_path=str(tmp_path / "e.pth")))
+    got = model.state_dict()
+    assert not model.training
+    assert all(torch.equal(got["low_res." + k], lsd[k]) for k in lsd) and all(torch.equal(got[k], esd[k]) for k in esd)
+    torch.save(lsd, tmp_path / "plain.pth")                       # the reference's fallback branch: a bare state_dict
+    l2 = models.load_checkpoint(str(tmp_path / "plain.pth"), LNet())
+    assert all(torch.equal(l2.state_dict()[k], lsd[k]) for k in lsd)
+    with pytest.raises(L.S2VError):                               # CPU module: no fallback
+        model(torch.zeros(1, 1, 80, 16), torch.zeros(1, 6, 96, 96), torch.zeros(1, 3, 96, 96))
+
+
+def test_pipeline_batches_and_plan_cache_bound():
+    from s2v_b200.pipeline import balanced_batches
+    assert balanced_batches(1497, 256) == [256] * 5 + [217] and balanced_batches(188, 192) == [188]
+    assert balanced_batches(0, 64) == [] and balanced_batches(64, 64) == [64] and sum(balanced_batches(14997, 192)) == 14997
+    # the per-engine plan cache is an LRU bounded by count (and bytes): plans built on a CPU "device" only validate shapes
+    from oracle import weights
+    from s2v_b200.models.LNet import LNetEngine
+    eng = LNetEngine(weights.make_state_dict("lnet", 0), torch.device("cpu"))
+    eng.max_plans = 2
+    for b in (8, 16, 24):
+        eng.plan_for(b)
+    info = eng.plan_cache_info()
+    assert info["plans"] == 2 and info["keys"] == [16, 24] and info["bytes"] > 0
+    eng.plan_for(16)
+    assert eng.plan_cache_info()["keys"] == [24, 16]              # a hit moves the plan to the young end
