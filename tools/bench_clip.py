@@ -25,7 +25,8 @@ if ROOT not in sys.path:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--batches", default="128", help="LNet batch sizes to sweep (DNet batch = min(batch, 64))")
+    ap.add_argument("--batches", default="256", help="LNet batch caps to sweep")
+    ap.add_argument("--dnet-batch", type=int, default=192, help="DNet batch cap")
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
 
@@ -67,7 +68,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     for b in [int(x) for x in args.batches.split(",")]:
-        pipe = LipSyncPipeline(lnet, dnet, lnet_batch=b, dnet_batch=min(b, 64))
+        pipe = LipSyncPipeline(lnet, dnet, lnet_batch=b, dnet_batch=min(b, args.dnet_batch))
 
         def step():
             frames = pipe.run(wav, srcs, coeffs, rank, world)
@@ -89,7 +90,7 @@ def main():
         if rank == 0:
             ms = t.item()
             print(json.dumps({"workload": "mel -> DNet -> glue -> LNet on a %.0f s synthetic clip (%d frames), frame-sharded, final all_gather timed" % (args.seconds, total),
-                              "n_gpus": world, "frames": total, "frames_per_rank": n, "lnet_batch": b, "dnet_batch": min(b, 64),
+                              "n_gpus": world, "frames": total, "frames_per_rank": n, "lnet_batch": b, "dnet_batch": min(b, args.dnet_batch),
                               "ms": round(ms, 2), "frames_per_s": round(total / ms * 1e3, 1),
                               "gather_bytes": int(total * 3 * 96 * 96 * 4), "reps": args.reps,
                               "checksum": float(out.double().sum().item())}), flush=True)
