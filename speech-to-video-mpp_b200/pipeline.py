@@ -71,6 +71,7 @@ class LipSyncPipeline:
     def __init__(self, lnet, dnet, lnet_batch: int = 256, dnet_batch: int = 192, fps: float = 25.0, overlap: bool | None = None):
         self.lnet, self.dnet, self.lb, self.db, self.fps = lnet, dnet, lnet_batch, dnet_batch, fps
         self.overlap = (os.environ.get("S2V_PIPE_OVERLAP", "1") == "1") if overlap is None else overlap
+        self.host_first = int(os.environ.get("S2V_HOST_FIRST", "48"))      # frames of the first DNet batch when the inputs are on the host
         self._stage = {}
 
     def n_frames(self, n_samples: int) -> int:
@@ -117,6 +118,10 @@ class LipSyncPipeline:
         deng, leng = self.dnet.engine(), self.lnet.engine()
         # ---- DNet batches (stream s_d), host inputs staged one batch ahead on s_in -----------------------------------------
         d_sizes, l_sizes = balanced_batches(n, self.db), balanced_batches(n, self.lb)
+        if host_in and n > 2 * self.host_first:
+            # host inputs: nothing can run before the first batch's sources have crossed PCIe (0.79 MB per frame), so the first
+            # DNet batch is small; every later batch's copy hides behind the previous batch's forward
+            d_sizes = [self.host_first] + balanced_batches(n - self.host_first, self.db)
         d_done = []                                     # (last frame + 1, event) per DNet batch
         pos = 0
         staged = None
