@@ -16,6 +16,8 @@ Layer mapping (reference file:line -> kernel):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -44,10 +46,30 @@ def convT_phase_weights(w):
 _IO_OF = {"flow_field": "flow", "warp_image": "warp", "fake_image": "fake"}
 
 
+def s2d_weights(w, p):
+    """4x4 stride-2 pad-1 conv [Cout,Cin,4,4] as a stride-1 conv on the row-phase-p view of its input.
+
+    The channels-last input [H,W,Cin] IS, without moving a byte, two tensors Z_p[H/2, W/2, 2*Cin] (row phase p = 0 / 1: base
+    offset p*W*Cin, row stride 2*W*Cin, pixel stride 2*Cin, channels = (column phase q, c)).  Input row 2Y-1+ky is row
+    Y + (ky - 1 - p) / 2 of Z_p for the two ky of that phase, input column 2X-1+kx is column X + dX of column phase q with
+    (dX, q) = (-1, 1), (0, 0), (0, 1), (+1, 0) for kx = 0..3.  So   out = conv_{2x3}(Z_0; pad (0,1)) + conv_{2x3}(Z_1; pad (1,1))
+    with the weights below (zero where a (dX, q) pair does not occur): two unit-stride K segments that the conv kernel serves from
+    ONE halo patch each instead of 16 strided tap loads per tile (TMA element strides fetch every skipped pixel as well)."""
+    co, ci = w.shape[:2]
+    out = torch.zeros(co, 2 * ci, 2, 3, dtype=w.dtype, device=w.device)
+    ky_of = {0: (1, 3), 1: (0, 2)}[p]                     # tap t = 0, 1 of the phase
+    kx_of = {(0, 1): 0, (1, 0): 1, (1, 1): 2, (2, 0): 3}  # (column tap u = dX + 1, column phase q) -> kx
+    for t, ky in enumerate(ky_of):
+        for (u, q), kx in kx_of.items():
+            out[:, q * ci:(q + 1) * ci, t, u] = w[:, :, ky, kx]
+    return out
+
+
 class DNetEngine(EngineBase):
     def __init__(self, sd, device, conv_impl="tc", use_graph=True):
         super().__init__(device, conv_impl, use_graph)
         assert conv_impl == "tc", "DNet engine is built on the tcgen05 conv path"
+        self.s2d = {int(v) for v in os.environ.get("S2V_S2D", "0").split(",") if v != ""}   # encoder levels on the s2d-view conv
         sd = {k: v.detach().to(self.fold_dev) for k, v in sd.items()}
         self._pack(sd)
         self.finish_pack()
@@ -72,6 +94,9 @@ class DNetEngine(EngineBase):
             cin, cout = min(ngf * 2 ** i, img_f), min(ngf * 2 ** (i + 1), img_f)
             p = f"{h}.encoder.encoder{i}"
             self.pack_conv(p + ".conv_0", sd[p + ".conv_0.weight"].float(), sd[p + ".conv_0.bias"])
+            if i in self.s2d:
+                e = self.pack_conv(p + ".conv_0.s2d", s2d_weights(sd[p + ".conv_0.weight"].float(), 0), sd[p + ".conv_0.bias"])
+                e["w"] = torch.cat([e["w"], ops.pack_w_tc(s2d_weights(sd[p + ".conv_0.weight"].float(), 1))], 1).contiguous()
             self.pack_conv(p + ".conv_1", sd[p + ".conv_1.weight"].float(), sd[p + ".conv_1.bias"])
             reg_adain(p + ".norm_0", cin)
             reg_adain(p + ".norm_1", cout)
@@ -186,7 +211,15 @@ class DNetEngine(EngineBase):
                 xa = buf(p + ".a0", (B, s, s, cin))
                 adain(p + ".norm_0", x, xa, stats=st_x)
                 y0 = buf(p + ".y0", (B, s // 2, s // 2, cout))
-                st = self.conv_stats(plan, ws, p + ".conv_0", xa, y0, stride=(2, 2), pad=(1, 1), fin=adain_fin(p + ".norm_1"))
+                if i in self.s2d:
+                    # 4x4 stride-2 conv as two unit-stride 2x3 K segments on the row-phase views of xa (see s2d_weights)
+                    z = [torch.as_strided(xa, (B, s // 2, s // 2, 2 * cin), (xa.stride(0), 2 * s * cin, 2 * cin, 1),
+                                          xa.storage_offset() + ph * s * cin) for ph in (0, 1)]
+                    st = self.conv_stats(plan, ws, p + ".conv_0.s2d", z[0], y0, tag=p + ".conv_0", k=(2, 3), pad=(0, 1), x2=z[1], k2=(2, 3),
+                                         pad2=(1, 1), fin=adain_fin(p + ".norm_1"),
+                                         alg_flops=2.0 * B * (s // 2) * (s // 2) * cout * 16 * cin)
+                else:
+                    st = self.conv_stats(plan, ws, p + ".conv_0", xa, y0, stride=(2, 2), pad=(1, 1), fin=adain_fin(p + ".norm_1"))
                 ya = buf(p + ".a1", (B, s // 2, s // 2, cout))
                 adain(p + ".norm_1", y0, ya, stats=st)
                 y1 = enc_out.get(i) if i in enc_out else buf(p + ".y1", (B, s // 2, s // 2, cout))
