@@ -5,18 +5,21 @@
 // As a plain implicit GEMM these layers are N = 16 wide and need 49 taps x 4 K-steps = 196 tcgen05.mma per 128-pixel tile
 // and 64-channel chunk - and one MMA costs ~60 cycles whatever N <= 128 is (tools/mb_umma.cu), i.e. 46-76 TFLOP/s.
 // Here the kx taps are FOLDED INTO N:
-//     P[pos, (kx, co)] = sum over ky, ci of  X[pos + ky * PW, ci] * W[co, ky, kx, ci]          (N = 7 * 8 = 56 -> 64)
+//     P[pos, (kx, co)] = sum over ky, ci of  X[pos + ky * PW, ci] * W[co, ky, kx, ci]          (N = 7 * CP, CP = Cout padded to 2 / 4 / 8)
 //     out[y, x, co]    = bias[co] + sum over kx of  P[y * PW + x + kx, (kx, co)]
 // where pos runs over the positions of a PW = 32 pixel wide input patch (row-major).  The M tile is 128 CONSECUTIVE patch
 // positions (4 patch rows), so the A operand of row tap ky is simply the K-major tile that starts ky * PW rows further
 // down the same TMA-loaded patch (10 rows x 32 pixels x 64 channels, zero fill = zero padding): 7 x 4 = 28 MMAs per tile
 // and chunk instead of 196.  A tile yields 4 rows x 26 output pixels (104 of 128 accumulator rows are useful).  The
-// epilogue parks the 128 x 56 fp32 accumulator in shared memory (column-major, conflict-free both ways) and every thread
+// epilogue parks the 128 x (7 CP) fp32 accumulator in shared memory (column-major, conflict-free both ways) and every thread
 // gathers the 7 shifted partial sums of its output pixel.
 //
 // Roles: warp 0 = TMA producer (patch slots + weight tiles), warp 1 = TMEM allocation + MMA issue, warps 2-9 = two
-// epilogue groups (group g drains accumulator buffer g = the tiles j = g, g+2, ... of this CTA); persistent over tiles.  Weights stay resident in smem when Cin = 64 (56 KB),
-// otherwise they stream through an 8-deep ring.
+// epilogue groups (group g drains accumulator buffer g = the tiles j = g, g+2, ... of this CTA); persistent over tiles.
+// The weight tile of one (chunk, ky) is [N = 7 CP -> 16 / 32 / 64 rows][64 channels]: 2 / 4 / 8 KB.  With the channel pad matched to
+// Cout the weights of every head of the nets stay RESIDENT in smem (FinalBlock2d, Cin 64, Cout 3: 28 KB; flow_out, Cin 256, Cout 2:
+// 56 KB - at a fixed pad of 8 flow_out's 224 KB had to stream through a ring, 896 KB of L2 -> smem traffic per tile, and that
+// stream, not the MMAs, bounded the launch); a layer whose weights do not fit still streams them through an 8-deep ring.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,9 +33,10 @@ constexpr int kK = 7, kPW = 32, kRows = 4, kOW = kPW - (kK - 1);   // 26 output 
 // resident (Cin = 64: the FinalBlock2d heads); the streaming-weights head (flow_out, Cin = 256) keeps SUB = 1.
 __host__ __device__ constexpr int patch_rows(int sub) { return sub * kRows + kK - 1; }
 __host__ __device__ constexpr int patch_bytes(int sub) { return kPW * patch_rows(sub) * 128; }
-constexpr int kBTile = 64 * 128;                         // 8 KB: (kx, co) x 64 channels of one (chunk, ky)
+__host__ __device__ constexpr int n_rows(int cp) { return cp == 8 ? 64 : cp == 4 ? 32 : 16; }   // MMA N: 7 * cp rounded up to 16
+__host__ __device__ constexpr int b_tile(int cp) { return n_rows(cp) * 128; }                  // (kx, co) x 64 channels of one (chunk, ky)
+__host__ __device__ constexpr int stage_bytes(int cp) { return 7 * cp * 128 * 4; }             // fp32 accumulator parked column-major, per epilogue group
 constexpr int kASlots = 2, kBRing = 8, kThreads = 320;   // producer, MMA, 2 x 4 epilogue warps (the epilogue is the longer stage)
-constexpr int kStageBytes = 56 * 128 * 4;               // fp32 accumulator parked column-major, one buffer per epilogue group
 constexpr unsigned kSpin = 1u << 26;
 
 struct Params {
@@ -97,10 +101,11 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& n, i
   x0 = (t - ty * p.tiles_x) * kOW;
 }
 
-template <int SUB>
+template <int SUB, int CP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   constexpr int kPatchBytes = patch_bytes(SUB);
+  constexpr int kNB = n_rows(CP), kBTile = b_tile(CP), kStageBytes = stage_bytes(CP), kCols = 7 * CP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_trigger();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -161,8 +166,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issue: D[128 positions, 64] (fp32, TMEM) += A(ky)[128, 64] * W(chunk, ky)[64, 64] =====
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // ===== MMA issue: D[128 positions, kNB] (fp32, TMEM) += A(ky)[128, 64] * W(chunk, ky)[kNB, 64] =====
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       if (p.b_resident) { mbar_wait(ball, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
       uint32_t a = 0, aph = 0, s = 0, sph = 0;
       int j = 0;
@@ -226,22 +231,23 @@ conv_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull + 8u * buf, SUB == 1 ? ((uint32_t)jj & 1u) : (((uint32_t)jj >> 1) & 1u));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (64u * SUB) + (SUB == 2 ? 64u * grp : 0u);
-      float v[64];
-      tmem_ld16(trow, v); tmem_ld16(trow + 16u, v + 16); tmem_ld16(trow + 32u, v + 32); tmem_ld16(trow + 48u, v + 48);
+      float v[kNB];
+#pragma unroll
+      for (int i = 0; i < kNB; i += 16) tmem_ld16(trow + (uint32_t)i, v + i);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8u * buf) : "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the previous tile's gathers are done with the staging buffer
 #pragma unroll
-      for (int i = 0; i < 56; ++i) stage[i * 128 + pos] = v[i];
+      for (int i = 0; i < kCols; ++i) stage[i * 128 + pos] = v[i];
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       const int Y = y0 + oy, X = x0 + ox;
       if (ox < kOW && Y < p.H && X < p.W) {
         for (int co = 0; co < p.cout; ++co) {
           float acc = p.bias ? p.bias[co] : 0.f;
 #pragma unroll
-          for (int kx = 0; kx < kK; ++kx) acc += stage[(kx * 8 + co) * 128 + et + kx];
+          for (int kx = 0; kx < kK; ++kx) acc += stage[(kx * CP + co) * 128 + et + kx];
           if (p.act == S2V_ACT_SIGMOID) acc = 1.f / (1.f + __expf(-acc));
           else if (p.act == S2V_ACT_TANH) acc = tanhf(acc);
           else if (p.act == S2V_ACT_RELU) acc = fmaxf(acc, 0.f);
@@ -281,8 +287,9 @@ using namespace s2v;
 using namespace s2v::head;
 
 // d: x fp16 NHWC (C a multiple of 64), kh = kw = 7, stride 1, pad 3, out_mode F32_NCHW with y_f32 [N][Cout][H][W], Cout <= 8,
-// bias optional, act NONE / RELU / LRELU / SIGMOID / TANH.  d->w: fp16 [64][chunks * 7 * 64]: row kx * 8 + co,
-// column (chunk * 7 + ky) * 64 + ci  (ops.pack_w_head); rows 56..63 and co >= Cout are zero.
+// bias optional, act NONE / RELU / LRELU / SIGMOID / TANH.  d->w: fp16 [NB][chunks * 7 * 64] with CP = 2 / 4 / 8 the smallest pad
+// >= Cout and NB = 16 / 32 / 64: row kx * CP + co, column (chunk * 7 + ky) * 64 + ci  (ops.pack_w_head); rows >= 7 CP and
+// co >= Cout are zero.
 extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   if (!d || !view_ok(&d->x) || !d->w || !d->y_f32) return S2V_EINVAL;
   if (d->kh != kK || d->kw != kK || d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1 || d->pad_h != kK / 2 ||
@@ -298,7 +305,9 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   p.N = N; p.H = H; p.W = W; p.cout = cout; p.chunks = d->x.c / 64;
   // two stacked M tiles per patch when the weights of the single chunk stay resident next to two 14-row patches (Cin = 64)
   static const int sub_env = [] { const char* e = getenv("S2V_HEAD_SUB"); return e ? atoi(e) : 2; }();      // development knob
-  const int fixed = 2 * kStageBytes + 256 + 1024;
+  const int cp = cout <= 2 ? 2 : cout <= 4 ? 4 : 8;
+  const int kBTile = b_tile(cp);
+  const int fixed = 2 * stage_bytes(cp) + 256 + 1024;
   const int sub = (sub_env == 2 && (long long)p.chunks * kK * kBTile + kASlots * patch_bytes(2) + fixed <= 227 * 1024) ? 2 : 1;
   p.rows_per_tile = sub * kRows;
   p.tiles_x = ceil_div(W, kOW); p.tiles_y = ceil_div(H, p.rows_per_tile);
@@ -321,9 +330,9 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   }
   {
     const cuuint64_t ktot = (cuuint64_t)p.chunks * kK * 64;
-    cuuint64_t gdim[2] = {ktot, 64};
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)n_rows(cp)};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, (cuuint32_t)n_rows(cp)};
     cuuint32_t es[2] = {1, 1};
     if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -332,17 +341,19 @@ extern "C" int s2v_conv_head(const s2v_conv* d, void* stream) {
   static DeviceOnce attr;     // per device, idempotent
   const int dev = current_device();
   if (dev < 0) return S2V_ECUDA;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+  static const KernelFn kernels[2][3] = {{conv_head_kernel<1, 2>, conv_head_kernel<1, 4>, conv_head_kernel<1, 8>},
+                                         {conv_head_kernel<2, 2>, conv_head_kernel<2, 4>, conv_head_kernel<2, 8>}};
   if (attr.needed(dev)) {
-    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    S2V_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 3; ++k) S2V_CUDA_TRY(cudaFuncSetAttribute(kernels[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr.mark(dev);
   }
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
   if (smem > 227 * 1024) return S2V_EINVAL;
-  if (sub == 2) S2V_CUDA_TRY(launch_pdl(conv_head_kernel<2>, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
-  else S2V_CUDA_TRY(launch_pdl(conv_head_kernel<1>, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
+  S2V_CUDA_TRY(launch_pdl(kernels[sub - 1][cp == 2 ? 0 : cp == 4 ? 1 : 2], grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, p));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -448,15 +448,22 @@ def pack_w_tc(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(co8, kh * kw * ci64).contiguous()
 
 
+def head_co_pad(cout: int) -> int:
+    """Channel pad of the folded-tap head GEMM (csrc/conv_head.cu): the smallest of 2 / 4 / 8 that holds Cout."""
+    assert 0 < cout <= 8
+    return 2 if cout <= 2 else 4 if cout <= 4 else 8
+
+
 def pack_w_head(w: torch.Tensor) -> torch.Tensor:
-    """7x7 head conv [Cout<=8, Cin, 7, 7] -> fp16 [64][chunks*7*64] for s2v_conv_head: row kx*8 + co, column
-    (chunk*7 + ky)*64 + ci (the kx taps are folded into the GEMM's N dimension)."""
+    """7x7 head conv [Cout<=8, Cin, 7, 7] -> fp16 [NB][chunks*7*64] for s2v_conv_head: row kx*CP + co, column
+    (chunk*7 + ky)*64 + ci (the kx taps are folded into the GEMM's N dimension; CP = head_co_pad(Cout), NB = 16 / 32 / 64 rows)."""
     co, ci, kh, kw = w.shape
     assert kh == 7 and kw == 7 and co <= 8 and ci % 64 == 0
-    chunks = ci // 64
-    out = torch.zeros(8, 8, chunks, 7, 64, dtype=torch.float16, device=w.device)          # [kx][co][chunk][ky][ci]
+    chunks, cp = ci // 64, head_co_pad(co)
+    nb = {2: 16, 4: 32, 8: 64}[cp]
+    out = torch.zeros(nb // cp, cp, chunks, 7, 64, dtype=torch.float16, device=w.device)      # [kx][co][chunk][ky][ci]
     out[:7, :co] = w.reshape(co, chunks, 64, 7, 7).permute(4, 0, 1, 3, 2).to(torch.float16)   # (kx, co, chunk, ky, ci)
-    return out.reshape(64, chunks * 7 * 64).contiguous()
+    return out.reshape(nb, chunks * 7 * 64).contiguous()
 
 
 def op_conv_head(lib, x, w, y_f32, *, bias=None, act=L.ACT_NONE, act_param=0.0, name="head") -> Op:
@@ -474,7 +481,8 @@ def op_conv_head(lib, x, w, y_f32, *, bias=None, act=L.ACT_NONE, act_param=0.0, 
     d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
     d.pad_h = d.pad_w = 3
     d.act, d.act_param = act, float(act_param)
-    assert w.dtype == torch.float16 and tuple(w.shape) == (64, x.shape[3] // 64 * 7 * 64) and x.shape[3] % 64 == 0
+    nb = {2: 16, 4: 32, 8: 64}[head_co_pad(co)]
+    assert w.dtype == torch.float16 and tuple(w.shape) == (nb, x.shape[3] // 64 * 7 * 64) and x.shape[3] % 64 == 0
     op = Op(name + "[head]", lib.s2v_conv_head, (C.byref(d),), (d, x, w, y_f32, bias))
     op.alg_flops = 2.0 * n * oh * ow * co * 49 * x.shape[3]
     op.io_bytes = 2.0 * x.numel() + 2.0 * w.numel() + 4.0 * y_f32.numel()

@@ -245,15 +245,17 @@ def test_conv_head_7x7_folded_taps(G):
     lib, L, ops = G.lib(), G.L, G.ops
     torch.manual_seed(31)
     for (n, h, w_, cin, cout, act) in ((3, 96, 96, 64, 3, L.ACT_SIGMOID), (2, 64, 64, 256, 2, L.ACT_NONE),
-                                       (2, 50, 37, 64, 3, L.ACT_TANH), (1, 8, 8, 128, 8, L.ACT_NONE)):
+                                       (2, 50, 37, 64, 3, L.ACT_TANH), (1, 8, 8, 128, 8, L.ACT_NONE), (2, 33, 70, 64, 1, L.ACT_RELU),
+                                       (1, 40, 27, 128, 5, L.ACT_LRELU), (2, 64, 64, 64, 4, L.ACT_NONE)):
         x = torch.randn(n, h, w_, cin, device="cuda").half()
         wt = torch.randn(cout, cin, 7, 7, device="cuda") / (cin * 49) ** 0.5
         b = torch.randn(cout, device="cuda")
         y = torch.full((n, cout, h, w_), float("nan"), device="cuda")
-        ops.op_conv_head(lib, x, ops.pack_w_head(wt), y, bias=b, act=act).run()
+        ops.op_conv_head(lib, x, ops.pack_w_head(wt), y, bias=b, act=act, act_param=0.1).run()
         torch.cuda.synchronize()
         ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.half().float(), b, padding=3)
-        ref = torch.sigmoid(ref) if act == L.ACT_SIGMOID else torch.tanh(ref) if act == L.ACT_TANH else ref
+        ref = {L.ACT_SIGMOID: torch.sigmoid, L.ACT_TANH: torch.tanh, L.ACT_RELU: torch.relu,
+               L.ACT_LRELU: lambda t: F.leaky_relu(t, 0.1), L.ACT_NONE: lambda t: t}[act](ref)
         m, rel = G.report("conv_head %dx%d cin%d cout%d" % (h, w_, cin, cout), y, ref)
         assert rel < 2e-3, (h, w_, cin, cout, rel)
 
