@@ -297,7 +297,8 @@ int s2v_conv_tc_tile_n(int cout);
  * models/DNet.py:72-76) on tcgen05 with the kx taps folded into the GEMM's N dimension (7x fewer MMAs than
  * s2v_conv_tc).  d->x: fp16 NHWC, C a multiple of 64; d->out_mode = S2V_OUT_F32_NCHW, d->y = {n, h, w, c = Cout} shape
  * only, d->y_f32 [N][Cout][H][W]; bias optional; act NONE / RELU / LRELU / SIGMOID / TANH.
- * d->w: fp16 [64][chunks*7*64]: row kx*8 + co, column (chunk*7 + ky)*64 + ci; rows 56..63 and co >= Cout zero.   */
+ * d->w: fp16 [NB][chunks*7*64] with CP = 2 / 4 / 8 the smallest pad >= Cout and NB = 16 / 32 / 64 rows: row kx*CP + co,
+ * column (chunk*7 + ky)*64 + ci; rows >= 7*CP and co >= Cout zero.                                               */
 int s2v_conv_head(const s2v_conv* d, void* stream);
 
 /* grouped small linears (all AdaIN gamma/beta heads of a net in one launch,
@@ -378,6 +379,36 @@ int s2v_attention(const s2v_view* q, const s2v_view* k, const s2v_view* v, const
 /* MappingNet tail: AdaptiveAvgPool1d(1) over L (models/DNet.py:53)
  * x [N,1,L,C] -> y [N,1,1,C]                                                    */
 int s2v_mean_over_w(const s2v_view* x, const s2v_view* y, void* stream);
+
+/* ------------------------------------------------------ whole networks ---
+ * LNet.forward (models/LNet.py:122-139) and DNet.forward (models/DNet.py:20-28) for hosts without Python.
+ * The layer plan of a network at ONE batch size (the ordered list of launcher calls of this header, with the folded and
+ * packed weights) is written once by the Python package (s2v_b200.plan_export.export_lnet / export_dnet) into a
+ * relocatable plan file; the functions below load it on the host, bind it to two caller-owned device buffers and replay
+ * it on a stream.  Nothing is allocated on the device and nothing synchronises (s2v_plan_bind's constant upload is a
+ * pageable-memory copy and therefore host-synchronous).  One plan object = one in-flight forward at a time (its workspace
+ * holds the activations); use one plan per stream for concurrent forwards.
+ *   const_dev      s2v_plan_const_bytes() bytes, 256-byte aligned: weights / epilogue vectors / pointer tables
+ *   workspace_dev  s2v_plan_workspace_bytes() bytes, 256-byte aligned: activations, statistics and the I/O slots
+ * I/O slots live inside the workspace (s2v_plan_io_info: name, byte offset, size): "mel" [B,1,80,16], "face" [B,6,96,96],
+ * "out" [B,3,96,96] for LNet; "img" [B,3,256,256], "coeff" [B,73,1,T], "flow" [B,2,64,64], "warp" / "fake" [B,3,256,256]
+ * for DNet - all float32, contiguous, B = the batch the plan was exported for (pad smaller batches with zeros: frames
+ * are independent).  s2v_lnet_forward / s2v_dnet_forward copy device buffers into / out of the slots around
+ * s2v_plan_run; output pointers of s2v_dnet_forward may be NULL.                                                  */
+typedef struct s2v_plan s2v_plan;
+int s2v_plan_load(const char* path_host, s2v_plan** out);
+int s2v_plan_load_memory(const void* data_host, int64_t bytes, s2v_plan** out);
+void s2v_plan_free(s2v_plan* plan);
+int64_t s2v_plan_const_bytes(const s2v_plan* plan);
+int64_t s2v_plan_workspace_bytes(const s2v_plan* plan);
+int s2v_plan_num_ops(const s2v_plan* plan);
+int s2v_plan_num_io(const s2v_plan* plan);
+int s2v_plan_io_info(const s2v_plan* plan, int i, const char** name, int64_t* offset, int64_t* bytes, int* is_output);
+int s2v_plan_bind(s2v_plan* plan, void* const_dev, void* workspace_dev, void* stream);
+int s2v_plan_run(const s2v_plan* plan, void* stream);
+int s2v_lnet_forward(const s2v_plan* plan, const float* mel, const float* face, float* out, void* stream);
+int s2v_dnet_forward(const s2v_plan* plan, const float* input_image, const float* driving_source, float* flow_field,
+                     float* warp_image, float* fake_image, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,18 @@ _SIGNATURES = {
     "s2v_irfft2": (C.c_int, [VP, VP, VP, c_vp]),
     "s2v_attention": (C.c_int, [VP, VP, VP, VP, C.c_int, c_f32, c_vp]),
     "s2v_mean_over_w": (C.c_int, [VP, VP, c_vp]),
+    "s2v_plan_load": (C.c_int, [C.c_char_p, C.POINTER(c_vp)]),
+    "s2v_plan_load_memory": (C.c_int, [c_vp, c_i64, C.POINTER(c_vp)]),
+    "s2v_plan_free": (None, [c_vp]),
+    "s2v_plan_const_bytes": (c_i64, [c_vp]),
+    "s2v_plan_workspace_bytes": (c_i64, [c_vp]),
+    "s2v_plan_num_ops": (C.c_int, [c_vp]),
+    "s2v_plan_num_io": (C.c_int, [c_vp]),
+    "s2v_plan_io_info": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int)]),
+    "s2v_plan_bind": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "s2v_plan_run": (C.c_int, [c_vp, c_vp]),
+    "s2v_lnet_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "s2v_dnet_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

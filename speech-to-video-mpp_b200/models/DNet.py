@@ -162,6 +162,7 @@ class DNetEngine(EngineBase):
             ones = buf("const.ones", (B, 256), torch.float32)
             zeros = buf("const.zeros", (B, 256), torch.float32, zero=True)
             ones.fill_(1.0)
+            ones._s2v_init = ("fill", 1.0)
 
             # ---- MappingNet -> z [B,1,1,256] --------------------------------------------------------
             c80 = buf("map.in", (B, 1, T, 80))

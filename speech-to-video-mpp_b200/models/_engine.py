@@ -83,6 +83,8 @@ class EngineBase:
             assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, name
             return t
         t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
+        if zero:
+            t._s2v_init = ("zero", 0.0)          # plan_export: a region the plan expects initialised (padding borders, never-written rows)
         ws[name] = t
         return t
 

@@ -198,3 +198,51 @@ def test_pipeline_batches_and_plan_cache_bound():
     assert info["plans"] == 2 and info["keys"] == [16, 24] and info["bytes"] > 0
     eng.plan_for(16)
     assert eng.plan_cache_info()["keys"] == [24, 16]              # a hit moves the plan to the young end
+
+
+def _tiny_plan_bytes():
+    """A hand-written one-launch plan (s2v_add on three 8-channel views of the workspace): exercises the host-side parser
+    of csrc/plan.cu without a GPU."""
+    import ctypes as C
+    import struct
+    view = L.View(None, 1, 2, 2, 8, 32, 16, 8)
+    blob = bytes(view)
+    def arg_view(off):
+        return struct.pack("<II", 3, len(blob)) + blob + struct.pack("<II", 1, 0) + struct.pack("<IIQ", 0, 1, off)
+    op = struct.pack("<40sII", b"s2v_add", 3, 0) + arg_view(0) + arg_view(256) + arg_view(512)
+    io = struct.pack("<32sQQII", b"a", 0, 64, 0, 0) + struct.pack("<32sQQII", b"y", 512, 64, 1, 0)
+    init = struct.pack("<QQIf", 256, 64, 0, 0.0)
+    image = bytes(range(256))
+    head = b"S2VPLAN1" + struct.pack("<IIQQIIII", 1, 1, len(image), 768, 2, 1, 0, 0)
+    return head + io + init + op + image
+
+
+def test_plan_file_parser_host_side():
+    """s2v_plan_load_memory / s2v_plan_*: header, I/O table and op table of a plan file are parsed and bounds-checked on
+    the host; malformed files are rejected with S2V_EINVAL (never a crash)."""
+    import ctypes as C
+    lib = s2v_b200.load_library()
+    data = _tiny_plan_bytes()
+    h = C.c_void_p()
+    assert lib.s2v_plan_load_memory(data, len(data), C.byref(h)) == 0
+    assert lib.s2v_plan_num_ops(h) == 1 and lib.s2v_plan_num_io(h) == 2
+    assert lib.s2v_plan_const_bytes(h) == 256 and lib.s2v_plan_workspace_bytes(h) == 768
+    name, off, nb, out = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int()
+    assert lib.s2v_plan_io_info(h, 1, C.byref(name), C.byref(off), C.byref(nb), C.byref(out)) == 0
+    assert (name.value, off.value, nb.value, out.value) == (b"y", 512, 64, 1)
+    assert lib.s2v_plan_io_info(h, 2, None, None, None, None) == -1
+    assert lib.s2v_plan_run(h, None) == -1                       # not bound to device buffers yet
+    lib.s2v_plan_free(h)
+    bad = [b"", b"S2VPLAN0" + data[8:], data[:-1], data + b"\0", data[:100],
+           data.replace(b"s2v_add", b"s2v_xyz"),                 # unknown launcher
+           data[:16] + (1 << 40).to_bytes(8, "little") + data[24:]]          # constant image larger than the file
+    for b in bad:
+        h = C.c_void_p()
+        assert lib.s2v_plan_load_memory(b, len(b), C.byref(h)) == -1
+        assert not h.value
+    # a relocation that points outside its arena
+    i = data.index(struct_reloc := (512).to_bytes(8, "little"), 200)
+    broken = data[:i] + (1 << 30).to_bytes(8, "little") + data[i + 8:]
+    h = C.c_void_p()
+    assert lib.s2v_plan_load_memory(broken, len(broken), C.byref(h)) == -1
+    assert lib.s2v_plan_load(b"/nonexistent/plan.s2vplan", C.byref(h)) == -1
