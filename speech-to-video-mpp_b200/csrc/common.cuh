@@ -149,7 +149,16 @@ __device__ __forceinline__ H8 f_to_h8(const float* f) {
   return h;
 }
 __device__ __forceinline__ H8 ld_h8(const __half* p) { return *reinterpret_cast<const H8*>(p); }
-__device__ __forceinline__ void st_h8(__half* p, const H8& v) { *reinterpret_cast<H8*>(p) = v; }
+// one 128-bit store: a struct copy of H8 is emitted as four 32-bit stores when the destination is shared memory (the conv
+// epilogue's staging tile: 4-way bank-conflicted STS.32 instead of one conflict-free STS.128)
+__device__ __forceinline__ void st_h8(__half* p, const H8& v) {
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&v.v[0]);
+  u.y = *reinterpret_cast<const uint32_t*>(&v.v[1]);
+  u.z = *reinterpret_cast<const uint32_t*>(&v.v[2]);
+  u.w = *reinterpret_cast<const uint32_t*>(&v.v[3]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -32,6 +32,14 @@ constexpr int kThreads = 320;                        // TMA warp, MMA warp, 2 x 
 constexpr int kMaxASlots = 8;                        // A-patch slots in flight (small 1x1 patches need many to cover the load latency)
 constexpr unsigned kSpinLimit = 1u << 26;            // bounded waits: trap instead of hanging the GPU
 
+#ifdef S2V_EPI_PROF
+// development build only (tools/build_variant.py): per-phase clock sums of ONE epilogue thread (CTA 0, group 0, thread 0)
+__device__ unsigned long long g_epi_prof[16];
+#define EPI_T(i) if (prof_on) tprof[i] = clock64()
+#else
+#define EPI_T(i)
+#endif
+
 struct TcParams {
   int N, OH, OW;
   int box_w, box_h, box_n;
@@ -45,6 +53,7 @@ struct TcParams {
   int ki0, k2w, pad2_h, pad2_w, cin2_chunks, ki_total;   // second K segment (x2)
   // halo mode: one A patch (box + (k-1) halo) per 64-channel chunk serves every tap; B tiles stream per tap
   int halo, taps0, taps2, pw0, prows0, pw2, prows2, a_slots, a_slot_bytes, b_resident, pf_dist;
+  int a_slots2, a_slot2_bytes;                            // second A ring (segment-2 patches) behind the first; 0 = one shared ring
   float* stats;                                           // fused per-(image, tile, channel) sum / sumsq
   int st_c_off, st_c_total, st_chunk_off, st_chunks_total, st_groups, st_gmax;
   View y, r1, r2;
@@ -54,6 +63,7 @@ struct TcParams {
   float ap;
   int out_mode;
   float* yf;
+  int exp;                                                // development experiment bits (S2V_EXP): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no stats walk
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -207,6 +217,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, float ap) {
   if (ACT == S2V_ACT_RELU) return fmaxf(v, 0.f);
@@ -310,6 +334,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
     return sm.stage + (size_t)sb * (p.stage_out_bytes >> 2) + (size_t)panel * (kTileM * 64) + (size_t)row * 64 + ((chunk ^ (row & 7)) << 3);
   };
   auto load_tables = [&](int ntile) {
+    if (!affine) return;                             // identity tables are not even allocated (p.tab = 0)
     for (int i = et; i < p.bn; i += 128) {
       const int c = ntile * p.bn + i;
       s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
@@ -317,6 +342,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
     }
   };
   if (p.n_tiles_n == 1) { load_tables(0); asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
+#ifdef S2V_EPI_PROF
+  const bool prof_on = blockIdx.x == 0 && grp == 0 && et == 0;
+  long long tprof[8];
+#endif
+  const int lg_w = __ffs(p.box_w) - 1, lg_wh = lg_w + __ffs(p.box_h) - 1;    // box_w * box_h * box_n = 128: powers of two
   const int jstep = p.epi_groups;
   int j = grp;
   for (int tile = w_first + grp * w_step; tile < w_total; tile += jstep * w_step, j += jstep) {
@@ -330,10 +360,21 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
       load_tables(ntile);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
+    EPI_T(0);
     mbar_wait(sm.tfull0 + 8u * buf, ((uint32_t)j >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    EPI_T(1);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.tmem_buf_cols;
     float ln_s = 0.f, ln_q = 0.f;
+    if (p.exp & 1) {                                // experiment: drain nothing, just hand the accumulator back
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (C2) mbar_arrive_cluster(tempty_remote0 + 8u * buf);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.tempty0 + 8u * buf) : "memory");
+      }
+      continue;
+    }
     for (int pass0 = 0; pass0 < p.bn; pass0 += half_n) {
       const int pass_n = min(half_n, p.bn - pass0);
       if (!direct) {
@@ -345,6 +386,51 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         if (p.stats && pass0 == 0) s_valid[m] = valid ? 1 : 0;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
+      EPI_T(2);
+      // Fast path (fp16 staged output, whole 32-column groups, every channel valid): one 32-column TMEM load per iteration
+      // and straight-line code with the per-launch conditions hoisted, so that the 32 values are independent instruction
+      // streams - the generic loop below is a chain of small basic blocks (latency-bound with two epilogue warps per scheduler:
+      // measured ~600 clocks per 32 columns)
+      const bool fast_cols = !direct && (pass_n & 31) == 0 && ntile * p.bn + pass0 + pass_n <= p.cout && !(p.exp & 8);
+      if (fast_cols) {
+        __half* const row_base = sm.stage + (size_t)sb * (p.stage_out_bytes >> 2) + (size_t)m * 64;
+        const int r7 = m & 7;
+#pragma unroll 1
+        for (int cb = 0; cb < pass_n; cb += 32) {
+          float v[32];
+          tmem_ld32_nowait(trow + (uint32_t)(pass0 + cb), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (affine) {
+            const float4* s4 = reinterpret_cast<const float4*>(s_scale + pass0 + cb);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + pass0 + cb);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 sc = s4[g], bi = b4[g];
+              v[4 * g] = fmaf(v[4 * g], sc.x, bi.x); v[4 * g + 1] = fmaf(v[4 * g + 1], sc.y, bi.y);
+              v[4 * g + 2] = fmaf(v[4 * g + 2], sc.z, bi.z); v[4 * g + 3] = fmaf(v[4 * g + 3], sc.w, bi.w);
+            }
+          }
+          if (ACT != S2V_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i], p.ap);
+          }
+          if (st_scalar) {                          // LayerNorm2d totals from the fp32 values (pairwise trees)
+            float ts[8], tq[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              ts[g] = (v[4 * g] + v[4 * g + 1]) + (v[4 * g + 2] + v[4 * g + 3]);
+              tq[g] = fmaf(v[4 * g + 1], v[4 * g + 1], v[4 * g] * v[4 * g]) + fmaf(v[4 * g + 3], v[4 * g + 3], v[4 * g + 2] * v[4 * g + 2]);
+            }
+            ln_s += ((ts[0] + ts[1]) + (ts[2] + ts[3])) + ((ts[4] + ts[5]) + (ts[6] + ts[7]));
+            ln_q += ((tq[0] + tq[1]) + (tq[2] + tq[3])) + ((tq[4] + tq[5]) + (tq[6] + tq[7]));
+          }
+          const int col = cb;                         // column within the pass
+          __half* const panel = row_base + (size_t)(col >> 6) * (kTileM * 64);
+          const int c0 = (col >> 3) & 7;              // 0 or 4: the four chunks c0 .. c0+3 never wrap
+#pragma unroll
+          for (int g = 0; g < 4; ++g) st_h8(panel + (((c0 + g) ^ r7) << 3), f_to_h8(v + 8 * g));
+        }
+      } else
       for (int cb = 0; cb < pass_n; cb += 32) {
         float v[32];
         tmem_ld16_nowait(trow + (uint32_t)(pass0 + cb), v);
@@ -369,8 +455,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
               for (int i = 0; i < 8; ++i) o[i] = act_t<ACT>(o[i], p.ap);
             }
             if (st_scalar && c < p.cout) {          // LayerNorm2d totals: this thread's row, all channels, straight from fp32
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { ln_s += o[i]; ln_q = fmaf(o[i], o[i], ln_q); }
+              // (pairwise tree: a serial chain of 16 dependent adds per 8 columns stalls the two epilogue warps of a scheduler)
+              const float s0 = o[0] + o[1], s1 = o[2] + o[3], s2 = o[4] + o[5], s3 = o[6] + o[7];
+              const float q0 = fmaf(o[1], o[1], o[0] * o[0]), q1 = fmaf(o[3], o[3], o[2] * o[2]);
+              const float q2 = fmaf(o[5], o[5], o[4] * o[4]), q3 = fmaf(o[7], o[7], o[6] * o[6]);
+              ln_s += (s0 + s1) + (s2 + s3);
+              ln_q += (q0 + q1) + (q2 + q3);
             }
             st_h8(stage_ptr(m, cl), f_to_h8(o));
             continue;
@@ -401,6 +491,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           }
         }
       }
+      EPI_T(3);
       const bool last_pass = pass0 + half_n >= p.bn;
       if (last_pass) {
         // all TMEM reads of this accumulator buffer are complete: hand it back to the MMA warp
@@ -414,6 +505,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
       if (direct) continue;
       if (tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to the TMA engine
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      EPI_T(4);
       if (tma_store && et == 0) {
         // one bulk tensor store per 64-channel panel; TMA clips rows/channels outside the output view
         for (int pc = 0; pc < pass_n; pc += 64) {
@@ -423,7 +515,16 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
                        : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#ifdef S2V_EPI_PROF
+        if ((p.exp & 16) && prof_on) {              // how long until the bulk store has READ the staging buffer?
+          const long long w0 = clock64();
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          atomicAdd(&g_epi_prof[13], (unsigned long long)(clock64() - w0));
+          atomicAdd(&g_epi_prof[14], 1ull);
+        }
+#endif
       }
+      EPI_T(5);
       if (st_scalar && last_pass) {
         // LayerNorm2d consumer: only the totals over (C, H, W) are needed.  Every thread summed its own output row over
         // all channels in registers (fp32, before the fp16 rounding); a fixed xor-butterfly over the lanes that share an
@@ -442,7 +543,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
           *o2 = make_float2(ss, qq);
         }
       }
-      if (p.stats && !st_scalar) {
+      if (p.stats && !st_scalar && !(p.exp & 4)) {
         // Column sums (sum, sum of squares) of the staged fp16 tile, ONE partial per (image, spatial tile, channel):
         // the G = 128 / (pass_n / 8) consecutive lanes that share a 16-byte chunk (8 channels) each walk rows g, g+G, ...
         // of one image of the box with conflict-free 128-bit smem loads, then a fixed butterfly over those lanes
@@ -529,6 +630,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         }
       }
       const int cpr = pass_n >> 3;                  // 16-byte chunks per staged row
+      const int cpr_sh = (cpr & (cpr - 1)) == 0 ? __ffs(cpr) - 1 : -1;
       const int total = tma_store ? 0 : kTileM * cpr;
       // 4 independent (row, 16 B chunk) items per iteration: the residual loads are issued together so
       // their L2 latency overlaps (y and res2 may be the same buffer, so the compiler cannot hoist them)
@@ -540,9 +642,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         for (int u = 0; u < 4; ++u) {
           const int idx = base + u * 128;
           ok[u] = idx < total;
-          const int row = ok[u] ? idx / cpr : 0, ch = ok[u] ? idx - row * cpr : 0;
+          // (the box dimensions are powers of two - their product is 128 - and so is cpr for every pass width but 48 / 24 / 40 ...:
+          //  shifts and masks instead of five runtime divisions per item; this loop was ~5 000 clocks per pass)
+          const int row = ok[u] ? (cpr_sh >= 0 ? idx >> cpr_sh : idx / cpr) : 0, ch = ok[u] ? idx - row * cpr : 0;
           const int c = ntile * p.bn + pass0 + ch * 8;
-          const int rw = row % p.box_w, rh = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
+          const int rw = row & (p.box_w - 1), rh = (row >> lg_w) & (p.box_h - 1), rn = row >> lg_wh;
           const int pn = n0 + rn, py = y0 + rh, px = x0 + rw;
           ok[u] = ok[u] && pn < p.N && py < p.OH && px < p.OW && c < p.cout;
           dst[u] = p.y.p + pn * p.y.sn + py * p.y.sh + px * p.y.sw + c;
@@ -566,6 +670,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
         }
       }
       if (p.stage_bufs == 2 && p.epi_groups == 1) sb ^= 1u;
+#ifdef S2V_EPI_PROF
+      if (prof_on) {                                 // single-pass layers only are meaningful
+        tprof[6] = clock64();
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_epi_prof[i], (unsigned long long)(tprof[i + 1] - tprof[i]));
+        atomicAdd(&g_epi_prof[8], 1ull);
+      }
+#endif
     }
   }
 }
@@ -601,7 +712,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   sm.aempty0 = sm.afull0 + 8u * kMaxASlots;
   sm.ball = sm.aempty0 + 8u * kMaxASlots;               // resident-weights barrier (halo mode)
   sm.tptr = sm.ball + 16u;
-  sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
+  sm.bring = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes + p.a_slots2 * p.a_slot2_bytes);
   sm.s_scale = reinterpret_cast<float*>(smem_raw + (sm.tptr + 16u - raw_u32));
   sm.s_bias = sm.s_scale + p.tab;
   sm.s_valid = reinterpret_cast<uint8_t*>(sm.s_scale + 4 * p.tab);     // two groups x (scale[tab] | bias[tab])
@@ -689,7 +800,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         pdl_wait();
-        uint32_t a = 0, aph = 0;
+        // A-patch rings: ring 0 (slots 0 .. a_slots-1) and, when a_slots2 > 0, a ring of its own for the segment-2 patches
+        // (slots a_slots .. a_slots+a_slots2-1): with few slots a short segment-2 chunk otherwise leaves the next big patch
+        // load uncovered (its slot frees only when the chunk before it retires)
+        uint32_t a = 0, aph = 0, a2 = 0, aph2 = 0;
+        const bool ring2 = p.a_slots2 > 0;
+        const uint32_t ring1_base = sm.ring + (uint32_t)(p.a_slots * p.a_slot_bytes);
         const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
         for (int tile = w_first; tile < w_total; tile += w_step) {
           int ntile, n0, y0, x0, tile_sp;
@@ -709,11 +825,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t abytes = (uint32_t)(seg == 0 ? p.prows0 : p.prows2) * 128u;
             const CUtensorMap* tm = seg == 0 ? &tmA : &tmA2;
             const int ax = x0 - (seg == 0 ? p.pad_w : p.pad2_w), ay = y0 - (seg == 0 ? p.pad_h : p.pad2_h);
+            const bool r1 = ring2 && seg == 1;
             for (int c = 0; c < chunks; ++c) {
-              mbar_wait(sm.aempty0 + 8u * a, aph ^ 1u);
-              if (leader) mbar_expect_tx(sm.afull0 + 8u * a, txm * abytes);
-              load_a(sm.ring + a * (uint32_t)p.a_slot_bytes, tm, afull_r + 8u * a, c * kChunkK, ax, ay, n0);
-              if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
+              const uint32_t idx = r1 ? (uint32_t)p.a_slots + a2 : a;
+              const uint32_t dst = r1 ? ring1_base + a2 * (uint32_t)p.a_slot2_bytes : sm.ring + a * (uint32_t)p.a_slot_bytes;
+              mbar_wait(sm.aempty0 + 8u * idx, (r1 ? aph2 : aph) ^ 1u);
+              if (leader) mbar_expect_tx(sm.afull0 + 8u * idx, txm * abytes);
+              load_a(dst, tm, afull_r + 8u * idx, c * kChunkK, ax, ay, n0);
+              if (r1) { if (++a2 == (uint32_t)p.a_slots2) { a2 = 0; aph2 ^= 1u; } }
+              else if (++a == (uint32_t)p.a_slots) { a = 0; aph ^= 1u; }
               if (p.b_resident) continue;
               for (int t = 0; t < taps; ++t, kcol += kChunkK) {
                 mbar_wait(sm.empty0 + 8u * s, ph ^ 1u);
@@ -789,7 +909,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }                                   \
     __syncwarp();                       \
   } while (0)
-      uint32_t s = 0, ph = 0, a = 0, aph = 0;
+      uint32_t s = 0, ph = 0, a = 0, aph = 0, a2 = 0, aph2 = 0;
       const int chunks2 = p.ki_total > p.ki0 ? p.cin2_chunks : 0;
       int j = 0;
       if (p.halo) {
@@ -816,13 +936,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t bu_n = ((uint32_t)(C2 ? (p.bn_narrow >> 1) : p.bn_narrow) * 128u) >> 4;
         const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.bn_narrow >> 3) << 17) | ((uint32_t)((C2 ? 2 * kTileM : kTileM) >> 4) << 24);
         const uint32_t a_slot_units = (uint32_t)p.a_slot_bytes >> 4, a_slots = (uint32_t)p.a_slots;
+        const uint32_t a_slot2_units = (uint32_t)p.a_slot2_bytes >> 4, a_slots2 = (uint32_t)p.a_slots2;
+        const bool ring2 = a_slots2 > 0;
         const uint32_t ring_lo = desc_lo(sm.ring), bring_lo = desc_lo(sm.bring);
+        const uint32_t ring1_lo = ring_lo + a_slots * a_slot_units;
         const bool b_res = p.b_resident != 0;
         if (b_res) { mbar_wait(sm.ball, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
         for (int tile = w_first; tile < w_total; tile += w_step, ++j) {
           const uint32_t buf = (uint32_t)j & 1u;
+#ifdef S2V_EPI_PROF
+          const bool mprof = blockIdx.x == 0 && lane == 0;
+          long long mt0 = clock64(), mt1, mw_a = 0, mw_i = 0;
+#endif
           mbar_wait(sm.tempty0 + 8u * buf, (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef S2V_EPI_PROF
+          mt1 = clock64();
+#endif
           const uint32_t d_tmem = tmem + buf * (uint32_t)p.tmem_buf_cols;
           uint32_t accum = 0;
           uint32_t b_res_lo = bring_lo;                                  // resident weights: walks the whole matrix per tile
@@ -831,14 +961,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kh = sg_kh[seg], kw = sg_kw[seg], shape = sg_shape[seg];
             const uint32_t a_hi = sg_ahi[seg], row_step = sg_rowstep[seg], ru = sg_ru[seg];
             for (int c = 0; c < sg_chunks[seg]; ++c) {
-              mbar_wait(sm.afull0 + 8u * a, aph);
+#ifdef S2V_EPI_PROF
+              const long long ca0 = clock64();
+#endif
+              const bool r1 = ring2 && seg == 1;
+              const uint32_t aidx = r1 ? a_slots + a2 : a;
+              mbar_wait(sm.afull0 + 8u * aidx, r1 ? aph2 : aph);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              uint32_t a_lo = ring_lo + a * a_slot_units;
+#ifdef S2V_EPI_PROF
+              const long long ca1 = clock64();
+              mw_a += ca1 - ca0;
+#endif
+              uint32_t a_lo = r1 ? ring1_lo + a2 * a_slot2_units : ring_lo + a * a_slot_units;
               if (shape) {
                 // narrow chunks (structural zero block of the weights): same A patch, N = bn_narrow columns of the accumulator
                 const bool nrw = seg == 0 && p.bn_narrow != 0 && c >= p.nf_chunk;
                 const uint32_t idc = nrw ? idesc_n : idesc, buc = nrw ? bu_n : bu;
-                if (elect_one()) {
+                if (!(p.exp & 2) && elect_one()) {
                   switch (shape) {
                     case 1: issue_chunk_resident<1, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
                     case 2: issue_chunk_resident<2, C2>(d_tmem, a_lo, a_hi, ru, b_res_lo, buc, hi1024, idc, accum, kh); break;
@@ -870,11 +1009,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               }
-              commit(sm.aempty0 + 8u * a);          // patch slot free once these MMAs retire
-              if (++a == a_slots) { a = 0; aph ^= 1u; }
+              commit(sm.aempty0 + 8u * aidx);       // patch slot free once these MMAs retire
+              if (r1) { if (++a2 == a_slots2) { a2 = 0; aph2 ^= 1u; } }
+              else if (++a == a_slots) { a = 0; aph ^= 1u; }
+#ifdef S2V_EPI_PROF
+              mw_i += clock64() - ca1;
+#endif
             }
           }
           commit(sm.tfull0 + 8u * buf);               // accumulator of this tile complete (signalled to both CTAs)
+#ifdef S2V_EPI_PROF
+          if (mprof) {
+            atomicAdd(&g_epi_prof[9], (unsigned long long)(mt1 - mt0));     // wait for the accumulator buffer
+            atomicAdd(&g_epi_prof[10], (unsigned long long)mw_a);           // wait for A patches
+            atomicAdd(&g_epi_prof[11], (unsigned long long)mw_i);           // issue
+            atomicAdd(&g_epi_prof[12], 1ull);
+          }
+#endif
         }
       } else {
         const uint32_t stages = (uint32_t)p.stages;
@@ -933,6 +1084,14 @@ static EncodeTiledFn get_encode() {
 }  // namespace s2v
 
 using namespace s2v;
+
+#ifdef S2V_EPI_PROF
+extern "C" int s2v_dbg_epi_prof(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, g_epi_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return S2V_ECUDA;
+  if (reset) { unsigned long long z[16] = {}; if (cudaMemcpyToSymbol(g_epi_prof, z, sizeof(z)) != cudaSuccess) return S2V_ECUDA; }
+  return S2V_OK;
+}
+#endif
 
 extern "C" int s2v_conv_tc_tile_n(int cout) {
   static int bn_max = 0;                   // development knob, resolved once
@@ -1000,7 +1159,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.k2w = seg2 ? d->k2w : 1; p.pad2_h = d->pad2_h; p.pad2_w = d->pad2_w;
   p.ki_total = p.ki0 + (seg2 ? p.taps2 * p.cin2_chunks : 0);
   p.n_tiles_n = ceil_div(cout, bn);
-  p.tab = (bn + 31) / 32 * 32;
+  p.tab = (d->scale || d->bias) ? (bn + 31) / 32 * 32 : 0;     // identity epilogues carry no tables
   // halo mode: stride 1, no dilation, and (1x1, any box) or (k > 1 with an 8-pixel-wide single-image box)
   const bool unit = d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1;
   const bool box816 = box_w == 8 && box_n == 1;
@@ -1029,7 +1188,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
     nf_chunk = d->narrow_cin_from / kChunkK;
     narrow_taps = (p.cin_chunks - nf_chunk) * p.taps0;
   }
-  struct SmemPlan { bool ok, resident, halo; int pass_cols, bufs, a_slots, stages, ring_bytes, stage_out_bytes, b_bytes; };
+  struct SmemPlan { bool ok, resident, halo; int pass_cols, bufs, a_slots, stages, ring_bytes, stage_out_bytes, b_bytes, a_slots2, s0, s1; };
   const int cap = 227 * 1024 - (16 * 8 + 240 + 4 * p.tab * (int)sizeof(float) + 512 + 1024);
   auto plan_smem = [&](bool pair) -> SmemPlan {
     SmemPlan sp = {};
@@ -1051,7 +1210,24 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
           if (sp.a_slots > kMaxASlots) sp.a_slots = kMaxASlots;
           // ~64 KB of patches in flight covers the load latency; beyond that extra slots only cost shared memory
           while (sp.a_slots > 4 && (long long)(sp.a_slots - 1) * a_slot_bytes >= 96 * 1024) --sp.a_slots;
-          sp.ring_bytes = sp.a_slots * a_slot_bytes + (int)wb;
+          sp.s0 = a_slot_bytes; sp.s1 = 0; sp.a_slots2 = 0;
+          // Few slots and a second K segment: give the segment-2 patches a ring of their own, each ring with slots of its own
+          // size (48 x 48 merged FFC GEMM: 2 x 23 KB + 1 x 16 KB instead of 2 x 23 KB; 24 x 24 l2g: 1 x 23 KB + 2 x 16 KB).
+          // Measured on B200: the MMA warp of the 48 x 48 GEMM spent 26 % of its time waiting for patches with the shared ring.
+          static const int ring2_env = [] { const char* e = getenv("S2V_RING2"); return e ? atoi(e) : 1; }();      // development knob
+          if (ring2_env && seg2 && sp.a_slots < 4) {
+            const int s0 = (p.prows0 * 128 + 1023) / 1024 * 1024, s1 = (p.prows2 * 128 + 1023) / 1024 * 1024;
+            const long long avail = cap - so - wb;
+            for (int n1 = p.cin2_chunks < 2 ? p.cin2_chunks : 2; n1 >= 1; --n1) {
+              int n0 = (int)((avail - (long long)n1 * s1) / s0);
+              if (n0 > kMaxASlots - n1) n0 = kMaxASlots - n1;
+              if (n0 >= 1 && n0 + n1 > sp.a_slots) {
+                sp.a_slots = n0; sp.a_slots2 = n1; sp.s0 = s0; sp.s1 = s1;
+                break;
+              }
+            }
+          }
+          sp.ring_bytes = sp.a_slots * sp.s0 + sp.a_slots2 * sp.s1 + (int)wb;
           return sp;
         }
     }
@@ -1110,7 +1286,9 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   static const int pf_env = [] { const char* e = getenv("S2V_PF"); return e ? atoi(e) : 0; }();      // development knob
   p.pf_dist = (sp.halo && p.n_tiles_n == 1) ? pf_env : 0;
   p.a_slots = sp.halo ? sp.a_slots : 0;
-  p.a_slot_bytes = sp.halo ? a_slot_bytes : 0;
+  p.a_slot_bytes = sp.halo ? (sp.a_slots2 ? sp.s0 : a_slot_bytes) : 0;
+  p.a_slots2 = sp.halo ? sp.a_slots2 : 0;
+  p.a_slot2_bytes = sp.halo ? sp.s1 : 0;
   p.ring_bytes = sp.ring_bytes;
   int stages = sp.stages;
   p.stages = stages;
@@ -1119,6 +1297,7 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   p.r2 = mk(d->res2.ptr ? &d->res2 : nullptr);
   p.scale = d->scale; p.bias = d->bias; p.act = d->act; p.ap = d->act_param;
   p.out_mode = d->out_mode; p.yf = d->y_f32;
+  { static const int exp_env = [] { const char* e = getenv("S2V_EXP"); return e ? atoi(e) : 0; }(); p.exp = exp_env; }
   p.stats = d->stats_partial;
   p.st_c_off = d->stats_c_off; p.st_c_total = d->stats_c_total;
   p.st_chunk_off = d->stats_chunk_off; p.st_chunks_total = d->stats_chunks_total;
@@ -1184,6 +1363,12 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   }
   CUtensorMap tmY = tmA;
   p.use_tma_store = (d->out_mode == S2V_OUT_F16_NHWC && !d->res1.ptr && !d->res2.ptr) ? 1 : 0;
+  {
+    // development knob: 0 = coalesced manual stores from the staging tile everywhere, 2 = manual stores when a tile takes several
+    // passes through ONE staging buffer per group (the next pass otherwise waits for the bulk store to have read the buffer)
+    static const int ts_env = [] { const char* e = getenv("S2V_TMA_STORE"); return e ? atoi(e) : 1; }();
+    if (ts_env == 0 || (ts_env == 2 && bn > sp.pass_cols)) p.use_tma_store = 0;
+  }
   if (p.use_tma_store) {
     cuuint64_t gdim[4] = {(cuuint64_t)d->y.c, (cuuint64_t)d->y.w, (cuuint64_t)d->y.h, (cuuint64_t)d->y.n};
     cuuint64_t gstr[3] = {(cuuint64_t)d->y.sw * 2, (cuuint64_t)d->y.sh * 2, (cuuint64_t)d->y.sn * 2};
@@ -1231,8 +1416,8 @@ extern "C" int s2v_conv_tc(const s2v_conv* d, int box_w, int box_h, int box_n, v
   if (dbg < 0) { const char* e = getenv("S2V_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   if (dbg)
     fprintf(stderr, "conv_tc: N=%d %dx%d cin=%d cout=%d k=%dx%d seg2=%d | bn=%d halo=%d resident=%d a_slots=%d stages=%d pass_cols=%d stage_bufs=%d "
-            "epi_groups=%d cta2=%d m_tiles=%d smem=%zu narrow=%d\n", N, OH, OW, d->x.c, cout, d->kh, d->kw, (int)seg2, bn, p.halo, p.b_resident, p.a_slots,
-            stages, p.pass_cols, p.stage_bufs, p.epi_groups, (int)cta2, p.m_tiles, smem, p.bn_narrow);
+            "epi_groups=%d cta2=%d m_tiles=%d smem=%zu narrow=%d a_slots2=%d\n", N, OH, OW, d->x.c, cout, d->kh, d->kw, (int)seg2, bn, p.halo, p.b_resident, p.a_slots,
+            stages, p.pass_cols, p.stage_bufs, p.epi_groups, (int)cta2, p.m_tiles, smem, p.bn_narrow, p.a_slots2);
   if (cta2) {
     p.m_pairs = (p.m_tiles + 1) / 2;
     p.total_pair_tiles = p.m_pairs * p.n_tiles_n;
