@@ -148,7 +148,16 @@ __device__ __forceinline__ H8 f_to_h8(const float* f) {
   for (int i = 0; i < 4; ++i) h.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return h;
 }
-__device__ __forceinline__ H8 ld_h8(const __half* p) { return *reinterpret_cast<const H8*>(p); }
+// one 128-bit load (a struct copy may be split into four 32-bit loads when the source is shared memory)
+__device__ __forceinline__ H8 ld_h8(const __half* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  H8 h;
+  *reinterpret_cast<uint32_t*>(&h.v[0]) = u.x;
+  *reinterpret_cast<uint32_t*>(&h.v[1]) = u.y;
+  *reinterpret_cast<uint32_t*>(&h.v[2]) = u.z;
+  *reinterpret_cast<uint32_t*>(&h.v[3]) = u.w;
+  return h;
+}
 // one 128-bit store: a struct copy of H8 is emitted as four 32-bit stores when the destination is shared memory (the conv
 // epilogue's staging tile: 4-way bank-conflicted STS.32 instead of one conflict-free STS.128)
 __device__ __forceinline__ void st_h8(__half* p, const H8& v) {
