@@ -298,6 +298,51 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int cra
   x0 = tw * p.box_w; y0 = th * p.box_h; n0 = tn * p.box_n;
 }
 
+// NC (32 or 16) accumulator columns of this thread's row: TMEM -> scale / bias -> activation -> [LayerNorm2d totals] -> fp16 ->
+// NC / 8 128-bit stores into the swizzled staging tile.  Straight-line code on NC independent values (the per-launch conditions
+// are warp-uniform branches around whole blocks): the generic column loop of epilogue_loop is a chain of small basic blocks and
+// ran at ~600 clocks per 32 columns with two epilogue warps per scheduler, this one at ~250.
+template <int ACT, int NC>
+__device__ __forceinline__ void epi_cols(uint32_t taddr, const float* s_scale, const float* s_bias, bool affine, bool st_scalar, float ap,
+                                         float& ln_s, float& ln_q, __half* row_base, int col, int r7) {
+  float v[NC];
+  if (NC == 32) tmem_ld32_nowait(taddr, v);
+  else tmem_ld16_nowait(taddr, v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (affine) {
+    const float4* s4 = reinterpret_cast<const float4*>(s_scale);
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias);
+#pragma unroll
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 sc = s4[g], bi = b4[g];
+      v[4 * g] = fmaf(v[4 * g], sc.x, bi.x); v[4 * g + 1] = fmaf(v[4 * g + 1], sc.y, bi.y);
+      v[4 * g + 2] = fmaf(v[4 * g + 2], sc.z, bi.z); v[4 * g + 3] = fmaf(v[4 * g + 3], sc.w, bi.w);
+    }
+  }
+  if (ACT != S2V_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = act_t<ACT>(v[i], ap);
+  }
+  if (st_scalar) {                                // LayerNorm2d totals from the fp32 values (pairwise trees)
+    float ts[NC / 4], tq[NC / 4];
+#pragma unroll
+    for (int g = 0; g < NC / 4; ++g) {
+      ts[g] = (v[4 * g] + v[4 * g + 1]) + (v[4 * g + 2] + v[4 * g + 3]);
+      tq[g] = fmaf(v[4 * g + 1], v[4 * g + 1], v[4 * g] * v[4 * g]) + fmaf(v[4 * g + 3], v[4 * g + 3], v[4 * g + 2] * v[4 * g + 2]);
+    }
+#pragma unroll
+    for (int w = NC / 8; w >= 1; w >>= 1)
+#pragma unroll
+      for (int g = 0; g < w; ++g) { ts[g] += ts[g + w]; tq[g] += tq[g + w]; }
+    ln_s += ts[0];
+    ln_q += tq[0];
+  }
+  __half* const panel = row_base + (size_t)(col >> 6) * (kTileM * 64);
+  const int c0 = (col >> 3) & 7;                  // multiple of 2 (NC = 16) or 4 (NC = 32): chunks c0 .. c0 + NC / 8 - 1 never wrap
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) st_h8(panel + (((c0 + g) ^ r7) << 3), f_to_h8(v + 8 * g));
+}
+
 // Epilogue warps (4): for every tile of this CTA, TMEM -> registers -> scale/bias/activation ->
 // (fp16 tile staged in smem -> optional column statistics -> coalesced 16-byte stores [+ residual]) or direct
 // stores (fp32 NCHW heads, pre-activation residual).  Runs concurrently with the producer / MMA warps
@@ -391,45 +436,17 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Smem& sm,
       // and straight-line code with the per-launch conditions hoisted, so that the 32 values are independent instruction
       // streams - the generic loop below is a chain of small basic blocks (latency-bound with two epilogue warps per scheduler:
       // measured ~600 clocks per 32 columns)
-      const bool fast_cols = !direct && (pass_n & 31) == 0 && ntile * p.bn + pass0 + pass_n <= p.cout && !(p.exp & 8);
+      const bool fast_cols = !direct && (pass_n & 15) == 0 && ntile * p.bn + pass0 + pass_n <= p.cout && !(p.exp & 8);
       if (fast_cols) {
         __half* const row_base = sm.stage + (size_t)sb * (p.stage_out_bytes >> 2) + (size_t)m * 64;
         const int r7 = m & 7;
 #pragma unroll 1
-        for (int cb = 0; cb < pass_n; cb += 32) {
-          float v[32];
-          tmem_ld32_nowait(trow + (uint32_t)(pass0 + cb), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (affine) {
-            const float4* s4 = reinterpret_cast<const float4*>(s_scale + pass0 + cb);
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + pass0 + cb);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 sc = s4[g], bi = b4[g];
-              v[4 * g] = fmaf(v[4 * g], sc.x, bi.x); v[4 * g + 1] = fmaf(v[4 * g + 1], sc.y, bi.y);
-              v[4 * g + 2] = fmaf(v[4 * g + 2], sc.z, bi.z); v[4 * g + 3] = fmaf(v[4 * g + 3], sc.w, bi.w);
-            }
-          }
-          if (ACT != S2V_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i], p.ap);
-          }
-          if (st_scalar) {                          // LayerNorm2d totals from the fp32 values (pairwise trees)
-            float ts[8], tq[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              ts[g] = (v[4 * g] + v[4 * g + 1]) + (v[4 * g + 2] + v[4 * g + 3]);
-              tq[g] = fmaf(v[4 * g + 1], v[4 * g + 1], v[4 * g] * v[4 * g]) + fmaf(v[4 * g + 3], v[4 * g + 3], v[4 * g + 2] * v[4 * g + 2]);
-            }
-            ln_s += ((ts[0] + ts[1]) + (ts[2] + ts[3])) + ((ts[4] + ts[5]) + (ts[6] + ts[7]));
-            ln_q += ((tq[0] + tq[1]) + (tq[2] + tq[3])) + ((tq[4] + tq[5]) + (tq[6] + tq[7]));
-          }
-          const int col = cb;                         // column within the pass
-          __half* const panel = row_base + (size_t)(col >> 6) * (kTileM * 64);
-          const int c0 = (col >> 3) & 7;              // 0 or 4: the four chunks c0 .. c0+3 never wrap
-#pragma unroll
-          for (int g = 0; g < 4; ++g) st_h8(panel + (((c0 + g) ^ r7) << 3), f_to_h8(v + 8 * g));
-        }
+        for (int cb = 0; cb + 32 <= pass_n; cb += 32)
+          epi_cols<ACT, 32>(trow + (uint32_t)(pass0 + cb), s_scale + pass0 + cb, s_bias + pass0 + cb, affine, st_scalar, p.ap, ln_s, ln_q,
+                            row_base, cb, r7);
+        if (pass_n & 16)                            // 48 / 80 / 112-column passes: one 16-column tail group
+          epi_cols<ACT, 16>(trow + (uint32_t)(pass0 + (pass_n & ~31)), s_scale + pass0 + (pass_n & ~31), s_bias + pass0 + (pass_n & ~31), affine,
+                            st_scalar, p.ap, ln_s, ln_q, row_base, pass_n & ~31, r7);
       } else
       for (int cb = 0; cb < pass_n; cb += 32) {
         float v[32];

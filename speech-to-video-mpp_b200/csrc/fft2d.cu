@@ -11,8 +11,16 @@ namespace s2v {
 
 __constant__ float2 c_tw48[48];   // exp(-2*pi*i*j/48)
 
+// (measured on B200: the same butterflies with the sm_100 packed fp32x2 instructions - __fadd2_rn / __ffma2_rn, 22 % fewer
+//  floating-point instructions - run in exactly the same time, 24.0 vs 23.7 us for rfft2 48 x 48 at B = 128: the kernels are
+//  not bound by their arithmetic instruction count; -DS2V_FFT_PACKED keeps the variant for A/B runs)
+#ifdef S2V_FFT_PACKED
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 template <bool INV>
 __device__ __forceinline__ float2 cmul_tw(float2 a, float2 w) {   // a * w  (INV: a * conj(w))
   if (INV) return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);

@@ -17,9 +17,17 @@ for S, ch in ((48, 48), (24, 96), (12, 384)):
             op.run()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            op.run()
-        b.record(); torch.cuda.synchronize()
+        if os.environ.get("MB_GRAPH", "1") == "1":      # device time only: the launches are replayed from a CUDA graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    op.run()
+            g.replay(); torch.cuda.synchronize()
+            a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+        else:
+            a.record()
+            for _ in range(reps):
+                op.run()
+            b.record(); torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / reps
         print("%-7s S=%d ch=%d  %7.1f us  %6.0f GB/s" % (name, S, ch, us, op.alg_bytes / us / 1e3), flush=True)
