@@ -250,10 +250,11 @@ def roofline_of(tot, total, what):
     return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 / TMEM / TMA implicit GEMM), %d launches per %s" % (tc[1], what),
             "achieved": round(ach, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4),
             # dram__bytes_read.sum + dram__bytes_write.sum of the class's largest launch on this metric (DNet editing_net.encoder.down0,
-            # 256 x 256, 64 -> 128, 3x3, batch 64: 5.8 % of the class time) from one ncu --set full capture
-            # (profiles/r2_ncu_full_conv_tc_dnet_down0_raw.csv): 537.1 MB read + 1016.4 MB written; algorithmic 1610.8 MB
-            # (536.9 in + 0.15 weights + 1073.7 out) - no re-reads.  LNet 12x12 3x3 K=9216: 57.5 MB vs 51.8 (profiles/r1c_*)
-            "traffic": 1553.5e6, "traffic_of": "one DNet down0 launch (256x256, 64->128, 3x3, B=64; ncu --set full, DRAM bytes per launch; algorithmic 1610.8e6); other shapes: profiles/",
+            # 256 x 256, 64 -> 128, 3x3, batch 64) from one ncu --set full capture of the current kernel
+            # (profiles/r2b_ncu_full_conv_tc_dnet_down0_raw.csv): 538.1 MB read + 1019.2 MB written; algorithmic 1610.8 MB
+            # (536.9 in + 0.15 weights + 1073.7 out) - no re-reads.  LNet 48 x 48 merged FFC GEMM: 153.9 MB vs 185.7 algorithmic
+            # (profiles/r2b_ncu_full_conv_tc_res0_all_raw.csv; part of the input still in L2)
+            "traffic": 1557.3e6, "traffic_of": "one DNet down0 launch (256x256, 64->128, 3x3, B=64; ncu --set full, DRAM bytes per launch; algorithmic 1610.8e6); other shapes: profiles/",
             "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
             "alg_gflop": round(tc[2] / 1e9, 1), "kernel_ms": round(tc[0], 3), "avg_launch_us": round(1e3 * tc[0] / tc[1], 2),
             "share_of_step_kernels": round(tc[0] / total, 4), "sum_of_classes_ms": round(total, 3),
