@@ -172,23 +172,29 @@ def test_stem_conv_overlapping_view(G, cin, cout, k, hw):
 
 
 def test_two_segment_gemm(G):
-    """y = conv3x3_reflect(x_l) + conv1x1(s2): both K segments accumulate in one TMEM tile (FFC out_g)."""
+    """y = conv3x3_reflect(x_l) + conv1x1(s2): both K segments accumulate in one TMEM tile (FFC out_g).  The 24 x 24 and 48 x 48
+    geometries run in halo mode with resident weights and few A-patch slots: the segment-2 patches get a ring of their own
+    (conv_tc.cu: a_slots2), with and without a per-channel scale / bias / activation epilogue (table space changes the slot plan)."""
     lib, L, ops = G.lib(), G.L, G.ops
     torch.manual_seed(11)
-    n, s, cl, cg, ch = 9, 12, 64, 192, 96
-    xp = torch.randn(n, s + 2, s + 2, cl + cg, device="cuda").half()
-    ops.op_reflect_border(lib, xp[:, 1:-1, 1:-1, :]).run()
-    s2 = torch.randn(n, s, s, ch, device="cuda").half()
-    w3 = torch.randn(cg, cl, 3, 3, device="cuda") / (cl * 9) ** 0.5
-    w1 = torch.randn(cg, ch, 1, 1, device="cuda") / ch ** 0.5
-    R = torch.full((n, s, s, cl + cg), 5.0, dtype=torch.float16, device="cuda")
-    wcat = torch.cat([ops.pack_w_tc(w3), ops.pack_w_tc(w1)], 1).contiguous()
-    ops.op_conv(lib, xp[..., :cl], wcat, R[..., cl:], k=(3, 3), x2=s2).run()
-    torch.cuda.synchronize()
-    xl = xp[:, 1:-1, 1:-1, :cl].permute(0, 3, 1, 2).float()
-    ref = F.conv2d(F.pad(xl, (1, 1, 1, 1), mode="reflect"), w3.half().float()) + F.conv2d(s2.permute(0, 3, 1, 2).float(), w1.half().float())
-    m, rel = G.report("conv_tc two-segment (3x3 + 1x1)", G.nchw(R[..., cl:]), ref)
-    assert rel < 3e-3 and (R[..., :cl] == 5).all()
+    for (n, s, cl, cg, ch, epi) in ((9, 12, 64, 192, 96, False), (3, 24, 64, 192, 96, False), (3, 24, 64, 192, 96, True),
+                                    (2, 48, 32, 96, 48, False), (5, 48, 32, 96, 48, True)):
+        xp = torch.randn(n, s + 2, s + 2, cl + cg, device="cuda").half()
+        ops.op_reflect_border(lib, xp[:, 1:-1, 1:-1, :]).run()
+        s2 = torch.randn(n, s, s, ch, device="cuda").half()
+        w3 = torch.randn(cg, cl, 3, 3, device="cuda") / (cl * 9) ** 0.5
+        w1 = torch.randn(cg, ch, 1, 1, device="cuda") / ch ** 0.5
+        R = torch.full((n, s, s, cl + cg), 5.0, dtype=torch.float16, device="cuda")
+        wcat = torch.cat([ops.pack_w_tc(w3), ops.pack_w_tc(w1)], 1).contiguous()
+        kw = dict(scale=torch.rand(cg, device="cuda") + 0.5, bias=torch.randn(cg, device="cuda"), act=L.ACT_LRELU, act_param=0.1) if epi else {}
+        ops.op_conv(lib, xp[..., :cl], wcat, R[..., cl:], k=(3, 3), x2=s2, **kw).run()
+        torch.cuda.synchronize()
+        xl = xp[:, 1:-1, 1:-1, :cl].permute(0, 3, 1, 2).float()
+        ref = F.conv2d(F.pad(xl, (1, 1, 1, 1), mode="reflect"), w3.half().float()) + F.conv2d(s2.permute(0, 3, 1, 2).float(), w1.half().float())
+        if epi:
+            ref = F.leaky_relu(ref * kw["scale"][None, :, None, None] + kw["bias"][None, :, None, None], 0.1)
+        m, rel = G.report("conv_tc two-segment (3x3 + 1x1) %dx%d%s" % (s, s, " + epilogue" if epi else ""), G.nchw(R[..., cl:]), ref)
+        assert rel < 3e-3 and (R[..., :cl] == 5).all(), (n, s, epi, rel)
 
 
 def test_fused_epilogue_statistics(G):
