@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libs2v.so")
-SOURCES = ["api.cu", "warp.cu", "mel.cu", "layout.cu", "norm.cu", "conv_simt.cu", "linear.cu", "fft2d.cu",
+SOURCES = ["api.cu", "warp.cu", "mel.cu", "layout.cu", "norm.cu", "conv_simt.cu", "linear.cu", "fft2d.cu", "fft2d_mma.cu",
            "attention.cu", "conv_tc.cu", "conv_head.cu", "semantic.cu", "blend.cu", "enet.cu", "resample.cu", "imageops.cu", "plan.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

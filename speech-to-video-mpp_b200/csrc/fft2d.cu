@@ -9,6 +9,15 @@
 
 namespace s2v {
 
+// fft2d_mma.cu: the same transforms as dense DFT matrix products on mma.sync, selected per size with S2V_FFT_MMA (bit 0 = 48 x 48,
+// bit 1 = 24 x 24, bit 2 = 12 x 12; default 0).  Measured on B200 (profiles/r2c_summary.md): 5 x fewer instructions and a 39 KB
+// tile, but the 250 registers of resident A fragments leave 8 warps per SM - 48 x 48 at B = 256: 45.0 / 67.5 us against 53.2 /
+// 75.9 us here, B = 128: 24.4 / 36.0 against 23.6 / 37.1, smaller sizes slower; LNet B = 256 24.62 against 24.92 ms.  Not
+// enough to pay for its extra fp16 rounding of the twiddles, so the register FFT below stays the default.
+int fft_mma_init();
+int rfft2_mma(const s2v_view* x, const s2v_view* sp, cudaStream_t st);
+int irfft2_mma(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st);
+
 __constant__ float2 c_tw48[48];   // exp(-2*pi*i*j/48)
 
 // (measured on B200: the same butterflies with the sm_100 packed fp32x2 instructions - __fadd2_rn / __ffma2_rn, 22 % fewer
@@ -176,6 +185,10 @@ static int fft24_cb32() {
   static const int v = [] { const char* e = getenv("S2V_FFT24_CB32"); return e ? atoi(e) : 1; }();     // development knob
   return v;
 }
+static bool fft_use_mma(int s) {
+  static const int mask = [] { const char* e = getenv("S2V_FFT_MMA"); return e ? atoi(e) : 0; }();       // development knob
+  return s == 48 ? (mask & 1) : s == 24 ? (mask & 2) : s == 12 ? (mask & 4) : false;
+}
 static int fft_rev() {
   static const int rev = [] { const char* e = getenv("S2V_FFT_REV"); return e ? atoi(e) : 0; }();
   return rev;
@@ -214,7 +227,8 @@ extern "C" int s2v_fft_init(void) {
     const double a = -2.0 * 3.14159265358979323846 * j / 48.0;
     h[j] = make_float2((float)cos(a), (float)sin(a));
   }
-  return cudaMemcpyToSymbol(c_tw48, h, sizeof(h)) == cudaSuccess ? S2V_OK : S2V_ECUDA;
+  if (cudaMemcpyToSymbol(c_tw48, h, sizeof(h)) != cudaSuccess) return S2V_ECUDA;
+  return fft_mma_init();
 }
 
 static bool fft_shapes_ok(const s2v_view* x, const s2v_view* sp) {
@@ -227,6 +241,7 @@ static bool fft_shapes_ok(const s2v_view* x, const s2v_view* sp) {
 extern "C" int s2v_rfft2(const s2v_view* x, const s2v_view* spec, void* stream) {
   if (!fft_shapes_ok(x, spec)) return S2V_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (fft_use_mma(x->h)) return rfft2_mma(x, spec, st);
   if (x->h == 12 && x->c % 32 == 0) return launch_rfft2<12, 32>(x, spec, st);
   if (x->h == 12 && x->c % 8 == 0) return launch_rfft2<12, 8>(x, spec, st);
   if (x->h == 24 && x->c % 32 == 0 && fft24_cb32()) return launch_rfft2<24, 32>(x, spec, st);
@@ -241,6 +256,7 @@ extern "C" int s2v_irfft2(const s2v_view* spec, const s2v_view* add, const s2v_v
   if (!fft_shapes_ok(y, spec)) return S2V_EINVAL;
   if (add && add->ptr && (!view_ok(add) || add->h != y->h || add->w != y->w || add->c != y->c || add->n != y->n)) return S2V_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (fft_use_mma(y->h)) return irfft2_mma(spec, add && add->ptr ? add : nullptr, y, st);
   if (y->h == 12 && y->c % 32 == 0) return launch_irfft2<12, 32>(spec, add, y, st);
   if (y->h == 12 && y->c % 8 == 0) return launch_irfft2<12, 8>(spec, add, y, st);
   if (y->h == 24 && y->c % 32 == 0 && fft24_cb32()) return launch_irfft2<24, 32>(spec, add, y, st);

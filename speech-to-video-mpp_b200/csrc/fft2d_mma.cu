@@ -1,0 +1,480 @@
+// FourierUnit transforms as small DENSE DFT matrix products on the tensor cores (reference: models/ffc.py:99-102 rfftn +
+// re/im channel interleave, :116-121 de-interleave + irfftn, norm='ortho'; same entry points and tensors as fft2d.cu).
+//
+// Why: the register FFT of fft2d.cu executes ~77 k thread-instructions per image-channel at 48 x 48 and is bound by its
+// instruction issue (ncu: 14.8 M warp instructions per launch, 55 % issue-active, one 400-thread block per SM, 0.37-0.41 of the
+// HBM peak).  A 48-point DFT is a 48 x 48 matrix: with the channels as the GEMM's N dimension (fp16 channels-last tensors are
+// already [.., K index, channel]) both passes of the 2-D transform are [M <= 64] x [K <= 64] constant matrices times the tile,
+// 0.76 MFLOP per image-channel on mma.sync.m16n8k16 (fp16 operands, fp32 accumulate) = 5 x fewer issued instructions, and the
+// tile needs 39 KB of shared memory instead of 154 KB, so three blocks per SM overlap their load / compute / store phases.
+// The contraction sizes are far below a 128-row tcgen05 tile and the operands change role between the two passes (the
+// accumulator of pass 1 is the B operand of pass 2), which is what warp-level mma + ldmatrix.trans is for.
+//
+// One block (4 warps) = one image n x 8 channels.  The tile lives in shared memory as rows of RS = 32 (S/2+1) + 16 bytes:
+//   forward:  X[h][w][8 c]  --pass 1 per h, in place-->  Y[h][(k, re|im)][8 c]  --pass 2 per k-->  spec[kh][k][2 c + ri]  (global)
+//   inverse:  spec[kh][(k, re|im)][8 c] (de-interleaved on load)  --pass A per k, in place-->  T[h][(k, re|im)][8 c]
+//             --pass B per h-->  y[h][w][c] (+ residual)
+// A "row" of 16 bytes = the 8 channels of one K index, so ldmatrix.trans delivers B fragments directly (K = w, (k, ri) along a
+// tile row; K = h / kh across tile rows, conflict-free because RS = 16 mod 32 bytes... see Cfg).  Every pass is in place: a warp
+// owns whole tile rows (pass 1 / B) or whole (k, ri) column pairs (pass 2 / A), reads them into fragments, and only then writes.
+// The DFT matrices (1/sqrt(S) folded into each pass = ortho; Hermitian weights 1, 2, .., 2, 1 and the ignored imaginary parts of
+// the DC / Nyquist columns folded into the c2r matrix) are built on the host in fp16, already in A-fragment order.
+// Accuracy: fp16 twiddles add one rounding (2^-12 relative) per product to the fp16 rounding of the stored result; measured
+// against torch.fft in tests/test_gpu_kernels.py::test_fft2 (same 2e-3 of max bound as the register FFT).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace s2v {
+namespace fftmma {
+
+constexpr int kThreads = 128, kWarps = 4, kFragsTotal = 90;
+
+template <int S>
+struct Cfg {
+  static constexpr int K1 = S / 2 + 1;                 // stored half-spectrum columns
+  static constexpr int KP = (S + 15) / 16 * 16;        // K extent of the w / h / kh contractions
+  static constexpr int KT = KP / 16;
+  static constexpr int MT1 = (K1 + 7) / 8;             // pass 1 m-tiles: 8 k's each, rows 0-7 = re, rows 8-15 = im
+  static constexpr int MT2 = (S + 15) / 16;            // m-tiles over kh / h / w
+  static constexpr int K2P = (2 * K1 + 15) / 16 * 16;  // K extent of the c2r contraction over (k, ri)
+  static constexpr int KT2 = K2P / 16;
+  static constexpr int RS = K1 * 32 + 16;              // tile row stride in bytes: 816 / 432 / 240 = 48, 48, 112 mod 128 -> eight
+                                                       // consecutive rows start in eight different 16-byte bank groups
+  static constexpr int ROWS = KP;                      // rows >= S stay zero (K padding of the contractions over h / kh)
+  static constexpr int TILE = ROWS * RS + 256;         // + tail: the K padding of pass 1 / B reads past the last row
+  static constexpr int N_F1 = MT1 * KT, N_G = MT2 * KT, N_A2 = MT2 * KT2;
+  static constexpr int COUNT = N_F1 + 4 * N_G + N_A2;  // 60 / 24 / 6 fragments
+  static constexpr int BASE = S == 48 ? 0 : S == 24 ? 60 : 84;
+  static constexpr int O_F1 = BASE, O_GR = O_F1 + N_F1, O_GI = O_GR + N_G, O_WR = O_GI + N_G, O_WI = O_WR + N_G, O_A2 = O_WI + N_G;
+};
+static_assert(Cfg<48>::COUNT == 60 && Cfg<24>::COUNT == 24 && Cfg<12>::COUNT == 6, "fragment table layout");
+
+// A fragments of every DFT matrix: [fragment][lane] -> 4 registers of mma.m16n8k16 (filled by fft_mma_init, per device)
+__device__ uint4 g_frag[kFragsTotal * 32];
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// B fragments of KTN k-tiles whose K rows are `stride` bytes apart, starting at shared address `a` (16-byte rows)
+template <int KTN>
+__device__ __forceinline__ void load_b(uint32_t a, uint32_t stride, int lane, uint32_t (&b)[KTN][2]) {
+#pragma unroll
+  for (int kt = 0; kt + 1 < KTN; kt += 2) ldsm_x4_t(a + (uint32_t)(kt * 16 + lane) * stride, b[kt][0], b[kt][1], b[kt + 1][0], b[kt + 1][1]);
+  if (KTN & 1) ldsm_x2_t(a + (uint32_t)((KTN - 1) * 16 + (lane & 15)) * stride, b[KTN - 1][0], b[KTN - 1][1]);
+}
+
+// The complex pass over the tile rows (forward pass 2 along h, inverse pass A along kh) for column pair k:
+//   zr = Ar * Bre - Ai * Bim,  zi = Ar * Bim + Ai * Bre     (rows = MT2 m-tiles, columns = 8 channels)
+template <int S>
+__device__ __forceinline__ void complex_pass(uint32_t tile, int k, int lane, const uint4 (&ar)[Cfg<S>::MT2][Cfg<S>::KT],
+                                             const uint4 (&ai)[Cfg<S>::MT2][Cfg<S>::KT], float (&zr)[Cfg<S>::MT2][4],
+                                             float (&zi)[Cfg<S>::MT2][4]) {
+  using C = Cfg<S>;
+  uint32_t bre[C::KT][2], bim[C::KT][2], bin[C::KT][2];
+  load_b<C::KT>(tile + (uint32_t)(2 * k) * 16u, C::RS, lane, bre);
+  load_b<C::KT>(tile + (uint32_t)(2 * k + 1) * 16u, C::RS, lane, bim);
+#pragma unroll
+  for (int kt = 0; kt < C::KT; ++kt) { bin[kt][0] = bim[kt][0] ^ 0x80008000u; bin[kt][1] = bim[kt][1] ^ 0x80008000u; }   // -Bim
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { zr[mt][i] = 0.f; zi[mt][i] = 0.f; }
+  // issue order: 2 * MT2 independent accumulators round-robin, so that an accumulator is touched again only every 2 * MT2 MMAs
+  // (mma.sync issues in program order; back-to-back MMAs on one accumulator wait out the whole pipeline latency)
+#pragma unroll
+  for (int kt = 0; kt < C::KT; ++kt) {
+#pragma unroll
+    for (int mt = 0; mt < C::MT2; ++mt) mma16816(zr[mt], ar[mt][kt], bre[kt][0], bre[kt][1]);
+#pragma unroll
+    for (int mt = 0; mt < C::MT2; ++mt) mma16816(zi[mt], ar[mt][kt], bim[kt][0], bim[kt][1]);
+#pragma unroll
+    for (int mt = 0; mt < C::MT2; ++mt) mma16816(zr[mt], ai[mt][kt], bin[kt][0], bin[kt][1]);
+#pragma unroll
+    for (int mt = 0; mt < C::MT2; ++mt) mma16816(zi[mt], ai[mt][kt], bre[kt][0], bre[kt][1]);
+  }
+}
+
+// Blocks are PERSISTENT: BPS blocks per SM, block b takes tiles b, b + grid, ...  The DFT matrices stay in registers for the
+// block's lifetime (48 x 48: 120 registers of A fragments), the tile buffer is double-buffered and the next tile's cp.async
+// loads are issued before the current tile's first pass, so a block's load latency hides behind its own MMAs.
+// (First version, one block per tile with 3-4 blocks per SM: 21.4 / 32.2 us for rfft2 / irfft2 48 x 48 at B = 128 against 23.6 /
+// 37.1 us of the register FFT - ncu: tensor pipe 44 % / 29 % active while resident, long_scoreboard the top stall: every block
+// paid the tile's DRAM latency, two L2 round trips for its tables and three barriers in sequence.)
+template <int S> constexpr int blocks_per_sm() { return S == 48 ? 2 : S == 24 ? 4 : 8; }
+
+template <int S>
+__device__ __forceinline__ void zero_tiles(uint32_t tile) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * Cfg<S>::TILE / 16; i += kThreads) st_shared_u4(tile + (uint32_t)i * 16u, z);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// x [N,S,S,C] -> spec [N,S,S/2+1,2C]; tiles = N * C / 8 (image-major), grid = min(tiles, BPS * #SMs)
+template <int S>
+__global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel(View x, View sp, int cblocks, int tiles) {
+  using C = Cfg<S>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_trigger();
+  const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  zero_tiles<S>(tile0);
+  uint4 a1[C::MT1][C::KT], ar[C::MT2][C::KT], ai[C::MT2][C::KT];     // constant tables: fetched ahead of the PDL wait
+#pragma unroll
+  for (int mt = 0; mt < C::MT1; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) a1[mt][kt] = g_frag[(C::O_F1 + mt * C::KT + kt) * 32 + lane];
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+      ar[mt][kt] = g_frag[(C::O_GR + mt * C::KT + kt) * 32 + lane];
+      ai[mt][kt] = g_frag[(C::O_GI + mt * C::KT + kt) * 32 + lane];
+    }
+  __syncthreads();
+  pdl_wait();
+  auto issue_load = [&](int ti, uint32_t tile) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    const __half* xp = x.p + n * x.sn + ch0;
+    // fully unrolled: a rolled loop re-uses the address registers, and every LDGSTS then waits for the previous one to have
+    // read them (ncu source page of the first version: the loop's first instruction held 15 % of all stall samples)
+#pragma unroll
+    for (int j = 0; j < (S * S + kThreads - 1) / kThreads; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      if (i < S * S) {
+        const int h = i / S, w = i - h * S;
+        cp_async16(tile + (uint32_t)(h * C::RS + w * 16), xp + h * x.sh + w * x.sw);
+      }
+    }
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < tiles) issue_load(blockIdx.x, tile0);
+  int it = 0;
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
+    const uint32_t tile = tile0 + (uint32_t)(it & 1) * C::TILE;
+    cp_async_wait_all();
+    __syncthreads();                         // tile ti has landed; every warp is done with the other buffer (pass 2 of tile ti - grid)
+    if (ti + (int)gridDim.x < tiles) issue_load(ti + gridDim.x, tile0 + (uint32_t)((it & 1) ^ 1) * C::TILE);
+    // ---- pass 1: real-input DFT along w, whole tile rows per warp, in place -------------------------------------------
+    for (int h = warp; h < S; h += 2 * kWarps) {                 // two rows per step = 2 * MT1 independent accumulators in flight
+      const bool two = h + kWarps < S;                             // (warp-uniform; an odd last step repeats its row, stores once)
+      const uint32_t row0 = tile + (uint32_t)h * C::RS, row1 = tile + (uint32_t)(two ? h + kWarps : h) * C::RS;
+      uint32_t b0[C::KT][2], b1[C::KT][2];
+      load_b<C::KT>(row0, 16u, lane, b0);
+      load_b<C::KT>(row1, 16u, lane, b1);
+      float acc0[C::MT1][4], acc1[C::MT1][4];
+#pragma unroll
+      for (int mt = 0; mt < C::MT1; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc0[mt][i] = 0.f; acc1[mt][i] = 0.f; }
+#pragma unroll
+      for (int kt = 0; kt < C::KT; ++kt) {
+#pragma unroll
+        for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc0[mt], a1[mt][kt], b0[kt][0], b0[kt][1]);
+#pragma unroll
+        for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc1[mt], a1[mt][kt], b1[kt][0], b1[kt][1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < C::MT1; ++mt) {
+        const int k = mt * 8 + g;
+        if (k < C::K1) {
+          const uint32_t o = (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+          st_shared_u32(row0 + o, pack_h2(acc0[mt][0], acc0[mt][1]));            // re, channels 2t, 2t+1
+          st_shared_u32(row0 + o + 16u, pack_h2(acc0[mt][2], acc0[mt][3]));      // im
+          if (two) {
+            st_shared_u32(row1 + o, pack_h2(acc1[mt][0], acc1[mt][1]));
+            st_shared_u32(row1 + o + 16u, pack_h2(acc1[mt][2], acc1[mt][3]));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: complex DFT along h for column k, straight to global ------------------------------------------------
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    __half* op = sp.p + n * sp.sn + 2 * (ch0 + 2 * t);
+    for (int k = warp; k < C::K1; k += kWarps) {
+      float zr[C::MT2][4], zi[C::MT2][4];
+      complex_pass<S>(tile, k, lane, ar, ai, zr, zi);
+#pragma unroll
+      for (int mt = 0; mt < C::MT2; ++mt) {
+        const int kh0 = mt * 16 + g, kh1 = kh0 + 8;
+        if (kh0 < S) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
+        if (kh1 < S) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
+      }
+    }
+  }
+}
+
+// spec [N,S,S/2+1,2C] -> y [N,S,S,C] (+ add); tiles = N * C / 8 (image-major), grid = min(tiles, BPS * #SMs)
+template <int S>
+__global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kernel(View sp, View add, View y, int cblocks, int tiles) {
+  using C = Cfg<S>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_trigger();
+  const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  zero_tiles<S>(tile0);
+  uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT], a2[C::MT2][C::KT2];
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt) {
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+      ar[mt][kt] = g_frag[(C::O_WR + mt * C::KT + kt) * 32 + lane];
+      ai[mt][kt] = g_frag[(C::O_WI + mt * C::KT + kt) * 32 + lane];
+    }
+#pragma unroll
+    for (int kt = 0; kt < C::KT2; ++kt) a2[mt][kt] = g_frag[(C::O_A2 + mt * C::KT2 + kt) * 32 + lane];
+  }
+  __syncthreads();
+  pdl_wait();
+  constexpr int kItems = S * C::K1;          // one item = the 8 channels of one (kh, k): 32 bytes, (re, im) interleaved in global
+  auto issue_load = [&](int ti, uint32_t tile) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    const __half* spp = sp.p + n * sp.sn + 2 * ch0;
+#pragma unroll
+    for (int j = 0; j < (kItems + kThreads - 1) / kThreads; ++j) {      // unrolled: see rfft2_mma_kernel
+      const int i = threadIdx.x + j * kThreads;
+      if (i < kItems) {
+        const int kh = i / C::K1, k = i - kh * C::K1;
+        const __half* src = spp + kh * sp.sh + k * sp.sw;
+        const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
+        cp_async16(d, src);
+        cp_async16(d + 16u, src + 8);
+      }
+    }
+    cp_async_commit();
+  };
+  const bool has_add = add.p != nullptr;
+  if ((int)blockIdx.x < tiles) issue_load(blockIdx.x, tile0);
+  int it = 0;
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
+    const uint32_t tile = tile0 + (uint32_t)(it & 1) * C::TILE;
+    cp_async_wait_all();
+    // de-interleave this thread's own items in place: [c0r c0i .. c7r c7i] -> [c0r .. c7r][c0i .. c7i]
+#pragma unroll 2
+    for (int i = threadIdx.x; i < kItems; i += kThreads) {
+      const int kh = i / C::K1, k = i - kh * C::K1;
+      const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
+      uint4 u0, u1;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0.x), "=r"(u0.y), "=r"(u0.z), "=r"(u0.w) : "r"(d) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u1.x), "=r"(u1.y), "=r"(u1.z), "=r"(u1.w) : "r"(d + 16u) : "memory");
+      st_shared_u4(d, make_uint4(__byte_perm(u0.x, u0.y, 0x5410), __byte_perm(u0.z, u0.w, 0x5410),
+                                 __byte_perm(u1.x, u1.y, 0x5410), __byte_perm(u1.z, u1.w, 0x5410)));
+      st_shared_u4(d + 16u, make_uint4(__byte_perm(u0.x, u0.y, 0x7632), __byte_perm(u0.z, u0.w, 0x7632),
+                                       __byte_perm(u1.x, u1.y, 0x7632), __byte_perm(u1.z, u1.w, 0x7632)));
+    }
+    __syncthreads();                         // tile ti is in place; every warp is done with the other buffer (pass B of tile ti - grid)
+    if (ti + (int)gridDim.x < tiles) issue_load(ti + gridDim.x, tile0 + (uint32_t)((it & 1) ^ 1) * C::TILE);
+    // ---- pass A: inverse complex DFT along kh for column k, in place ---------------------------------------------------
+    for (int k = warp; k < C::K1; k += kWarps) {
+      float zr[C::MT2][4], zi[C::MT2][4];
+      complex_pass<S>(tile, k, lane, ar, ai, zr, zi);
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < C::MT2; ++mt) {
+        const int h0 = mt * 16 + g, h1 = h0 + 8;
+        const uint32_t c0 = tile + (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+        if (h0 < S) {
+          st_shared_u32(c0 + (uint32_t)h0 * C::RS, pack_h2(zr[mt][0], zr[mt][1]));
+          st_shared_u32(c0 + (uint32_t)h0 * C::RS + 16u, pack_h2(zi[mt][0], zi[mt][1]));
+        }
+        if (h1 < S) {
+          st_shared_u32(c0 + (uint32_t)h1 * C::RS, pack_h2(zr[mt][2], zr[mt][3]));
+          st_shared_u32(c0 + (uint32_t)h1 * C::RS + 16u, pack_h2(zi[mt][2], zi[mt][3]));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass B: complex-to-real along w for tile row h (K = (k, re|im)), + residual, to global ---------------------------
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    const __half* ap = has_add ? add.p + n * add.sn + ch0 + 2 * t : nullptr;
+    __half* yp = y.p + n * y.sn + ch0 + 2 * t;
+    uint32_t rn[2][C::MT2][2];
+    auto load_res = [&](int r, int h) {
+#pragma unroll
+      for (int mt = 0; mt < C::MT2; ++mt) {
+        const int w0 = mt * 16 + g, w1 = w0 + 8;
+        rn[r][mt][0] = (has_add && h < S && w0 < S) ? *reinterpret_cast<const uint32_t*>(ap + h * add.sh + w0 * add.sw) : 0u;
+        rn[r][mt][1] = (has_add && h < S && w1 < S) ? *reinterpret_cast<const uint32_t*>(ap + h * add.sh + w1 * add.sw) : 0u;
+      }
+    };
+    load_res(0, warp);
+    load_res(1, warp + kWarps);
+    for (int h = warp; h < S; h += 2 * kWarps) {                 // two rows per step = 2 * MT2 independent accumulators in flight
+      const bool two = h + kWarps < S;                             // (warp-uniform; an odd last step repeats its row, stores once)
+      const int hh[2] = {h, two ? h + kWarps : h};
+      uint32_t rc[2][C::MT2][2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt) { rc[r][mt][0] = rn[r][mt][0]; rc[r][mt][1] = rn[r][mt][1]; }
+      load_res(0, h + 2 * kWarps);                                 // the next step's residual is in flight behind this step's MMAs
+      load_res(1, h + 3 * kWarps);
+      uint32_t b[2][C::KT2][2];
+      load_b<C::KT2>(tile + (uint32_t)hh[0] * C::RS, 16u, lane, b[0]);
+      load_b<C::KT2>(tile + (uint32_t)hh[1] * C::RS, 16u, lane, b[1]);
+      float acc[2][C::MT2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[r][mt][i] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < C::KT2; ++kt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int mt = 0; mt < C::MT2; ++mt) mma16816(acc[r][mt], a2[mt][kt], b[r][kt][0], b[r][kt][1]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt) {
+          const int w0 = mt * 16 + g, w1 = w0 + 8;
+          const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&rc[r][mt][0]));
+          const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&rc[r][mt][1]));
+          if (w0 < S) *reinterpret_cast<uint32_t*>(yp + hh[r] * y.sh + w0 * y.sw) = pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y);
+          if (w1 < S) *reinterpret_cast<uint32_t*>(yp + hh[r] * y.sh + w1 * y.sw) = pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y);
+        }
+      }
+    }
+  }
+}
+
+// ---- host: DFT matrices in A-fragment order ---------------------------------------------------------------------------
+template <typename F>
+static void fill_frags(uint4* dst, int mts, int kts, F f) {
+  for (int mt = 0; mt < mts; ++mt)
+    for (int kt = 0; kt < kts; ++kt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t r[4];
+        for (int i = 0; i < 4; ++i) {       // a0,a1: row g | a2,a3: row g+8 | a4,a5: row g, col +8 | a6,a7: row g+8, col +8
+          const int row = mt * 16 + g + 8 * (i & 1), col = kt * 16 + 2 * t + 8 * (i >> 1);
+          const __half_raw lo = static_cast<__half_raw>(__float2half_rn((float)f(row, col))), hi = static_cast<__half_raw>(__float2half_rn((float)f(row, col + 1)));
+          r[i] = (uint32_t)lo.x | ((uint32_t)hi.x << 16);
+        }
+        dst[(mt * kts + kt) * 32 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+}
+
+template <int S>
+static void build_tables(uint4* tab) {
+  using C = Cfg<S>;
+  const double s = 1.0 / sqrt((double)S), w0 = 2.0 * 3.14159265358979323846 / S;
+  auto cs = [&](int a, int b) { return cos(w0 * ((a * b) % S)) * s; };
+  auto sn = [&](int a, int b) { return sin(w0 * ((a * b) % S)) * s; };
+  // pass 1: row = m-tile of 8 k's, rows 0-7 re, 8-15 im; col = w
+  fill_frags(tab + C::O_F1 * 32, C::MT1, C::KT, [&](int row, int w) {
+    const int k = (row / 16) * 8 + (row % 8), ri = (row % 16) / 8;
+    if (k >= C::K1 || w >= S) return 0.0;
+    return ri ? -sn(k, w) : cs(k, w);
+  });
+  auto in = [&](int a, int b) { return a < S && b < S; };
+  fill_frags(tab + C::O_GR * 32, C::MT2, C::KT, [&](int kh, int h) { return in(kh, h) ? cs(kh, h) : 0.0; });
+  fill_frags(tab + C::O_GI * 32, C::MT2, C::KT, [&](int kh, int h) { return in(kh, h) ? -sn(kh, h) : 0.0; });
+  fill_frags(tab + C::O_WR * 32, C::MT2, C::KT, [&](int h, int kh) { return in(h, kh) ? cs(h, kh) : 0.0; });
+  fill_frags(tab + C::O_WI * 32, C::MT2, C::KT, [&](int h, int kh) { return in(h, kh) ? sn(h, kh) : 0.0; });
+  // c2r: col = (k, ri); Hermitian weights 1 (k = 0, S/2) / 2; sin(0) = sin(pi w) = 0 drops the imaginary parts of DC / Nyquist
+  fill_frags(tab + C::O_A2 * 32, C::MT2, C::KT2, [&](int w, int col) {
+    const int k = col / 2, ri = col % 2;
+    if (w >= S || k >= C::K1) return 0.0;
+    const double ck = (k == 0 || k == S / 2) ? 1.0 : 2.0;
+    return ri ? -ck * sn(k, w) : ck * cs(k, w);
+  });
+}
+
+template <int S>
+static int grid_for(int tiles, int dev) {
+  const int n_sm = sm_count(dev);
+  if (n_sm <= 0) return -1;
+  const int cap = n_sm * blocks_per_sm<S>();
+  return tiles < cap ? tiles : cap;
+}
+template <int S>
+static int launch_r(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
+  static DeviceOnce attr;
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  constexpr int smem = 2 * Cfg<S>::TILE;
+  if (attr.needed(dev)) {
+    S2V_CUDA_TRY(cudaFuncSetAttribute(rfft2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr.mark(dev);
+  }
+  const int cblocks = x->c / 8, tiles = cblocks * x->n, grid = grid_for<S>(tiles, dev);
+  if (grid <= 0) return S2V_ECUDA;
+  S2V_CUDA_TRY(launch_pdl(rfft2_mma_kernel<S>, dim3(grid), kThreads, (size_t)smem, st, mk(x), mk(sp), cblocks, tiles));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+template <int S>
+static int launch_i(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
+  static DeviceOnce attr;
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  constexpr int smem = 2 * Cfg<S>::TILE;
+  if (attr.needed(dev)) {
+    S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr.mark(dev);
+  }
+  const int cblocks = y->c / 8, tiles = cblocks * y->n, grid = grid_for<S>(tiles, dev);
+  if (grid <= 0) return S2V_ECUDA;
+  S2V_CUDA_TRY(launch_pdl(irfft2_mma_kernel<S>, dim3(grid), kThreads, (size_t)smem, st, mk(sp), mk(add), mk(y), cblocks, tiles));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
+}  // namespace fftmma
+
+// ---- entry points used by fft2d.cu ------------------------------------------------------------------------------------
+int fft_mma_init() {
+  static uint4 host[fftmma::kFragsTotal * 32];     // rebuilt per call (per device): same values every time
+  fftmma::build_tables<48>(host);
+  fftmma::build_tables<24>(host);
+  fftmma::build_tables<12>(host);
+  if (cudaMemcpyToSymbol(fftmma::g_frag, host, sizeof(host)) != cudaSuccess) return S2V_ECUDA;
+  return S2V_OK;
+}
+bool fft_mma_supports(int s) { return s == 48 || s == 24 || s == 12; }
+int rfft2_mma(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
+  switch (x->h) {
+    case 48: return fftmma::launch_r<48>(x, sp, st);
+    case 24: return fftmma::launch_r<24>(x, sp, st);
+    case 12: return fftmma::launch_r<12>(x, sp, st);
+  }
+  return S2V_EINVAL;
+}
+int irfft2_mma(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
+  switch (y->h) {
+    case 48: return fftmma::launch_i<48>(sp, add, y, st);
+    case 24: return fftmma::launch_i<24>(sp, add, y, st);
+    case 12: return fftmma::launch_i<12>(sp, add, y, st);
+  }
+  return S2V_EINVAL;
+}
+
+}  // namespace s2v
