@@ -1,8 +1,8 @@
 """Development: lane-level CPU emulation of csrc/fft2d_mma.cu (fragment tables, ldmatrix.trans addressing, mma.m16n8k16 register
 layouts, the in-place tile passes) against numpy's FFT.  No GPU needed:
 
-    nvcc ... -o /tmp/emu/dump /tmp/emu/dump.cu   (a main() that calls fftmma::build_tables and writes /tmp/emu/frag.bin)
-    python tools/emu_fft_mma.py /tmp/emu/frag.bin
+    nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr -o /tmp/dump tools/dump_fft_frags.cu
+    /tmp/dump /tmp/frag.bin && python tools/emu_fft_mma.py /tmp/frag.bin          (tests/test_fft_mma_emulation.py does exactly this)
 
 It transcribes the kernels' index arithmetic line by line; what it proves is that the arithmetic + the PTX fragment layouts as
 documented give the transform, not that the hardware was programmed correctly (tests/test_gpu_kernels.py::test_fft2 does that)."""
