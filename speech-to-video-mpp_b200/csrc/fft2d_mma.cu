@@ -113,24 +113,44 @@ __device__ __forceinline__ void complex_pass(uint32_t tile, int k, int lane, con
   }
 }
 
-// Blocks are PERSISTENT: BPS blocks per SM, block b takes tiles b, b + grid, ...  The DFT matrices stay in registers for the
-// block's lifetime (48 x 48: 120 registers of A fragments), the tile buffer is double-buffered and the next tile's cp.async
-// loads are issued before the current tile's first pass, so a block's load latency hides behind its own MMAs.
-// (First version, one block per tile with 3-4 blocks per SM: 21.4 / 32.2 us for rfft2 / irfft2 48 x 48 at B = 128 against 23.6 /
-// 37.1 us of the register FFT - ncu: tensor pipe 44 % / 29 % active while resident, long_scoreboard the top stall: every block
-// paid the tile's DRAM latency, two L2 round trips for its tables and three barriers in sequence.)
-template <int S> constexpr int blocks_per_sm() { return S == 48 ? 2 : S == 24 ? 4 : 8; }
+// Blocks are PERSISTENT (BPS blocks per SM, block b takes tiles b, b + grid, ...) and register-light: the A fragments of the DFT
+// matrices are copied to shared memory once per block and re-read from there in front of each pass (12 - 18 LDS.128 per thread and
+// tile), so a thread needs ~120 registers and FOUR 48 x 48 blocks (16 warps) share an SM, each with one 39 KB tile + 15 KB of tables.
+// Versions measured on B200 (us for rfft2 / irfft2, 48 x 48 x 48 channels; register FFT of fft2d.cu: 23.6 / 37.1 at B = 128, 53.2 /
+// 75.9 at B = 256; profiles/r2c_summary.md):
+//   v1  one block per tile, tables from L2 in front of each pass, 3 - 4 blocks per SM          21.4 / 32.2 (B = 128)
+//       ncu: tensor pipe 44 % / 29 % active while resident, long_scoreboard the top stall (tile DRAM latency + two L2 round trips
+//       for the tables + the rolled cp.async loop, whose address registers every LDGSTS has to release first: 15 % of the samples)
+//   v2  persistent, double-buffered tile, all tables resident in 250 registers, 2 blocks per SM  24.4 / 36.0 (B = 128), 45.0 / 67.5 (B = 256)
+//       ncu: 7.2 stall cycles per issued instruction with two warps per scheduler, tensor pipe 41 % / 27 %
+//   v3  this one
+template <int S> constexpr int blocks_per_sm() { return S == 48 ? 4 : S == 24 ? 6 : 8; }
 
-template <int S>
-__device__ __forceinline__ void zero_tiles(uint32_t tile) {
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < 2 * Cfg<S>::TILE / 16; i += kThreads) st_shared_u4(tile + (uint32_t)i * 16u, z);
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// block prologue: zero the tile (pads, K-padding rows and the tail stay zero for the block's lifetime) and copy NF fragments
+// [fragment][lane] of the table, starting at fragment F0, behind it
+template <int S>
+__device__ __forceinline__ void block_prologue(uint32_t tile, int f0, int nf) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < Cfg<S>::TILE / 16; i += kThreads) st_shared_u4(tile + (uint32_t)i * 16u, z);
+  for (int i = threadIdx.x; i < nf * 32; i += kThreads) st_shared_u4(tile + Cfg<S>::TILE + (uint32_t)i * 16u, g_frag[f0 * 32 + i]);
+}
+template <int MT, int KTN>
+__device__ __forceinline__ void load_a(uint32_t tab, int frag0, int lane, uint4 (&a)[MT][KTN]) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < KTN; ++kt) a[mt][kt] = ld_shared_u4(tab + (uint32_t)((frag0 + mt * KTN + kt) * 32 + lane) * 16u);
+}
 
 // x [N,S,S,C] -> spec [N,S,S/2+1,2C]; tiles = N * C / 8 (image-major), grid = min(tiles, BPS * #SMs)
 template <int S>
@@ -138,82 +158,71 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
   using C = Cfg<S>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_trigger();
-  const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t tile = (uint32_t)__cvta_generic_to_shared(smem_raw), tab = tile + C::TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  zero_tiles<S>(tile0);
-  uint4 a1[C::MT1][C::KT], ar[C::MT2][C::KT], ai[C::MT2][C::KT];     // constant tables: fetched ahead of the PDL wait
-#pragma unroll
-  for (int mt = 0; mt < C::MT1; ++mt)
-#pragma unroll
-    for (int kt = 0; kt < C::KT; ++kt) a1[mt][kt] = g_frag[(C::O_F1 + mt * C::KT + kt) * 32 + lane];
-#pragma unroll
-  for (int mt = 0; mt < C::MT2; ++mt)
-#pragma unroll
-    for (int kt = 0; kt < C::KT; ++kt) {
-      ar[mt][kt] = g_frag[(C::O_GR + mt * C::KT + kt) * 32 + lane];
-      ai[mt][kt] = g_frag[(C::O_GI + mt * C::KT + kt) * 32 + lane];
-    }
+  block_prologue<S>(tile, C::O_F1, C::N_F1 + 2 * C::N_G);       // constant tables: copied ahead of the PDL wait
   __syncthreads();
   pdl_wait();
-  auto issue_load = [&](int ti, uint32_t tile) {
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x) {
     const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
-    const __half* xp = x.p + n * x.sn + ch0;
-    // fully unrolled: a rolled loop re-uses the address registers, and every LDGSTS then waits for the previous one to have
-    // read them (ncu source page of the first version: the loop's first instruction held 15 % of all stall samples)
+    {
+      const __half* xp = x.p + n * x.sn + ch0;
+      // fully unrolled: a rolled loop re-uses the address registers, and every LDGSTS then waits for the previous one to have read them
 #pragma unroll
-    for (int j = 0; j < (S * S + kThreads - 1) / kThreads; ++j) {
-      const int i = threadIdx.x + j * kThreads;
-      if (i < S * S) {
-        const int h = i / S, w = i - h * S;
-        cp_async16(tile + (uint32_t)(h * C::RS + w * 16), xp + h * x.sh + w * x.sw);
+      for (int j = 0; j < (S * S + kThreads - 1) / kThreads; ++j) {
+        const int i = threadIdx.x + j * kThreads;
+        if (i < S * S) {
+          const int h = i / S, w = i - h * S;
+          cp_async16(tile + (uint32_t)(h * C::RS + w * 16), xp + h * x.sh + w * x.sw);
+        }
       }
+      cp_async_commit();
     }
-    cp_async_commit();
-  };
-  if ((int)blockIdx.x < tiles) issue_load(blockIdx.x, tile0);
-  int it = 0;
-  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
-    const uint32_t tile = tile0 + (uint32_t)(it & 1) * C::TILE;
-    cp_async_wait_all();
-    __syncthreads();                         // tile ti has landed; every warp is done with the other buffer (pass 2 of tile ti - grid)
-    if (ti + (int)gridDim.x < tiles) issue_load(ti + gridDim.x, tile0 + (uint32_t)((it & 1) ^ 1) * C::TILE);
-    // ---- pass 1: real-input DFT along w, whole tile rows per warp, in place -------------------------------------------
-    for (int h = warp; h < S; h += 2 * kWarps) {                 // two rows per step = 2 * MT1 independent accumulators in flight
-      const bool two = h + kWarps < S;                             // (warp-uniform; an odd last step repeats its row, stores once)
-      const uint32_t row0 = tile + (uint32_t)h * C::RS, row1 = tile + (uint32_t)(two ? h + kWarps : h) * C::RS;
-      uint32_t b0[C::KT][2], b1[C::KT][2];
-      load_b<C::KT>(row0, 16u, lane, b0);
-      load_b<C::KT>(row1, 16u, lane, b1);
-      float acc0[C::MT1][4], acc1[C::MT1][4];
+    {
+      uint4 a1[C::MT1][C::KT];
+      load_a<C::MT1, C::KT>(tab, 0, lane, a1);
+      cp_async_wait_all();
+      __syncthreads();
+      // ---- pass 1: real-input DFT along w, whole tile rows per warp, in place -----------------------------------------
+      for (int h = warp; h < S; h += 2 * kWarps) {               // two rows per step = 2 * MT1 independent accumulators in flight
+        const bool two = h + kWarps < S;                           // (warp-uniform; an odd last step repeats its row, stores once)
+        const uint32_t row0 = tile + (uint32_t)h * C::RS, row1 = tile + (uint32_t)(two ? h + kWarps : h) * C::RS;
+        uint32_t b0[C::KT][2], b1[C::KT][2];
+        load_b<C::KT>(row0, 16u, lane, b0);
+        load_b<C::KT>(row1, 16u, lane, b1);
+        float acc0[C::MT1][4], acc1[C::MT1][4];
 #pragma unroll
-      for (int mt = 0; mt < C::MT1; ++mt)
+        for (int mt = 0; mt < C::MT1; ++mt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc0[mt][i] = 0.f; acc1[mt][i] = 0.f; }
+          for (int i = 0; i < 4; ++i) { acc0[mt][i] = 0.f; acc1[mt][i] = 0.f; }
 #pragma unroll
-      for (int kt = 0; kt < C::KT; ++kt) {
+        for (int kt = 0; kt < C::KT; ++kt) {
 #pragma unroll
-        for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc0[mt], a1[mt][kt], b0[kt][0], b0[kt][1]);
+          for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc0[mt], a1[mt][kt], b0[kt][0], b0[kt][1]);
 #pragma unroll
-        for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc1[mt], a1[mt][kt], b1[kt][0], b1[kt][1]);
-      }
-      __syncwarp();
+          for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc1[mt], a1[mt][kt], b1[kt][0], b1[kt][1]);
+        }
+        __syncwarp();
 #pragma unroll
-      for (int mt = 0; mt < C::MT1; ++mt) {
-        const int k = mt * 8 + g;
-        if (k < C::K1) {
-          const uint32_t o = (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
-          st_shared_u32(row0 + o, pack_h2(acc0[mt][0], acc0[mt][1]));            // re, channels 2t, 2t+1
-          st_shared_u32(row0 + o + 16u, pack_h2(acc0[mt][2], acc0[mt][3]));      // im
-          if (two) {
-            st_shared_u32(row1 + o, pack_h2(acc1[mt][0], acc1[mt][1]));
-            st_shared_u32(row1 + o + 16u, pack_h2(acc1[mt][2], acc1[mt][3]));
+        for (int mt = 0; mt < C::MT1; ++mt) {
+          const int k = mt * 8 + g;
+          if (k < C::K1) {
+            const uint32_t o = (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+            st_shared_u32(row0 + o, pack_h2(acc0[mt][0], acc0[mt][1]));            // re, channels 2t, 2t+1
+            st_shared_u32(row0 + o + 16u, pack_h2(acc0[mt][2], acc0[mt][3]));      // im
+            if (two) {
+              st_shared_u32(row1 + o, pack_h2(acc1[mt][0], acc1[mt][1]));
+              st_shared_u32(row1 + o + 16u, pack_h2(acc1[mt][2], acc1[mt][3]));
+            }
           }
         }
       }
     }
+    uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT];
+    load_a<C::MT2, C::KT>(tab, C::N_F1, lane, ar);
+    load_a<C::MT2, C::KT>(tab, C::N_F1 + C::N_G, lane, ai);
     __syncthreads();
     // ---- pass 2: complex DFT along h for column k, straight to global ------------------------------------------------
-    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
     __half* op = sp.p + n * sp.sn + 2 * (ch0 + 2 * t);
     for (int k = warp; k < C::K1; k += kWarps) {
       float zr[C::MT2][4], zi[C::MT2][4];
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
         if (kh1 < S) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
       }
     }
+    __syncthreads();                           // every warp is done reading the tile before the next tile's loads land in it
   }
 }
 
@@ -234,82 +244,71 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kerne
   using C = Cfg<S>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_trigger();
-  const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t tile = (uint32_t)__cvta_generic_to_shared(smem_raw), tab = tile + C::TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  zero_tiles<S>(tile0);
-  uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT], a2[C::MT2][C::KT2];
-#pragma unroll
-  for (int mt = 0; mt < C::MT2; ++mt) {
-#pragma unroll
-    for (int kt = 0; kt < C::KT; ++kt) {
-      ar[mt][kt] = g_frag[(C::O_WR + mt * C::KT + kt) * 32 + lane];
-      ai[mt][kt] = g_frag[(C::O_WI + mt * C::KT + kt) * 32 + lane];
-    }
-#pragma unroll
-    for (int kt = 0; kt < C::KT2; ++kt) a2[mt][kt] = g_frag[(C::O_A2 + mt * C::KT2 + kt) * 32 + lane];
-  }
+  block_prologue<S>(tile, C::O_WR, 2 * C::N_G + C::N_A2);
   __syncthreads();
   pdl_wait();
   constexpr int kItems = S * C::K1;          // one item = the 8 channels of one (kh, k): 32 bytes, (re, im) interleaved in global
-  auto issue_load = [&](int ti, uint32_t tile) {
-    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
-    const __half* spp = sp.p + n * sp.sn + 2 * ch0;
-#pragma unroll
-    for (int j = 0; j < (kItems + kThreads - 1) / kThreads; ++j) {      // unrolled: see rfft2_mma_kernel
-      const int i = threadIdx.x + j * kThreads;
-      if (i < kItems) {
-        const int kh = i / C::K1, k = i - kh * C::K1;
-        const __half* src = spp + kh * sp.sh + k * sp.sw;
-        const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
-        cp_async16(d, src);
-        cp_async16(d + 16u, src + 8);
-      }
-    }
-    cp_async_commit();
-  };
   const bool has_add = add.p != nullptr;
-  if ((int)blockIdx.x < tiles) issue_load(blockIdx.x, tile0);
-  int it = 0;
-  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
-    const uint32_t tile = tile0 + (uint32_t)(it & 1) * C::TILE;
-    cp_async_wait_all();
-    // de-interleave this thread's own items in place: [c0r c0i .. c7r c7i] -> [c0r .. c7r][c0i .. c7i]
-#pragma unroll 2
-    for (int i = threadIdx.x; i < kItems; i += kThreads) {
-      const int kh = i / C::K1, k = i - kh * C::K1;
-      const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
-      uint4 u0, u1;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0.x), "=r"(u0.y), "=r"(u0.z), "=r"(u0.w) : "r"(d) : "memory");
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u1.x), "=r"(u1.y), "=r"(u1.z), "=r"(u1.w) : "r"(d + 16u) : "memory");
-      st_shared_u4(d, make_uint4(__byte_perm(u0.x, u0.y, 0x5410), __byte_perm(u0.z, u0.w, 0x5410),
-                                 __byte_perm(u1.x, u1.y, 0x5410), __byte_perm(u1.z, u1.w, 0x5410)));
-      st_shared_u4(d + 16u, make_uint4(__byte_perm(u0.x, u0.y, 0x7632), __byte_perm(u0.z, u0.w, 0x7632),
-                                       __byte_perm(u1.x, u1.y, 0x7632), __byte_perm(u1.z, u1.w, 0x7632)));
-    }
-    __syncthreads();                         // tile ti is in place; every warp is done with the other buffer (pass B of tile ti - grid)
-    if (ti + (int)gridDim.x < tiles) issue_load(ti + gridDim.x, tile0 + (uint32_t)((it & 1) ^ 1) * C::TILE);
-    // ---- pass A: inverse complex DFT along kh for column k, in place ---------------------------------------------------
-    for (int k = warp; k < C::K1; k += kWarps) {
-      float zr[C::MT2][4], zi[C::MT2][4];
-      complex_pass<S>(tile, k, lane, ar, ai, zr, zi);
-      __syncwarp();
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    {
+      const __half* spp = sp.p + n * sp.sn + 2 * ch0;
 #pragma unroll
-      for (int mt = 0; mt < C::MT2; ++mt) {
-        const int h0 = mt * 16 + g, h1 = h0 + 8;
-        const uint32_t c0 = tile + (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
-        if (h0 < S) {
-          st_shared_u32(c0 + (uint32_t)h0 * C::RS, pack_h2(zr[mt][0], zr[mt][1]));
-          st_shared_u32(c0 + (uint32_t)h0 * C::RS + 16u, pack_h2(zi[mt][0], zi[mt][1]));
+      for (int j = 0; j < (kItems + kThreads - 1) / kThreads; ++j) {      // unrolled: see rfft2_mma_kernel
+        const int i = threadIdx.x + j * kThreads;
+        if (i < kItems) {
+          const int kh = i / C::K1, k = i - kh * C::K1;
+          const __half* src = spp + kh * sp.sh + k * sp.sw;
+          const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
+          cp_async16(d, src);
+          cp_async16(d + 16u, src + 8);
         }
-        if (h1 < S) {
-          st_shared_u32(c0 + (uint32_t)h1 * C::RS, pack_h2(zr[mt][2], zr[mt][3]));
-          st_shared_u32(c0 + (uint32_t)h1 * C::RS + 16u, pack_h2(zi[mt][2], zi[mt][3]));
+      }
+      cp_async_commit();
+    }
+    {
+      uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT];
+      load_a<C::MT2, C::KT>(tab, 0, lane, ar);
+      load_a<C::MT2, C::KT>(tab, C::N_G, lane, ai);
+      cp_async_wait_all();
+      // de-interleave this thread's own items in place: [c0r c0i .. c7r c7i] -> [c0r .. c7r][c0i .. c7i]
+#pragma unroll 2
+      for (int i = threadIdx.x; i < kItems; i += kThreads) {
+        const int kh = i / C::K1, k = i - kh * C::K1;
+        const uint32_t d = tile + (uint32_t)(kh * C::RS + k * 32);
+        const uint4 u0 = ld_shared_u4(d), u1 = ld_shared_u4(d + 16u);
+        st_shared_u4(d, make_uint4(__byte_perm(u0.x, u0.y, 0x5410), __byte_perm(u0.z, u0.w, 0x5410),
+                                   __byte_perm(u1.x, u1.y, 0x5410), __byte_perm(u1.z, u1.w, 0x5410)));
+        st_shared_u4(d + 16u, make_uint4(__byte_perm(u0.x, u0.y, 0x7632), __byte_perm(u0.z, u0.w, 0x7632),
+                                         __byte_perm(u1.x, u1.y, 0x7632), __byte_perm(u1.z, u1.w, 0x7632)));
+      }
+      __syncthreads();
+      // ---- pass A: inverse complex DFT along kh for column k, in place -------------------------------------------------
+      for (int k = warp; k < C::K1; k += kWarps) {
+        float zr[C::MT2][4], zi[C::MT2][4];
+        complex_pass<S>(tile, k, lane, ar, ai, zr, zi);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt) {
+          const int h0 = mt * 16 + g, h1 = h0 + 8;
+          const uint32_t c0 = tile + (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+          if (h0 < S) {
+            st_shared_u32(c0 + (uint32_t)h0 * C::RS, pack_h2(zr[mt][0], zr[mt][1]));
+            st_shared_u32(c0 + (uint32_t)h0 * C::RS + 16u, pack_h2(zi[mt][0], zi[mt][1]));
+          }
+          if (h1 < S) {
+            st_shared_u32(c0 + (uint32_t)h1 * C::RS, pack_h2(zr[mt][2], zr[mt][3]));
+            st_shared_u32(c0 + (uint32_t)h1 * C::RS + 16u, pack_h2(zi[mt][2], zi[mt][3]));
+          }
         }
       }
     }
+    uint4 a2[C::MT2][C::KT2];
+    load_a<C::MT2, C::KT2>(tab, 2 * C::N_G, lane, a2);
     __syncthreads();
     // ---- pass B: complex-to-real along w for tile row h (K = (k, re|im)), + residual, to global ---------------------------
-    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
     const __half* ap = has_add ? add.p + n * add.sn + ch0 + 2 * t : nullptr;
     __half* yp = y.p + n * y.sn + ch0 + 2 * t;
     uint32_t rn[2][C::MT2][2];
@@ -362,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kerne
         }
       }
     }
+    __syncthreads();                           // every warp is done reading the tile before the next tile's loads land in it
   }
 }
 
@@ -420,7 +420,7 @@ static int launch_r(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
   static DeviceOnce attr;
   const int dev = current_device();
   if (dev < 0) return S2V_ECUDA;
-  constexpr int smem = 2 * Cfg<S>::TILE;
+  constexpr int smem = Cfg<S>::TILE + (Cfg<S>::N_F1 + 2 * Cfg<S>::N_G) * 512;
   if (attr.needed(dev)) {
     S2V_CUDA_TRY(cudaFuncSetAttribute(rfft2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr.mark(dev);
@@ -436,7 +436,7 @@ static int launch_i(const s2v_view* sp, const s2v_view* add, const s2v_view* y, 
   static DeviceOnce attr;
   const int dev = current_device();
   if (dev < 0) return S2V_ECUDA;
-  constexpr int smem = 2 * Cfg<S>::TILE;
+  constexpr int smem = Cfg<S>::TILE + (2 * Cfg<S>::N_G + Cfg<S>::N_A2) * 512;
   if (attr.needed(dev)) {
     S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr.mark(dev);
