@@ -168,7 +168,12 @@ int s2v_compose_pred_u8(const float* pred, const float* img_batch, const float* 
  * bilinear resize of the grid, F.grid_sample bilinear/zeros/align_corners=False)
  * as ONE kernel.  src/out float32 NCHW [B,C,H,W]; flow float32 NCHW [B,2,h,w].
  * out16 (nullable): additionally writes the warped image as fp16 NHWC into the
- * view's channels [c_off, c_off+C) (feeds DNet's editing net).                */
+ * view's channels [c_off, c_off+C) (feeds DNet's editing net).
+ * c_off | S2V_WARP_PACK_SRC (needs c_off == C, 2 C <= 8, an 8-channel-aligned
+ * texel at channel 0): the same launch also writes src itself (fp16) into channels
+ * [0, C) and zeros into [2 C, 8), i.e. the whole 16-byte texel [src | warp | 0]
+ * of models/DNet.py:104 (torch.cat([input_image, warp_image], 1)) in one store. */
+#define S2V_WARP_PACK_SRC 0x100
 int s2v_flow_warp_f32(const float* src, const float* flow, float* out,
                       int B, int C, int H, int W, int h, int w,
                       const s2v_view* out16, int c_off, void* stream);

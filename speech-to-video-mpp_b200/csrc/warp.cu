@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) flow_warp_kernel(const f
 // before any arithmetic.  Arithmetic (operation order, rounding) is identical to the kernel above.
 constexpr int kW4BX = 32, kW4BY = 4, kW4Cells = 16 * 12;      // block = 32 x 16 pixels
 
+// PACK (C <= 4, c_off == C): the fp16 side output is the whole 8-channel texel [src | warp | 0] in one 16-byte store (the source
+// pixel is read once more, coalesced) - replaces a separate pack launch and three 2-byte partial-sector stores per pixel.
+template <bool PACK>
 __global__ void __launch_bounds__(kW4BX * kW4BY) flow_warp4_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                                   float* __restrict__ out, int C, int H, int W, int h, int w,
                                                                   View o16, int c_off, float sch, float scw, float inv_wm1,
@@ -215,6 +218,50 @@ __global__ void __launch_bounds__(kW4BX * kW4BY) flow_warp4_kernel(const float* 
   const int po = Y0 * W + X;
   float* ob = out + (size_t)b * C * plane + po;
   __half* p16 = o16.p ? o16.p + (size_t)b * o16.sn + (size_t)Y0 * o16.sh + (size_t)X * o16.sw + c_off : nullptr;
+  if (PACK) {                                      // C <= 4: every plane's gathers in flight at once, one texel store per pixel
+    float v[4][4][4], sv[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) {
+        const float* sp = sb + c * plane;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          sv[c][p] = __ldg(sp + po + p * W);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v[c][p][t] = __ldg(sp + off[p][t]);
+        }
+      }
+    float aw[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {               // same accumulation order as the reference kernel: nw, ne, sw, se
+          float a = v[c][p][0] * wt[p][0];
+          a += v[c][p][1] * wt[p][1];
+          a += v[c][p][2] * wt[p][2];
+          a += v[c][p][3] * wt[p][3];
+          ob[c * plane + p * W] = a;
+          aw[c][p] = a;
+        }
+      }
+    __half* tp = p16 - c_off;                       // channel 0 of the texel (16-byte aligned: checked on the host)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                 // slot i = src channel i (i < C), warp channel i - C (C <= i < 2 C), else 0
+        float val = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < C && i == c) val = sv[c][p];
+          if (c < C && i == C + c) val = aw[c][p];
+        }
+        f[i] = val;
+      }
+      st_h8(tp + (size_t)p * o16.sh, f_to_h8(f));
+    }
+  } else {
   for (int c0 = 0; c0 < C; c0 += 3) {              // 3 planes at a time: 48 gathers in flight
     float v[3][4][4];
 #pragma unroll
@@ -239,6 +286,7 @@ __global__ void __launch_bounds__(kW4BX * kW4BY) flow_warp4_kernel(const float* 
           if (p16) p16[(size_t)p * o16.sh + c0 + c] = __float2half_rn(a);
         }
       }
+  }
   }
 }
 
@@ -288,16 +336,27 @@ extern "C" int s2v_flow_warp_f32(const float* src, const float* flow, float* out
   if (B == 0) return S2V_OK;
   if (!src || !flow || !out || B < 0 || C <= 0 || H <= 0 || W <= 0 || h < 2 || w < 2) return S2V_EINVAL;
   if (B > 65535 || H > 65535) return S2V_EINVAL;
+  const bool pack = (c_off & S2V_WARP_PACK_SRC) != 0;
+  c_off &= ~S2V_WARP_PACK_SRC;
   View o16 = mk(out16);
   if (out16 && out16->ptr && (out16->n < B || out16->h != H || out16->w != W || c_off + C > out16->c)) return S2V_EINVAL;
+  if (pack && (!out16 || !out16->ptr || !view_ok(out16) || c_off != C || 2 * C > 8 || out16->c < 8)) return S2V_EINVAL;
   const float sch = (float)h / (float)H, scw = (float)w / (float)W;
   const bool fits4 = ((int)(scw * kW4BX) + 3) * ((int)(sch * (kW4BY * 4)) + 3) <= kW4Cells;
   if (!(h == H && w == W) && H % 4 == 0 && fits4 && (long long)C * H * W < (1ll << 31) && !getenv("S2V_WARP1")) {
     dim3 grid(ceil_div(W, kW4BX), ceil_div(H, kW4BY * 4), B);
-    launch_pdl(flow_warp4_kernel, grid, dim3(kW4BX, kW4BY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16, c_off, sch, scw,
-               1.f / (float)(w - 1), 1.f / (float)(h - 1));
+    if (pack)
+      S2V_CUDA_TRY(launch_pdl(flow_warp4_kernel<true>, grid, dim3(kW4BX, kW4BY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16,
+                              c_off, sch, scw, 1.f / (float)(w - 1), 1.f / (float)(h - 1)));
+    else
+      S2V_CUDA_TRY(launch_pdl(flow_warp4_kernel<false>, grid, dim3(kW4BX, kW4BY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16,
+                              c_off, sch, scw, 1.f / (float)(w - 1), 1.f / (float)(h - 1)));
     S2V_CHECK_LAUNCH();
     return S2V_OK;
+  }
+  if (pack) {   // geometries the 4-pixel kernel does not take: the texel is written by the pack launch + the partial side output
+    const int rc = s2v_pack_nchw_f32(src, B, C, H, W, (int64_t)C * H * W, out16, 0, 8, 1.f, 0.f, stream);
+    if (rc != S2V_OK) return rc;
   }
   dim3 grid(ceil_div(W, kWarpBX), ceil_div(H, kWarpBY), B);
   launch_pdl(flow_warp_kernel, grid, dim3(kWarpBX, kWarpBY), 0, (cudaStream_t)stream, src, flow, out, C, H, W, h, w, o16, c_off);

@@ -262,8 +262,8 @@ class DNetEngine(EngineBase):
             io["fake"] = fake
             xp = buf("ed.in8p", (B, 262, 264, 8), zero=True)          # stem input, padded by 3: [img | warp | 0 0]
             inter = xp[:, 3:259, 3:259, :]
-            plan.add(ops.op_pack(lib, img, inter, 0, 3))
-            plan.add(ops.op_flow_warp(lib, img, flow, warp, inter, 3))
+            # torch.cat([input_image, warp_image], 1) (DNet.py:104) as ONE 16-byte texel store per pixel from the warp kernel itself
+            plan.add(ops.op_flow_warp(lib, img, flow, warp, inter, 3, pack_src=True))
             win = torch.as_strided(xp, (B, 262, 256, 64), (xp.stride(0), xp.stride(1), 8, 1))
             p = e + ".encoder.first.model"
             raw = buf("ed.raw0", (B, 256, 256, 64))

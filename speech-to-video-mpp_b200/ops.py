@@ -425,11 +425,18 @@ def op_mean_over_w(lib, x, y) -> Op:
     return Op("mean_over_w", lib.s2v_mean_over_w, (C.byref(vx), C.byref(vy)), (vx, vy, x, y))
 
 
-def op_flow_warp(lib, src, flow, out, out16=None, c_off=0) -> Op:
+WARP_PACK_SRC = 0x100     # include/s2v.h: S2V_WARP_PACK_SRC
+
+
+def op_flow_warp(lib, src, flow, out, out16=None, c_off=0, pack_src=False) -> Op:
+    """pack_src: the launch writes the whole 8-channel fp16 texel [src | warp | 0] of out16 (c_off == C), not only the warp channels."""
     b, c, h, w = src.shape
     fh, fw = flow.shape[2], flow.shape[3]
     v16 = view(out16) if out16 is not None else null_view()
-    return Op("flow_warp", lib.s2v_flow_warp_f32, (_ptr(src), _ptr(flow), _ptr(out), b, c, h, w, fh, fw, C.byref(v16), c_off),
+    if pack_src:
+        assert out16 is not None and c_off == c and src.is_contiguous()
+    return Op("flow_warp", lib.s2v_flow_warp_f32,
+              (_ptr(src), _ptr(flow), _ptr(out), b, c, h, w, fh, fw, C.byref(v16), c_off | (WARP_PACK_SRC if pack_src else 0)),
               (src, flow, out, out16, v16))
 
 

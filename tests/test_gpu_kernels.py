@@ -52,6 +52,29 @@ def test_flow_warp_vs_oracle_and_golden(G):
     assert side[..., :3].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("hw,fhw", [(256, 64), (32, 32)])
+def test_flow_warp_texel_pack_equals_pack_then_warp(G, hw, fhw):
+    """S2V_WARP_PACK_SRC (DNet's stem input torch.cat([input_image, warp_image], 1), models/DNet.py:104): the warp launch that also
+    writes the source into the texel gives bit for bit what the separate pack launch + the plain warp launch give - in the 4-pixel
+    kernel (256 / 64, DNet's geometry) and in the fallback (same-size grid)."""
+    lib = G.lib()
+    torch.manual_seed(11)
+    s = (torch.rand(3, 3, hw, hw, device="cuda") * 2 - 1).contiguous()
+    fl = torch.randn(3, 2, fhw, fhw, device="cuda") * 3
+    pad = torch.full((3, hw + 6, hw + 8, 8), 7.0, dtype=torch.float16, device="cuda")      # a padded stem buffer: strided interior view
+    a, b = pad.clone(), pad.clone()
+    ia, ib = a[:, 3:3 + hw, 3:3 + hw, :], b[:, 3:3 + hw, 3:3 + hw, :]
+    oa, ob = torch.empty_like(s), torch.empty_like(s)
+    G.ops.op_pack(lib, s, ia, 0, 8).run()
+    G.ops.op_flow_warp(lib, s, fl, oa, ia, 3).run()
+    G.ops.op_flow_warp(lib, s, fl, ob, ib, 3, pack_src=True).run()
+    torch.cuda.synchronize()
+    assert torch.equal(oa, ob)
+    assert torch.equal(a, b)
+    assert torch.equal(ib[..., :3].permute(0, 3, 1, 2), s.half()) and ib[..., 6:].abs().max().item() == 0
+    assert torch.equal(b[:, :3], pad[:, :3]) and torch.equal(b[:, :, :3], pad[:, :, :3])       # the border is untouched
+
+
 def test_mel_vs_oracle(G):
     from oracle import mel as omel, synth
     from s2v_b200.futils import audio
