@@ -6,8 +6,11 @@
 // HBM peak).  A 48-point DFT is a 48 x 48 matrix: with the channels as the GEMM's N dimension (fp16 channels-last tensors are
 // already [.., K index, channel]) both passes of the 2-D transform are [M <= 64] x [K <= 64] constant matrices times the tile,
 // 0.76 MFLOP per image-channel on mma.sync.m16n8k16 (fp16 operands, fp32 accumulate) = 5 x fewer issued instructions, and the
-// tile needs 39 KB of shared memory instead of 154 KB, so three blocks per SM overlap their load / compute / store phases.
-// The contraction sizes are far below a 128-row tcgen05 tile and the operands change role between the two passes (the
+// tile needs 39 KB of shared memory instead of 154 KB, so four blocks per SM overlap their load / compute / store phases.
+// STATUS: parity-tested (tests/test_gpu_kernels.py::test_fft2_mma_path, CPU emulation in tests/test_fft_mma_emulation.py) and
+// measured EQUAL to the register FFT (profiles/r2c_summary.md), hence opt-in (S2V_FFT_MMA): an 8-channel tile is a 16-byte slice of
+// every pixel, one LDGSTS.128 of a warp touches 32 cache lines and one STG.64 eight, and those L1TEX line accesses - not the MMAs -
+// set its time.  The contraction sizes are far below a 128-row tcgen05 tile and the operands change role between the two passes (the
 // accumulator of pass 1 is the B operand of pass 2), which is what warp-level mma + ldmatrix.trans is for.
 //
 // One block (4 warps) = one image n x 8 channels.  The tile lives in shared memory as rows of RS = 32 (S/2+1) + 16 bytes:
@@ -15,7 +18,7 @@
 //   inverse:  spec[kh][(k, re|im)][8 c] (de-interleaved on load)  --pass A per k, in place-->  T[h][(k, re|im)][8 c]
 //             --pass B per h-->  y[h][w][c] (+ residual)
 // A "row" of 16 bytes = the 8 channels of one K index, so ldmatrix.trans delivers B fragments directly (K = w, (k, ri) along a
-// tile row; K = h / kh across tile rows, conflict-free because RS = 16 mod 32 bytes... see Cfg).  Every pass is in place: a warp
+// tile row; K = h / kh across tile rows, conflict-free because eight consecutive rows start in eight different 16-byte bank groups: Cfg).  Every pass is in place: a warp
 // owns whole tile rows (pass 1 / B) or whole (k, ri) column pairs (pass 2 / A), reads them into fragments, and only then writes.
 // The DFT matrices (1/sqrt(S) folded into each pass = ortho; Hermitian weights 1, 2, .., 2, 1 and the ignored imaginary parts of
 // the DC / Nyquist columns folded into the c2r matrix) are built on the host in fp16, already in A-fragment order.
@@ -459,7 +462,6 @@ int fft_mma_init() {
   if (cudaMemcpyToSymbol(fftmma::g_frag, host, sizeof(host)) != cudaSuccess) return S2V_ECUDA;
   return S2V_OK;
 }
-bool fft_mma_supports(int s) { return s == 48 || s == 24 || s == 12; }
 int rfft2_mma(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
   switch (x->h) {
     case 48: return fftmma::launch_r<48>(x, sp, st);
