@@ -26,6 +26,10 @@
 // against torch.fft in tests/test_gpu_kernels.py::test_fft2 (same 2e-3 of max bound as the register FFT).
 #include <math.h>
 
+#ifndef S2V_FFT_EXP
+#define S2V_FFT_EXP 0      // development: bit 0 = rfft2 without its global loads, bit 1 = without its global stores (profiles/r2c_summary.md)
+#endif
+
 #include "common.cuh"
 
 namespace s2v {
@@ -176,7 +180,11 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
         const int i = threadIdx.x + j * kThreads;
         if (i < S * S) {
           const int h = i / S, w = i - h * S;
+#if !(S2V_FFT_EXP & 1)
           cp_async16(tile + (uint32_t)(h * C::RS + w * 16), xp + h * x.sh + w * x.sw);
+#else
+          if (h < 0) cp_async16(tile + (uint32_t)(h * C::RS + w * 16), xp + h * x.sh + w * x.sw);
+#endif
         }
       }
       cp_async_commit();
@@ -233,8 +241,13 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
 #pragma unroll
       for (int mt = 0; mt < C::MT2; ++mt) {
         const int kh0 = mt * 16 + g, kh1 = kh0 + 8;
+#if (S2V_FFT_EXP & 2)      // experiment: keep the arithmetic alive, store (practically) nothing
+        if (kh0 < S && zr[mt][0] == 1234.5f) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
+        if (kh1 < S && zr[mt][2] == 1234.5f) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
+#else
         if (kh0 < S) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
         if (kh1 < S) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
+#endif
       }
     }
     __syncthreads();                           // every warp is done reading the tile before the next tile's loads land in it
