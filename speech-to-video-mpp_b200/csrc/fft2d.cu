@@ -185,9 +185,11 @@ static int fft24_cb32() {
   static const int v = [] { const char* e = getenv("S2V_FFT24_CB32"); return e ? atoi(e) : 1; }();     // development knob
   return v;
 }
-static bool fft_use_mma(int s) {
+// S2V_FFT_MMA: bits 0 / 1 / 2 = rfft2 at 48 / 24 / 12 px, bits 3 / 4 / 5 = irfft2 at 48 / 24 / 12 px on the tensor-core path (fft2d_mma.cu)
+static bool fft_use_mma(int s, bool inverse) {
   static const int mask = [] { const char* e = getenv("S2V_FFT_MMA"); return e ? atoi(e) : 0; }();       // development knob
-  return s == 48 ? (mask & 1) : s == 24 ? (mask & 2) : s == 12 ? (mask & 4) : false;
+  const int bit = s == 48 ? 0 : s == 24 ? 1 : s == 12 ? 2 : -1;
+  return bit >= 0 && ((mask >> (bit + (inverse ? 3 : 0))) & 1);
 }
 static int fft_rev() {
   static const int rev = [] { const char* e = getenv("S2V_FFT_REV"); return e ? atoi(e) : 0; }();
@@ -241,7 +243,7 @@ static bool fft_shapes_ok(const s2v_view* x, const s2v_view* sp) {
 extern "C" int s2v_rfft2(const s2v_view* x, const s2v_view* spec, void* stream) {
   if (!fft_shapes_ok(x, spec)) return S2V_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if (fft_use_mma(x->h)) return rfft2_mma(x, spec, st);
+  if (fft_use_mma(x->h, false)) return rfft2_mma(x, spec, st);
   if (x->h == 12 && x->c % 32 == 0) return launch_rfft2<12, 32>(x, spec, st);
   if (x->h == 12 && x->c % 8 == 0) return launch_rfft2<12, 8>(x, spec, st);
   if (x->h == 24 && x->c % 32 == 0 && fft24_cb32()) return launch_rfft2<24, 32>(x, spec, st);
@@ -256,7 +258,7 @@ extern "C" int s2v_irfft2(const s2v_view* spec, const s2v_view* add, const s2v_v
   if (!fft_shapes_ok(y, spec)) return S2V_EINVAL;
   if (add && add->ptr && (!view_ok(add) || add->h != y->h || add->w != y->w || add->c != y->c || add->n != y->n)) return S2V_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if (fft_use_mma(y->h)) return irfft2_mma(spec, add && add->ptr ? add : nullptr, y, st);
+  if (fft_use_mma(y->h, true)) return irfft2_mma(spec, add && add->ptr ? add : nullptr, y, st);
   if (y->h == 12 && y->c % 32 == 0) return launch_irfft2<12, 32>(spec, add, y, st);
   if (y->h == 12 && y->c % 8 == 0) return launch_irfft2<12, 8>(spec, add, y, st);
   if (y->h == 24 && y->c % 32 == 0 && fft24_cb32()) return launch_irfft2<24, 32>(spec, add, y, st);

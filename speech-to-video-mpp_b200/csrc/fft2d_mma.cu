@@ -24,6 +24,7 @@
 // the DC / Nyquist columns folded into the c2r matrix) are built on the host in fp16, already in A-fragment order.
 // Accuracy: fp16 twiddles add one rounding (2^-12 relative) per product to the fp16 rounding of the stored result; measured
 // against torch.fft in tests/test_gpu_kernels.py::test_fft2 (same 2e-3 of max bound as the register FFT).
+#include <cuda.h>
 #include <math.h>
 
 #ifndef S2V_FFT_EXP
@@ -94,11 +95,11 @@ __device__ __forceinline__ void load_b(uint32_t a, uint32_t stride, int lane, ui
 template <int S>
 __device__ __forceinline__ void complex_pass(uint32_t tile, int k, int lane, const uint4 (&ar)[Cfg<S>::MT2][Cfg<S>::KT],
                                              const uint4 (&ai)[Cfg<S>::MT2][Cfg<S>::KT], float (&zr)[Cfg<S>::MT2][4],
-                                             float (&zi)[Cfg<S>::MT2][4]) {
+                                             float (&zi)[Cfg<S>::MT2][4], uint32_t pitch = Cfg<S>::RS) {
   using C = Cfg<S>;
   uint32_t bre[C::KT][2], bim[C::KT][2], bin[C::KT][2];
-  load_b<C::KT>(tile + (uint32_t)(2 * k) * 16u, C::RS, lane, bre);
-  load_b<C::KT>(tile + (uint32_t)(2 * k + 1) * 16u, C::RS, lane, bim);
+  load_b<C::KT>(tile + (uint32_t)(2 * k) * 16u, pitch, lane, bre);
+  load_b<C::KT>(tile + (uint32_t)(2 * k + 1) * 16u, pitch, lane, bim);
 #pragma unroll
   for (int kt = 0; kt < C::KT; ++kt) { bin[kt][0] = bim[kt][0] ^ 0x80008000u; bin[kt][1] = bim[kt][1] ^ 0x80008000u; }   // -Bim
 #pragma unroll
@@ -159,14 +160,81 @@ __device__ __forceinline__ void load_a(uint32_t tab, int frag0, int lane, uint4 
     for (int kt = 0; kt < KTN; ++kt) a[mt][kt] = ld_shared_u4(tab + (uint32_t)((frag0 + mt * KTN + kt) * 32 + lane) * 16u);
 }
 
+// ---- forward passes (shared by the cp.async kernel and the TMA kernel) ------------------------------------------------------
+// pass 1: real-input DFT along w.  X rows at xb + h * xpitch (K rows = pixels, 16 bytes apart), Y rows at yb + h * RS; in place when
+// xb == yb and xpitch == RS (a warp reads its rows into fragments before it writes them).  Two rows per step = 2 * MT1 independent
+// accumulators in flight (mma.sync issues in program order; back-to-back MMAs on one accumulator wait out the pipeline latency).
+template <int S>
+__device__ __forceinline__ void rfft_pass1(uint32_t xb, uint32_t xpitch, uint32_t yb, const uint4 (&a1)[Cfg<S>::MT1][Cfg<S>::KT], int warp, int lane) {
+  using C = Cfg<S>;
+  const int g = lane >> 2, t = lane & 3;
+  for (int h = warp; h < S; h += 2 * kWarps) {
+    const bool two = h + kWarps < S;                             // (warp-uniform; an odd last step repeats its row, stores once)
+    const int h1 = two ? h + kWarps : h;
+    uint32_t b0[C::KT][2], b1[C::KT][2];
+    load_b<C::KT>(xb + (uint32_t)h * xpitch, 16u, lane, b0);
+    load_b<C::KT>(xb + (uint32_t)h1 * xpitch, 16u, lane, b1);
+    float acc0[C::MT1][4], acc1[C::MT1][4];
+#pragma unroll
+    for (int mt = 0; mt < C::MT1; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc0[mt][i] = 0.f; acc1[mt][i] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+#pragma unroll
+      for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc0[mt], a1[mt][kt], b0[kt][0], b0[kt][1]);
+#pragma unroll
+      for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc1[mt], a1[mt][kt], b1[kt][0], b1[kt][1]);
+    }
+    __syncwarp();
+    const uint32_t row0 = yb + (uint32_t)h * C::RS, row1 = yb + (uint32_t)h1 * C::RS;
+#pragma unroll
+    for (int mt = 0; mt < C::MT1; ++mt) {
+      const int k = mt * 8 + g;
+      if (k < C::K1) {
+        const uint32_t o = (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+        st_shared_u32(row0 + o, pack_h2(acc0[mt][0], acc0[mt][1]));            // re, channels 2t, 2t+1
+        st_shared_u32(row0 + o + 16u, pack_h2(acc0[mt][2], acc0[mt][3]));      // im
+        if (two) {
+          st_shared_u32(row1 + o, pack_h2(acc1[mt][0], acc1[mt][1]));
+          st_shared_u32(row1 + o + 16u, pack_h2(acc1[mt][2], acc1[mt][3]));
+        }
+      }
+    }
+  }
+}
+// pass 2: complex DFT along h for column k of the Y tile, straight to global (op = the tile's channel 0 of spec, image n)
+template <int S>
+__device__ __forceinline__ void rfft_pass2(uint32_t yb, const uint4 (&ar)[Cfg<S>::MT2][Cfg<S>::KT], const uint4 (&ai)[Cfg<S>::MT2][Cfg<S>::KT],
+                                           const View& sp, __half* op0, int warp, int lane) {
+  using C = Cfg<S>;
+  const int g = lane >> 2, t = lane & 3;
+  __half* op = op0 + 4 * t;
+  for (int k = warp; k < C::K1; k += kWarps) {
+    float zr[C::MT2][4], zi[C::MT2][4];
+    complex_pass<S>(yb, k, lane, ar, ai, zr, zi);
+#pragma unroll
+    for (int mt = 0; mt < C::MT2; ++mt) {
+      const int kh0 = mt * 16 + g, kh1 = kh0 + 8;
+#if (S2V_FFT_EXP & 2)      // experiment: keep the arithmetic alive, store (practically) nothing
+      if (kh0 < S && zr[mt][0] == 1234.5f) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
+      if (kh1 < S && zr[mt][2] == 1234.5f) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
+#else
+      if (kh0 < S) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
+      if (kh1 < S) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
+#endif
+    }
+  }
+}
+
 // x [N,S,S,C] -> spec [N,S,S/2+1,2C]; tiles = N * C / 8 (image-major), grid = min(tiles, BPS * #SMs)
 template <int S>
 __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel(View x, View sp, int cblocks, int tiles) {
   using C = Cfg<S>;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   pdl_trigger();
   const uint32_t tile = (uint32_t)__cvta_generic_to_shared(smem_raw), tab = tile + C::TILE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   block_prologue<S>(tile, C::O_F1, C::N_F1 + 2 * C::N_G);       // constant tables: copied ahead of the PDL wait
   __syncthreads();
   pdl_wait();
@@ -194,63 +262,83 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
       load_a<C::MT1, C::KT>(tab, 0, lane, a1);
       cp_async_wait_all();
       __syncthreads();
-      // ---- pass 1: real-input DFT along w, whole tile rows per warp, in place -----------------------------------------
-      for (int h = warp; h < S; h += 2 * kWarps) {               // two rows per step = 2 * MT1 independent accumulators in flight
-        const bool two = h + kWarps < S;                           // (warp-uniform; an odd last step repeats its row, stores once)
-        const uint32_t row0 = tile + (uint32_t)h * C::RS, row1 = tile + (uint32_t)(two ? h + kWarps : h) * C::RS;
-        uint32_t b0[C::KT][2], b1[C::KT][2];
-        load_b<C::KT>(row0, 16u, lane, b0);
-        load_b<C::KT>(row1, 16u, lane, b1);
-        float acc0[C::MT1][4], acc1[C::MT1][4];
-#pragma unroll
-        for (int mt = 0; mt < C::MT1; ++mt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { acc0[mt][i] = 0.f; acc1[mt][i] = 0.f; }
-#pragma unroll
-        for (int kt = 0; kt < C::KT; ++kt) {
-#pragma unroll
-          for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc0[mt], a1[mt][kt], b0[kt][0], b0[kt][1]);
-#pragma unroll
-          for (int mt = 0; mt < C::MT1; ++mt) mma16816(acc1[mt], a1[mt][kt], b1[kt][0], b1[kt][1]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int mt = 0; mt < C::MT1; ++mt) {
-          const int k = mt * 8 + g;
-          if (k < C::K1) {
-            const uint32_t o = (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
-            st_shared_u32(row0 + o, pack_h2(acc0[mt][0], acc0[mt][1]));            // re, channels 2t, 2t+1
-            st_shared_u32(row0 + o + 16u, pack_h2(acc0[mt][2], acc0[mt][3]));      // im
-            if (two) {
-              st_shared_u32(row1 + o, pack_h2(acc1[mt][0], acc1[mt][1]));
-              st_shared_u32(row1 + o + 16u, pack_h2(acc1[mt][2], acc1[mt][3]));
-            }
-          }
-        }
-      }
+      rfft_pass1<S>(tile, C::RS, tile, a1, warp, lane);       // in place
     }
     uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT];
     load_a<C::MT2, C::KT>(tab, C::N_F1, lane, ar);
     load_a<C::MT2, C::KT>(tab, C::N_F1 + C::N_G, lane, ai);
     __syncthreads();
-    // ---- pass 2: complex DFT along h for column k, straight to global ------------------------------------------------
-    __half* op = sp.p + n * sp.sn + 2 * (ch0 + 2 * t);
-    for (int k = warp; k < C::K1; k += kWarps) {
-      float zr[C::MT2][4], zi[C::MT2][4];
-      complex_pass<S>(tile, k, lane, ar, ai, zr, zi);
-#pragma unroll
-      for (int mt = 0; mt < C::MT2; ++mt) {
-        const int kh0 = mt * 16 + g, kh1 = kh0 + 8;
-#if (S2V_FFT_EXP & 2)      // experiment: keep the arithmetic alive, store (practically) nothing
-        if (kh0 < S && zr[mt][0] == 1234.5f) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
-        if (kh1 < S && zr[mt][2] == 1234.5f) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
-#else
-        if (kh0 < S) *reinterpret_cast<uint2*>(op + kh0 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][0], zi[mt][0]), pack_h2(zr[mt][1], zi[mt][1]));
-        if (kh1 < S) *reinterpret_cast<uint2*>(op + kh1 * sp.sh + k * sp.sw) = make_uint2(pack_h2(zr[mt][2], zi[mt][2]), pack_h2(zr[mt][3], zi[mt][3]));
-#endif
-      }
-    }
+    rfft_pass2<S>(tile, ar, ai, sp, sp.p + n * sp.sn + 2 * ch0, warp, lane);
     __syncthreads();                           // every warp is done reading the tile before the next tile's loads land in it
+  }
+}
+
+// ---- the forward transform with the tile gathered by TMA ---------------------------------------------------------------------
+// The 16-byte channel slices make the cp.async loads of the kernel above the largest part of its time (19 of 46 us at 48 x 48,
+// B = 256: 24 cache lines per warp request).  One bulk-tensor load {8 ch, S, S, 1} per tile moves the same slices at one 16-byte row
+// per clock per SM (tools/mb_tma_rows.cu: 2 326 clocks per 36 KB tile) WITHOUT occupying the LSU or an issue slot, into a dense
+// X buffer (TMA destinations are 128-byte aligned, so the padded in-place pitch is not an option); pass 1 reads X and writes the
+// padded Y tile, the next tile's load is issued as soon as pass 1 is done and lands during pass 2.  76 KB -> 2 blocks per SM, so all
+// A fragments stay in registers.
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  for (unsigned spins = 0; spins < (1u << 26); ++spins) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+template <int S> constexpr int x_bytes() { return S * S * 16 + 256; }          // dense tile + tail (K padding of pass 1 reads past the last row)
+
+template <int S> constexpr int blocks_per_sm_tma() { return S == 48 ? 2 : S == 24 ? 4 : 8; }
+template <int S>
+__global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) rfft2_mma_tma_kernel(const __grid_constant__ CUtensorMap tmx, View sp, int cblocks, int tiles) {
+  using C = Cfg<S>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  pdl_trigger();
+  const uint32_t xb = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u, yb = xb + x_bytes<S>(), bar = yb + C::TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (x_bytes<S>() + C::TILE) / 16; i += kThreads) st_shared_u4(xb + (uint32_t)i * 16u, z);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint4 a1[C::MT1][C::KT], ar[C::MT2][C::KT], ai[C::MT2][C::KT];     // constant tables: fetched ahead of the PDL wait
+#pragma unroll
+  for (int mt = 0; mt < C::MT1; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) a1[mt][kt] = g_frag[(C::O_F1 + mt * C::KT + kt) * 32 + lane];
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+      ar[mt][kt] = g_frag[(C::O_GR + mt * C::KT + kt) * 32 + lane];
+      ai[mt][kt] = g_frag[(C::O_GI + mt * C::KT + kt) * 32 + lane];
+    }
+  __syncthreads();
+  pdl_wait();
+  auto issue_load = [&](int ti) {              // one thread; every generic access to X is behind a block barrier at this point
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(S * S * 16)) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(xb), "l"(&tmx), "r"(bar), "r"(ch0), "r"(0), "r"(0), "r"(n) : "memory");
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < tiles) issue_load(blockIdx.x);
+  int it = 0;
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    mbar_wait_parity(bar, (uint32_t)(it & 1));
+    rfft_pass1<S>(xb, (uint32_t)(S * 16), yb, a1, warp, lane);
+    __syncthreads();                           // X is consumed, Y is complete
+    if (threadIdx.x == 0 && ti + (int)gridDim.x < tiles) issue_load(ti + gridDim.x);
+    rfft_pass2<S>(yb, ar, ai, sp, sp.p + n * sp.sn + 2 * ch0, warp, lane);
+    __syncthreads();                           // every warp is done reading Y before the next tile's pass 1 writes it
   }
 }
 
@@ -258,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) rfft2_mma_kernel
 template <int S>
 __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kernel(View sp, View add, View y, int cblocks, int tiles) {
   using C = Cfg<S>;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   pdl_trigger();
   const uint32_t tile = (uint32_t)__cvta_generic_to_shared(smem_raw), tab = tile + C::TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -381,6 +469,147 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kerne
   }
 }
 
+// ---- the inverse transform with all three global streams on TMA --------------------------------------------------------------
+// spec tile {2 x 8 ch, S/2+1, S} (32-byte inner rows) -> SP (dense 32 (S/2+1)-byte rows: two-way bank conflicts on pass A's fragment
+// loads, accepted), residual tile {8 ch, S, S} -> R; pass A in place in SP, pass B adds its result into R in place (4-byte shared
+// accesses instead of 4-byte global ones: 8 cache lines per warp request), one bulk-tensor store R -> y.  75 KB -> 2 blocks per SM.
+template <int S> constexpr int sp_pitch() { return Cfg<S>::K1 * 32; }
+template <int S> constexpr int sp_bytes() { return Cfg<S>::KP * sp_pitch<S>() + 256; }      // rows >= S (K padding over kh) and the tail stay zero
+template <int S> constexpr int r_bytes() { return S * S * 16; }
+
+template <int S>
+__global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_tma_kernel(const __grid_constant__ CUtensorMap tmsp,
+                                                                                         const __grid_constant__ CUtensorMap tmadd,
+                                                                                         const __grid_constant__ CUtensorMap tmy, int has_add,
+                                                                                         int cblocks, int tiles) {
+  using C = Cfg<S>;
+  constexpr uint32_t kPitch = sp_pitch<S>();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  pdl_trigger();
+  const uint32_t rb = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u, spb = rb + r_bytes<S>(), bar = spb + sp_bytes<S>();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (r_bytes<S>() + sp_bytes<S>()) / 16; i += kThreads) st_shared_u4(rb + (uint32_t)i * 16u, z);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmsp) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+    if (has_add) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmadd) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT], a2[C::MT2][C::KT2];     // constant tables: fetched ahead of the PDL wait
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt) {
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+      ar[mt][kt] = g_frag[(C::O_WR + mt * C::KT + kt) * 32 + lane];
+      ai[mt][kt] = g_frag[(C::O_WI + mt * C::KT + kt) * 32 + lane];
+    }
+#pragma unroll
+    for (int kt = 0; kt < C::KT2; ++kt) a2[mt][kt] = g_frag[(C::O_A2 + mt * C::KT2 + kt) * 32 + lane];
+  }
+  __syncthreads();
+  pdl_wait();
+  constexpr int kItems = S * C::K1;
+  int it = 0;
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    if (threadIdx.x == 0) {                    // every generic access to SP / R of the previous tile is behind the loop's last barrier
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the previous tile's store has read R
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kItems * 32 + (has_add ? r_bytes<S>() : 0))) : "memory");
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(spb), "l"(&tmsp), "r"(bar), "r"(2 * ch0), "r"(0), "r"(0), "r"(n) : "memory");
+      if (has_add)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(rb), "l"(&tmadd), "r"(bar), "r"(ch0), "r"(0), "r"(0), "r"(n) : "memory");
+    }
+    mbar_wait_parity(bar, (uint32_t)(it & 1));
+    // de-interleave in place: [c0r c0i .. c7r c7i] -> [c0r .. c7r][c0i .. c7i]
+#pragma unroll 2
+    for (int i = threadIdx.x; i < kItems; i += kThreads) {
+      const int kh = i / C::K1, k = i - kh * C::K1;
+      const uint32_t d = spb + (uint32_t)kh * kPitch + (uint32_t)k * 32u;
+      const uint4 u0 = ld_shared_u4(d), u1 = ld_shared_u4(d + 16u);
+      st_shared_u4(d, make_uint4(__byte_perm(u0.x, u0.y, 0x5410), __byte_perm(u0.z, u0.w, 0x5410),
+                                 __byte_perm(u1.x, u1.y, 0x5410), __byte_perm(u1.z, u1.w, 0x5410)));
+      st_shared_u4(d + 16u, make_uint4(__byte_perm(u0.x, u0.y, 0x7632), __byte_perm(u0.z, u0.w, 0x7632),
+                                       __byte_perm(u1.x, u1.y, 0x7632), __byte_perm(u1.z, u1.w, 0x7632)));
+    }
+    __syncthreads();
+    // ---- pass A: inverse complex DFT along kh for column k, in place ---------------------------------------------------
+    for (int k = warp; k < C::K1; k += kWarps) {
+      float zr[C::MT2][4], zi[C::MT2][4];
+      complex_pass<S>(spb, k, lane, ar, ai, zr, zi, kPitch);
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < C::MT2; ++mt) {
+        const int h0 = mt * 16 + g, h1 = h0 + 8;
+        const uint32_t c0 = spb + (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+        if (h0 < S) {
+          st_shared_u32(c0 + (uint32_t)h0 * kPitch, pack_h2(zr[mt][0], zr[mt][1]));
+          st_shared_u32(c0 + (uint32_t)h0 * kPitch + 16u, pack_h2(zi[mt][0], zi[mt][1]));
+        }
+        if (h1 < S) {
+          st_shared_u32(c0 + (uint32_t)h1 * kPitch, pack_h2(zr[mt][2], zr[mt][3]));
+          st_shared_u32(c0 + (uint32_t)h1 * kPitch + 16u, pack_h2(zi[mt][2], zi[mt][3]));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass B: complex-to-real along w for tile row h (K = (k, re|im)), added into R in place --------------------------
+    for (int h = warp; h < S; h += 2 * kWarps) {                 // two rows per step = 2 * MT2 independent accumulators in flight
+      const bool two = h + kWarps < S;
+      const int hh[2] = {h, two ? h + kWarps : h};
+      uint32_t b[2][C::KT2][2];
+      load_b<C::KT2>(spb + (uint32_t)hh[0] * kPitch, 16u, lane, b[0]);
+      load_b<C::KT2>(spb + (uint32_t)hh[1] * kPitch, 16u, lane, b[1]);
+      float acc[2][C::MT2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[r][mt][i] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < C::KT2; ++kt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int mt = 0; mt < C::MT2; ++mt) mma16816(acc[r][mt], a2[mt][kt], b[r][kt][0], b[r][kt][1]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt) {
+          const int w0 = mt * 16 + g, w1 = w0 + 8;
+          const uint32_t p0 = rb + (uint32_t)((hh[r] * S + w0) * 16 + t * 4), p1 = rb + (uint32_t)((hh[r] * S + w1) * 16 + t * 4);
+          float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+          if (has_add) {
+            uint32_t u0 = 0u, u1 = 0u;
+            if (w0 < S) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u0) : "r"(p0) : "memory");
+            if (w1 < S) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u1) : "r"(p1) : "memory");
+            r0 = __half22float2(*reinterpret_cast<const __half2*>(&u0));
+            r1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+          }
+          if (w0 < S) st_shared_u32(p0, pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y));
+          if (w1 < S) st_shared_u32(p1, pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y));
+        }
+      }
+    }
+    __syncthreads();                           // R holds the finished tile; SP is free
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                   ::"l"(&tmy), "r"(rb), "r"(ch0), "r"(0), "r"(0), "r"(n) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last store is done with R before the block exits
+}
+
 // ---- host: DFT matrices in A-fragment order ---------------------------------------------------------------------------
 template <typename F>
 static void fill_frags(uint4* dst, int mts, int kts, F f) {
@@ -447,6 +676,48 @@ static int launch_r(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;     // resolved once; immutable afterwards
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+template <int S>
+static int launch_r_tma(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return S2V_EUNSUPPORTED;
+  static DeviceOnce attr;
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  constexpr int smem = x_bytes<S>() + Cfg<S>::TILE + 16 + 128;
+  if (attr.needed(dev)) {
+    S2V_CUDA_TRY(cudaFuncSetAttribute(rfft2_mma_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr.mark(dev);
+  }
+  CUtensorMap tmx;
+  cuuint64_t gdim[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+  cuuint64_t gstr[3] = {(cuuint64_t)x->sw * 2, (cuuint64_t)x->sh * 2, (cuuint64_t)x->sn * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)S, (cuuint32_t)S, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return S2V_ECUDA;
+  const int n_sm = sm_count(dev);
+  if (n_sm <= 0) return S2V_ECUDA;
+  const int cblocks = x->c / 8, tiles = cblocks * x->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
+  typedef void (*KernelFn)(const CUtensorMap, View, int, int);
+  const KernelFn kfn = rfft2_mma_tma_kernel<S>;
+  S2V_CUDA_TRY(launch_pdl(kfn, dim3(grid), kThreads, (size_t)smem, st, tmx, mk(sp), cblocks, tiles));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
 template <int S>
 static int launch_i(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
   static DeviceOnce attr;
@@ -464,6 +735,40 @@ static int launch_i(const s2v_view* sp, const s2v_view* add, const s2v_view* y, 
   return S2V_OK;
 }
 
+static bool make_map4(EncodeTiledFn enc, CUtensorMap* tm, const s2v_view* v, int c_elems, int w_elems, int box_c, int box_w, int box_h) {
+  cuuint64_t gdim[4] = {(cuuint64_t)c_elems, (cuuint64_t)w_elems, (cuuint64_t)v->h, (cuuint64_t)v->n};
+  cuuint64_t gstr[3] = {(cuuint64_t)v->sw * 2, (cuuint64_t)v->sh * 2, (cuuint64_t)v->sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, v->ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <int S>
+static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return S2V_EUNSUPPORTED;
+  static DeviceOnce attr;
+  const int dev = current_device();
+  if (dev < 0) return S2V_ECUDA;
+  constexpr int smem = r_bytes<S>() + sp_bytes<S>() + 16 + 128;
+  if (attr.needed(dev)) {
+    S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr.mark(dev);
+  }
+  CUtensorMap tmsp, tmadd, tmy;
+  if (!make_map4(enc, &tmsp, sp, sp->c, sp->w, 16, Cfg<S>::K1, S)) return S2V_ECUDA;
+  if (!make_map4(enc, &tmy, y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
+  if (!make_map4(enc, &tmadd, add ? add : y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
+  const int n_sm = sm_count(dev);
+  if (n_sm <= 0) return S2V_ECUDA;
+  const int cblocks = y->c / 8, tiles = cblocks * y->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int);
+  const KernelFn kfn = irfft2_mma_tma_kernel<S>;
+  S2V_CUDA_TRY(launch_pdl(kfn, dim3(grid), kThreads, (size_t)smem, st, tmsp, tmadd, tmy, add ? 1 : 0, cblocks, tiles));
+  S2V_CHECK_LAUNCH();
+  return S2V_OK;
+}
+
 }  // namespace fftmma
 
 // ---- entry points used by fft2d.cu ------------------------------------------------------------------------------------
@@ -476,18 +781,20 @@ int fft_mma_init() {
   return S2V_OK;
 }
 int rfft2_mma(const s2v_view* x, const s2v_view* sp, cudaStream_t st) {
+  static const int tma = [] { const char* e = getenv("S2V_FFT_TMA"); return e ? atoi(e) : 1; }();       // development knob: 0 = cp.async tile loads
   switch (x->h) {
-    case 48: return fftmma::launch_r<48>(x, sp, st);
-    case 24: return fftmma::launch_r<24>(x, sp, st);
-    case 12: return fftmma::launch_r<12>(x, sp, st);
+    case 48: return tma ? fftmma::launch_r_tma<48>(x, sp, st) : fftmma::launch_r<48>(x, sp, st);
+    case 24: return tma ? fftmma::launch_r_tma<24>(x, sp, st) : fftmma::launch_r<24>(x, sp, st);
+    case 12: return tma ? fftmma::launch_r_tma<12>(x, sp, st) : fftmma::launch_r<12>(x, sp, st);
   }
   return S2V_EINVAL;
 }
 int irfft2_mma(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st) {
+  static const int tma = [] { const char* e = getenv("S2V_FFT_TMA"); return e ? atoi(e) : 1; }();       // development knob: 0 = cp.async tile loads
   switch (y->h) {
-    case 48: return fftmma::launch_i<48>(sp, add, y, st);
-    case 24: return fftmma::launch_i<24>(sp, add, y, st);
-    case 12: return fftmma::launch_i<12>(sp, add, y, st);
+    case 48: return tma ? fftmma::launch_i_tma<48>(sp, add, y, st) : fftmma::launch_i<48>(sp, add, y, st);
+    case 24: return tma ? fftmma::launch_i_tma<24>(sp, add, y, st) : fftmma::launch_i<24>(sp, add, y, st);
+    case 12: return tma ? fftmma::launch_i_tma<12>(sp, add, y, st) : fftmma::launch_i<12>(sp, add, y, st);
   }
   return S2V_EINVAL;
 }

@@ -313,12 +313,12 @@ def test_fft2(G, s, c):
 
 
 def test_fft2_mma_path():
-    """The tensor-core DFT variant of the same entry points (csrc/fft2d_mma.cu, S2V_FFT_MMA=7: all three sizes) against torch.fft.
+    """The tensor-core DFT variant of the same entry points (csrc/fft2d_mma.cu, S2V_FFT_MMA=63: both directions, all three sizes) against torch.fft.
     The switch is read once per process, so the parametrised test above is re-run in a child process."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, S2V_FFT_MMA="7")
+    env = dict(os.environ, S2V_FFT_MMA="63")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "test_fft2 and not mma_path"],
                        env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
