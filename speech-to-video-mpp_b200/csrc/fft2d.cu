@@ -9,11 +9,11 @@
 
 namespace s2v {
 
-// fft2d_mma.cu: the same transforms as dense DFT matrix products on mma.sync, selected per size with S2V_FFT_MMA (bit 0 = 48 x 48,
-// bit 1 = 24 x 24, bit 2 = 12 x 12; default 0).  Measured on B200 (profiles/r2c_summary.md): 5 x fewer instructions and a 39 KB
-// tile, but the 250 registers of resident A fragments leave 8 warps per SM - 48 x 48 at B = 256: 45.0 / 67.5 us against 53.2 /
-// 75.9 us here, B = 128: 24.4 / 36.0 against 23.6 / 37.1, smaller sizes slower; LNet B = 256 24.62 against 24.92 ms.  Not
-// enough to pay for its extra fp16 rounding of the twiddles, so the register FFT below stays the default.
+// fft2d_mma.cu: the same transforms as dense DFT matrix products on mma.sync with the tiles moved by TMA, selected per direction and
+// size with S2V_FFT_MMA.  Measured on B200 (profiles/r2c_summary.md, us at B = 128 / 256): 48 x 48 rfft2 18.9 / 33.7 against 23.6 / 53.2
+// here, irfft2 33.7 / 60.1 against 37.1 / 75.9 -> the default for both 48 x 48 transforms; at 24 and 12 px the register FFT below is
+// as fast or faster (11.4 / 18.2 vs 10.2 / 18.5 and 11.2 / 19.5 vs 9.7 / 13.6 for rfft2) and stays.  The price is one extra fp16 rounding
+// (the twiddles): 7e-4 - 1e-3 of the output peak against 3e-4 - 6e-4 (test_fft2), LNet parity unchanged within 0.1 dB.
 int fft_mma_init();
 int rfft2_mma(const s2v_view* x, const s2v_view* sp, cudaStream_t st);
 int irfft2_mma(const s2v_view* sp, const s2v_view* add, const s2v_view* y, cudaStream_t st);
@@ -187,7 +187,7 @@ static int fft24_cb32() {
 }
 // S2V_FFT_MMA: bits 0 / 1 / 2 = rfft2 at 48 / 24 / 12 px, bits 3 / 4 / 5 = irfft2 at 48 / 24 / 12 px on the tensor-core path (fft2d_mma.cu)
 static bool fft_use_mma(int s, bool inverse) {
-  static const int mask = [] { const char* e = getenv("S2V_FFT_MMA"); return e ? atoi(e) : 0; }();       // development knob
+  static const int mask = [] { const char* e = getenv("S2V_FFT_MMA"); return e ? atoi(e) : 9; }();       // default: both 48 x 48 transforms (measured faster); 0 = register FFT everywhere
   const int bit = s == 48 ? 0 : s == 24 ? 1 : s == 12 ? 2 : -1;
   return bit >= 0 && ((mask >> (bit + (inverse ? 3 : 0))) & 1);
 }

@@ -477,10 +477,12 @@ template <int S> constexpr int sp_pitch() { return Cfg<S>::K1 * 32; }
 template <int S> constexpr int sp_bytes() { return Cfg<S>::KP * sp_pitch<S>() + 256; }      // rows >= S (K padding over kh) and the tail stay zero
 template <int S> constexpr int r_bytes() { return S * S * 16; }
 
-template <int S>
+// STORE_TMA = false: y leaves through 4-byte global stores from the registers instead (the TMA unit moves one 16 / 32-byte row per
+// clock, and with the store on it as well it is the unit that bounds this kernel; the LSU is idle otherwise)
+template <int S, bool STORE_TMA>
 __global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_tma_kernel(const __grid_constant__ CUtensorMap tmsp,
                                                                                          const __grid_constant__ CUtensorMap tmadd,
-                                                                                         const __grid_constant__ CUtensorMap tmy, int has_add,
+                                                                                         const __grid_constant__ CUtensorMap tmy, View y, int has_add,
                                                                                          int cblocks, int tiles) {
   using C = Cfg<S>;
   constexpr uint32_t kPitch = sp_pitch<S>();
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_t
   for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
     const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
     if (threadIdx.x == 0) {                    // every generic access to SP / R of the previous tile is behind the loop's last barrier
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the previous tile's store has read R
+      if (STORE_TMA) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the previous tile's store has read R
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kItems * 32 + (has_add ? r_bytes<S>() : 0))) : "memory");
       asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -594,20 +596,26 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_t
             r0 = __half22float2(*reinterpret_cast<const __half2*>(&u0));
             r1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
           }
-          if (w0 < S) st_shared_u32(p0, pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y));
-          if (w1 < S) st_shared_u32(p1, pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y));
+          if (STORE_TMA) {
+            if (w0 < S) st_shared_u32(p0, pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y));
+            if (w1 < S) st_shared_u32(p1, pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y));
+          } else {
+            __half* yp = y.p + n * y.sn + hh[r] * y.sh + ch0 + 2 * t;
+            if (w0 < S) *reinterpret_cast<uint32_t*>(yp + w0 * y.sw) = pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y);
+            if (w1 < S) *reinterpret_cast<uint32_t*>(yp + w1 * y.sw) = pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y);
+          }
         }
       }
     }
     __syncthreads();                           // R holds the finished tile; SP is free
-    if (threadIdx.x == 0) {
+    if (STORE_TMA && threadIdx.x == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                    ::"l"(&tmy), "r"(rb), "r"(ch0), "r"(0), "r"(0), "r"(n) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last store is done with R before the block exits
+  if (STORE_TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last store is done with R before the block exits
 }
 
 // ---- host: DFT matrices in A-fragment order ---------------------------------------------------------------------------
@@ -752,9 +760,11 @@ static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view*
   if (dev < 0) return S2V_ECUDA;
   constexpr int smem = r_bytes<S>() + sp_bytes<S>() + 16 + 128;
   if (attr.needed(dev)) {
-    S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr.mark(dev);
   }
+  static const int store_tma = [] { const char* e = getenv("S2V_FFT_TMA_STORE"); return e ? atoi(e) : 1; }();      // development knob
   CUtensorMap tmsp, tmadd, tmy;
   if (!make_map4(enc, &tmsp, sp, sp->c, sp->w, 16, Cfg<S>::K1, S)) return S2V_ECUDA;
   if (!make_map4(enc, &tmy, y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
@@ -762,9 +772,9 @@ static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view*
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int cblocks = y->c / 8, tiles = cblocks * y->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int);
-  const KernelFn kfn = irfft2_mma_tma_kernel<S>;
-  S2V_CUDA_TRY(launch_pdl(kfn, dim3(grid), kThreads, (size_t)smem, st, tmsp, tmadd, tmy, add ? 1 : 0, cblocks, tiles));
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, View, int, int, int);
+  const KernelFn kfn = store_tma ? irfft2_mma_tma_kernel<S, true> : irfft2_mma_tma_kernel<S, false>;
+  S2V_CUDA_TRY(launch_pdl(kfn, dim3(grid), kThreads, (size_t)smem, st, tmsp, tmadd, tmy, mk(y), add ? 1 : 0, cblocks, tiles));
   S2V_CHECK_LAUNCH();
   return S2V_OK;
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, third session: evidence of the final build (N = 1): all -m gpu tests, smoke, bench, ncu launch list of one step
-P=r2d
+P=r2e
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.txt
 timeout 1500 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/${P}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${P}_pytest.log
