@@ -7,10 +7,12 @@
 // already [.., K index, channel]) both passes of the 2-D transform are [M <= 64] x [K <= 64] constant matrices times the tile,
 // 0.76 MFLOP per image-channel on mma.sync.m16n8k16 (fp16 operands, fp32 accumulate) = 5 x fewer issued instructions, and the
 // tile needs 39 KB of shared memory instead of 154 KB, so four blocks per SM overlap their load / compute / store phases.
-// STATUS: parity-tested (tests/test_gpu_kernels.py::test_fft2_mma_path, CPU emulation in tests/test_fft_mma_emulation.py) and
-// measured EQUAL to the register FFT (profiles/r2c_summary.md), hence opt-in (S2V_FFT_MMA): an 8-channel tile is a 16-byte slice of
-// every pixel, one LDGSTS.128 of a warp touches 32 cache lines and one STG.64 eight, and those L1TEX line accesses - not the MMAs -
-// set its time.  The contraction sizes are far below a 128-row tcgen05 tile and the operands change role between the two passes (the
+// STATUS (profiles/r2c_summary.md): parity-tested (tests/test_gpu_kernels.py::test_fft2_mma_path, CPU emulation in
+// tests/test_fft_mma_emulation.py).  With cp.async tile loads the kernels only MATCH the register FFT: an 8-channel tile is a 16-byte
+// slice of every pixel, one LDGSTS.128 of a warp touches 24 cache lines, and those L1TEX line accesses - not the MMAs - set the time
+// (19 of 46 us at 48 x 48, B = 256).  With the tiles moved by TMA (rfft2_mma_tma_kernel / irfft2_mma_tma_kernel below: one 16-byte row
+// per clock per SM, off the LSU) the 48 x 48 transforms run 1.2 - 1.6 x faster than the register FFT and are the default for that size
+// (S2V_FFT_MMA, fft2d.cu); at 24 and 12 px the register FFT stays.  The contraction sizes are far below a 128-row tcgen05 tile and the operands change role between the two passes (the
 // accumulator of pass 1 is the B operand of pass 2), which is what warp-level mma + ldmatrix.trans is for.
 //
 // One block (4 warps) = one image n x 8 channels.  The tile lives in shared memory as rows of RS = 32 (S/2+1) + 16 bytes:
