@@ -12,7 +12,7 @@ KEEP = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "U
 print("# SASS opcode histogram per object of libs2v.so (round 2, final build; tools/sass_hist.py)")
 print("# cuobjdump -sass speech-to-video-mpp_b200/build/<obj>.o | opcode (modifiers stripped) | count   -- static instruction counts (loops counted once)")
 print("# UTCHMMA = tcgen05.mma (kind::f16, incl. .2CTA pair form), LDTM = tcgen05.ld, UTMALDG / UTMASTG / UTMAPF = TMA tensor load / store / L2 prefetch,")
-print("# UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, HMMA + LDSM = the mma.sync cross-check attention kernel, DFMA/DADD/DMUL = float64 statistics / resampler / cv2-double taps")
+print("# UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, HMMA + LDSM = mma.sync (the tensor-core DFT of fft2d_mma and the cross-check attention kernel), DFMA/DADD/DMUL = float64 statistics / resampler / cv2-double taps")
 for obj in sorted(glob.glob(os.path.join(ROOT, "speech-to-video-mpp_b200", "build", "*.o"))):
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     cnt = collections.Counter()
