@@ -369,8 +369,12 @@ int s2v_reflect_border(const s2v_view* interior, void* stream);
  *         (torch.fft.rfftn norm='ortho' + stack/permute/view interleave)
  * irfft2: spec -> y [N,H,W,C] (torch.fft.irfftn norm='ortho', Im of the DC and
  *         Nyquist columns ignored after the H inverse) ; y += add (x + fu(x) of
- *         ffc.py:172) when add.ptr != NULL                                      */
-/* uploads the constant W_48 twiddle table; call once per device before the first FFT call */
+ *         ffc.py:172) when add.ptr != NULL
+ * 48 x 48: dense fp16 DFT matrices on the tensor cores, 8-channel tiles moved by
+ * TMA (csrc/fft2d_mma.cu; fp32 accumulate, one more fp16 rounding than the
+ * register FFT: <= 1e-3 of the output peak); 24 / 12: register FFT (fft2d.cu).
+ * S2V_FFT_MMA selects per direction and size (0 = register FFT everywhere).      */
+/* uploads the constant W_48 twiddle table and the DFT matrix fragment tables; call once per device before the first FFT call */
 int s2v_fft_init(void);
 int s2v_rfft2(const s2v_view* x, const s2v_view* spec, void* stream);
 int s2v_irfft2(const s2v_view* spec, const s2v_view* add, const s2v_view* y, void* stream);
