@@ -11,7 +11,7 @@ namespace s2v {
 
 // fft2d_mma.cu: the same transforms as dense DFT matrix products on mma.sync with the tiles moved by TMA, selected per direction and
 // size with S2V_FFT_MMA.  Measured on B200 (profiles/r2c_summary.md, us at B = 128 / 256): 48 x 48 rfft2 18.9 / 33.7 against 23.6 / 53.2
-// here, irfft2 33.7 / 60.1 against 37.1 / 75.9 -> the default for both 48 x 48 transforms; at 24 and 12 px the register FFT below is
+// here, irfft2 27.7 / 46.7 against 37.1 / 75.9 -> the default for both 48 x 48 transforms; at 24 and 12 px the register FFT below is
 // as fast or faster (11.4 / 18.2 vs 10.2 / 18.5 and 11.2 / 19.5 vs 9.7 / 13.6 for rfft2) and stays.  The price is one extra fp16 rounding
 // (the twiddles): 7e-4 - 1e-3 of the output peak against 3e-4 - 6e-4 (test_fft2), LNet parity unchanged within 0.1 dB.
 int fft_mma_init();

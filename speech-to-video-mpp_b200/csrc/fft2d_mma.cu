@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm<S>()) irfft2_mma_kerne
 // loads, accepted), residual tile {8 ch, S, S} -> R; pass A in place in SP, pass B adds its result into R in place (4-byte shared
 // accesses instead of 4-byte global ones: 8 cache lines per warp request), one bulk-tensor store R -> y.  75 KB -> 2 blocks per SM.
 template <int S> constexpr int sp_pitch() { return Cfg<S>::K1 * 32; }
-template <int S> constexpr int sp_bytes() { return Cfg<S>::KP * sp_pitch<S>() + 256; }      // rows >= S (K padding over kh) and the tail stay zero
+template <int S> constexpr int sp_bytes() { return (Cfg<S>::KP * sp_pitch<S>() + 256 + 127) / 128 * 128; }      // rows >= S (K padding over kh) and the tail stay zero
 template <int S> constexpr int r_bytes() { return S * S * 16; }
 
 // STORE_TMA = false: y leaves through 4-byte global stores from the registers instead (the TMA unit moves one 16 / 32-byte row per
@@ -618,6 +618,151 @@ __global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_t
     }
   }
   if (STORE_TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last store is done with R before the block exits
+}
+
+// Pipelined form of the inverse kernel: TWO spec buffers (the next tile's spec load is issued at the top of the current tile), the
+// residual tile loaded one phase ahead (issued as soon as pass B is done with the buffer), y through 4-byte stores from the registers
+// (fire and forget).  112 KB -> still 2 blocks per SM.  The default (S2V_FFT_TMA_STORE=0): 27.7 / 46.7 us at 48 x 48, B = 128 / 256, against
+// 33.7 / 60.1 us for the single-buffered kernel above and 37.1 / 75.9 us for the register FFT.
+template <int S>
+__global__ void __launch_bounds__(kThreads, blocks_per_sm_tma<S>()) irfft2_mma_tma2_kernel(const __grid_constant__ CUtensorMap tmsp,
+                                                                                          const __grid_constant__ CUtensorMap tmadd, View y, int has_add,
+                                                                                          int cblocks, int tiles) {
+  using C = Cfg<S>;
+  constexpr uint32_t kPitch = sp_pitch<S>();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  pdl_trigger();
+  const uint32_t rb = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u, sp0 = rb + r_bytes<S>(),
+                 bar_sp = sp0 + 2 * sp_bytes<S>(), bar_r = bar_sp + 16u;
+  static_assert(sp_bytes<S>() % 128 == 0, "second spec buffer must be 128-byte aligned");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (r_bytes<S>() + 2 * sp_bytes<S>()) / 16; i += kThreads) st_shared_u4(rb + (uint32_t)i * 16u, z);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmsp) : "memory");
+    if (has_add) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmadd) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_sp) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_sp + 8u) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_r) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint4 ar[C::MT2][C::KT], ai[C::MT2][C::KT], a2[C::MT2][C::KT2];     // constant tables: fetched ahead of the PDL wait
+#pragma unroll
+  for (int mt = 0; mt < C::MT2; ++mt) {
+#pragma unroll
+    for (int kt = 0; kt < C::KT; ++kt) {
+      ar[mt][kt] = g_frag[(C::O_WR + mt * C::KT + kt) * 32 + lane];
+      ai[mt][kt] = g_frag[(C::O_WI + mt * C::KT + kt) * 32 + lane];
+    }
+#pragma unroll
+    for (int kt = 0; kt < C::KT2; ++kt) a2[mt][kt] = g_frag[(C::O_A2 + mt * C::KT2 + kt) * 32 + lane];
+  }
+  __syncthreads();
+  pdl_wait();
+  constexpr int kItems = S * C::K1;
+  auto issue_spec = [&](int ti, int buf) {     // one thread; every generic access to that buffer is behind a block barrier
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_sp + 8u * buf), "r"((uint32_t)(kItems * 32)) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(sp0 + (uint32_t)buf * sp_bytes<S>()), "l"(&tmsp), "r"(bar_sp + 8u * buf), "r"(2 * ch0), "r"(0), "r"(0), "r"(n) : "memory");
+  };
+  auto issue_res = [&](int ti) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_r), "r"((uint32_t)r_bytes<S>()) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(rb), "l"(&tmadd), "r"(bar_r), "r"(ch0), "r"(0), "r"(0), "r"(n) : "memory");
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < tiles) {
+    issue_spec(blockIdx.x, 0);
+    if (has_add) issue_res(blockIdx.x);
+  }
+  int it = 0;
+  for (int ti = blockIdx.x; ti < tiles; ti += gridDim.x, ++it) {
+    const int n = ti / cblocks, ch0 = (ti - n * cblocks) * 8, buf = it & 1;
+    const uint32_t spb = sp0 + (uint32_t)buf * sp_bytes<S>();
+    // the other spec buffer was last touched by the previous tile, which ended behind a block barrier: prefetch the next tile into it
+    if (threadIdx.x == 0 && ti + (int)gridDim.x < tiles) issue_spec(ti + gridDim.x, buf ^ 1);
+    mbar_wait_parity(bar_sp + 8u * buf, (uint32_t)((it >> 1) & 1));
+    // de-interleave in place: [c0r c0i .. c7r c7i] -> [c0r .. c7r][c0i .. c7i]
+#pragma unroll 2
+    for (int i = threadIdx.x; i < kItems; i += kThreads) {
+      const int kh = i / C::K1, k = i - kh * C::K1;
+      const uint32_t d = spb + (uint32_t)kh * kPitch + (uint32_t)k * 32u;
+      const uint4 u0 = ld_shared_u4(d), u1 = ld_shared_u4(d + 16u);
+      st_shared_u4(d, make_uint4(__byte_perm(u0.x, u0.y, 0x5410), __byte_perm(u0.z, u0.w, 0x5410),
+                                 __byte_perm(u1.x, u1.y, 0x5410), __byte_perm(u1.z, u1.w, 0x5410)));
+      st_shared_u4(d + 16u, make_uint4(__byte_perm(u0.x, u0.y, 0x7632), __byte_perm(u0.z, u0.w, 0x7632),
+                                       __byte_perm(u1.x, u1.y, 0x7632), __byte_perm(u1.z, u1.w, 0x7632)));
+    }
+    __syncthreads();
+    // ---- pass A: inverse complex DFT along kh for column k, in place ---------------------------------------------------
+    for (int k = warp; k < C::K1; k += kWarps) {
+      float zr[C::MT2][4], zi[C::MT2][4];
+      complex_pass<S>(spb, k, lane, ar, ai, zr, zi, kPitch);
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < C::MT2; ++mt) {
+        const int h0 = mt * 16 + g, h1 = h0 + 8;
+        const uint32_t c0 = spb + (uint32_t)(2 * k) * 16u + (uint32_t)t * 4u;
+        if (h0 < S) {
+          st_shared_u32(c0 + (uint32_t)h0 * kPitch, pack_h2(zr[mt][0], zr[mt][1]));
+          st_shared_u32(c0 + (uint32_t)h0 * kPitch + 16u, pack_h2(zi[mt][0], zi[mt][1]));
+        }
+        if (h1 < S) {
+          st_shared_u32(c0 + (uint32_t)h1 * kPitch, pack_h2(zr[mt][2], zr[mt][3]));
+          st_shared_u32(c0 + (uint32_t)h1 * kPitch + 16u, pack_h2(zi[mt][2], zi[mt][3]));
+        }
+      }
+    }
+    __syncthreads();
+    if (has_add) mbar_wait_parity(bar_r, (uint32_t)(it & 1));
+    // ---- pass B: complex-to-real along w for tile row h (K = (k, re|im)) + residual (shared memory) -> y (global) ---------
+    for (int h = warp; h < S; h += 2 * kWarps) {                 // two rows per step = 2 * MT2 independent accumulators in flight
+      const bool two = h + kWarps < S;
+      const int hh[2] = {h, two ? h + kWarps : h};
+      uint32_t b[2][C::KT2][2];
+      load_b<C::KT2>(spb + (uint32_t)hh[0] * kPitch, 16u, lane, b[0]);
+      load_b<C::KT2>(spb + (uint32_t)hh[1] * kPitch, 16u, lane, b[1]);
+      float acc[2][C::MT2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[r][mt][i] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < C::KT2; ++kt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int mt = 0; mt < C::MT2; ++mt) mma16816(acc[r][mt], a2[mt][kt], b[r][kt][0], b[r][kt][1]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        __half* yp = y.p + n * y.sn + hh[r] * y.sh + ch0 + 2 * t;
+#pragma unroll
+        for (int mt = 0; mt < C::MT2; ++mt) {
+          const int w0 = mt * 16 + g, w1 = w0 + 8;
+          float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+          if (has_add) {
+            uint32_t u0 = 0u, u1 = 0u;
+            if (w0 < S) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u0) : "r"(rb + (uint32_t)((hh[r] * S + w0) * 16 + t * 4)) : "memory");
+            if (w1 < S) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u1) : "r"(rb + (uint32_t)((hh[r] * S + w1) * 16 + t * 4)) : "memory");
+            r0 = __half22float2(*reinterpret_cast<const __half2*>(&u0));
+            r1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+          }
+          if (w0 < S) *reinterpret_cast<uint32_t*>(yp + w0 * y.sw) = pack_h2(acc[r][mt][0] + r0.x, acc[r][mt][1] + r0.y);
+          if (w1 < S) *reinterpret_cast<uint32_t*>(yp + w1 * y.sw) = pack_h2(acc[r][mt][2] + r1.x, acc[r][mt][3] + r1.y);
+        }
+      }
+    }
+    __syncthreads();                           // every warp is done with the residual tile and with this spec buffer
+    if (threadIdx.x == 0 && has_add && ti + (int)gridDim.x < tiles) issue_res(ti + gridDim.x);
+  }
 }
 
 // ---- host: DFT matrices in A-fragment order ---------------------------------------------------------------------------
@@ -766,7 +911,7 @@ static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view*
     S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr.mark(dev);
   }
-  static const int store_tma = [] { const char* e = getenv("S2V_FFT_TMA_STORE"); return e ? atoi(e) : 1; }();      // development knob
+  static const int store_tma = [] { const char* e = getenv("S2V_FFT_TMA_STORE"); return e ? atoi(e) : 0; }();      // development knob: 0 = pipelined kernel (default), 1 / 2 = single-buffered with TMA / LSU store
   CUtensorMap tmsp, tmadd, tmy;
   if (!make_map4(enc, &tmsp, sp, sp->c, sp->w, 16, Cfg<S>::K1, S)) return S2V_ECUDA;
   if (!make_map4(enc, &tmy, y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
@@ -774,8 +919,21 @@ static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view*
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int cblocks = y->c / 8, tiles = cblocks * y->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
+  if (store_tma == 0) {                       // pipelined form: two spec buffers, LSU stores
+    constexpr int smem2 = r_bytes<S>() + 2 * sp_bytes<S>() + 32 + 128;
+    static DeviceOnce attr2;
+    if (attr2.needed(dev)) {
+      S2V_CUDA_TRY(cudaFuncSetAttribute(irfft2_mma_tma2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2.mark(dev);
+    }
+    typedef void (*KernelFn2)(const CUtensorMap, const CUtensorMap, View, int, int, int);
+    const KernelFn2 kfn2 = irfft2_mma_tma2_kernel<S>;
+    S2V_CUDA_TRY(launch_pdl(kfn2, dim3(grid), kThreads, (size_t)smem2, st, tmsp, tmadd, mk(y), add ? 1 : 0, cblocks, tiles));
+    S2V_CHECK_LAUNCH();
+    return S2V_OK;
+  }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, View, int, int, int);
-  const KernelFn kfn = store_tma ? irfft2_mma_tma_kernel<S, true> : irfft2_mma_tma_kernel<S, false>;
+  const KernelFn kfn = store_tma == 1 ? irfft2_mma_tma_kernel<S, true> : irfft2_mma_tma_kernel<S, false>;
   S2V_CUDA_TRY(launch_pdl(kfn, dim3(grid), kThreads, (size_t)smem, st, tmsp, tmadd, tmy, mk(y), add ? 1 : 0, cblocks, tiles));
   S2V_CHECK_LAUNCH();
   return S2V_OK;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, third session: evidence of the final build (N = 1): all -m gpu tests, smoke, bench, ncu launch list of one step
-P=r2e
+P=r2f
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.txt
 timeout 1500 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/${P}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${P}_pytest.log
@@ -9,5 +9,3 @@ cp gpurun_out/parity_report.txt gpurun_out/${P}_parity_report.txt 2>/dev/null
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${P}_smoke.log
 timeout 900 python bench.py > gpurun_out/${P}_bench.json 2> gpurun_out/${P}_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/${P}_bench.err
 head -c 700 gpurun_out/${P}_bench.json; echo
-timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${P}_ncu_launches_clip12s.csv python tools/profile_step.py --seconds 12 > gpurun_out/${P}_ncu_launches.log 2>&1
-echo "launch list rc=$? lines=$(wc -l < gpurun_out/${P}_ncu_launches_clip12s.csv)"
