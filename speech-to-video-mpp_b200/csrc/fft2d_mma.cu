@@ -862,7 +862,7 @@ static int launch_r_tma(const s2v_view* x, const s2v_view* sp, cudaStream_t st) 
   cuuint32_t es[4] = {1, 1, 1, 1};
   if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return S2V_ECUDA;
+    return launch_r<S>(x, sp, st);            // a view the tensor map cannot describe: the cp.async kernel takes any view_ok view
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int cblocks = x->c / 8, tiles = cblocks * x->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
@@ -913,9 +913,9 @@ static int launch_i_tma(const s2v_view* sp, const s2v_view* add, const s2v_view*
   }
   static const int store_tma = [] { const char* e = getenv("S2V_FFT_TMA_STORE"); return e ? atoi(e) : 0; }();      // development knob: 0 = pipelined kernel (default), 1 / 2 = single-buffered with TMA / LSU store
   CUtensorMap tmsp, tmadd, tmy;
-  if (!make_map4(enc, &tmsp, sp, sp->c, sp->w, 16, Cfg<S>::K1, S)) return S2V_ECUDA;
-  if (!make_map4(enc, &tmy, y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
-  if (!make_map4(enc, &tmadd, add ? add : y, y->c, y->w, 8, S, S)) return S2V_ECUDA;
+  if (!make_map4(enc, &tmsp, sp, sp->c, sp->w, 16, Cfg<S>::K1, S) || !make_map4(enc, &tmy, y, y->c, y->w, 8, S, S) ||
+      !make_map4(enc, &tmadd, add ? add : y, y->c, y->w, 8, S, S))
+    return launch_i<S>(sp, add, y, st);       // a view the tensor maps cannot describe: the cp.async kernel takes any view_ok view
   const int n_sm = sm_count(dev);
   if (n_sm <= 0) return S2V_ECUDA;
   const int cblocks = y->c / 8, tiles = cblocks * y->n, cap = blocks_per_sm_tma<S>() * n_sm, grid = tiles < cap ? tiles : cap;
