@@ -1,7 +1,9 @@
 """CPU check of the tensor-core DFT variant of the FourierUnit transforms (csrc/fft2d_mma.cu, reference: models/ffc.py:99-121):
 the A-fragment tables the host builds and the kernels' index arithmetic (ldmatrix.trans addressing, mma.m16n8k16 register layouts,
 in-place tile passes), emulated lane by lane in numpy (tools/emu_fft_mma.py), must give numpy's rfft2 / irfft2 (ortho) for the three
-LNet sizes within the same 2e-3-of-max bound the GPU test uses.  Needs nvcc (host code only; no GPU)."""
+LNet sizes within the same 2e-3-of-max bound the GPU test uses - in both buffer layouts: the padded in-place tile of the cp.async
+kernels and the dense TMA destination buffers of the default (48 x 48) kernels, bit-identical to each other.  Needs nvcc (host code
+only; no GPU)."""
 import os
 import shutil
 import subprocess

@@ -118,9 +118,10 @@ def acc_lane(Cm, lane):
     return Cm[g, 2 * t], Cm[g, 2 * t + 1], Cm[g + 8, 2 * t], Cm[g + 8, 2 * t + 1]
 
 
-def complex_pass(c, sm, k, ar, ai):
-    bre = load_b(sm, (2 * k) * 16, c.RS, c.KT)
-    bim = load_b(sm, (2 * k + 1) * 16, c.RS, c.KT)
+def complex_pass(c, sm, k, ar, ai, base=0, pitch=None):
+    pitch = c.RS if pitch is None else pitch
+    bre = load_b(sm, base + (2 * k) * 16, pitch, c.KT)
+    bim = load_b(sm, base + (2 * k + 1) * 16, pitch, c.KT)
     zr, zi = [], []
     for mt in range(c.MT2):
         r = np.zeros((16, 8), np.float32)
@@ -133,17 +134,21 @@ def complex_pass(c, sm, k, ar, ai):
     return zr, zi
 
 
-def rfft2_emu(S, x):
-    """x [S][S][8] fp16 -> spec [S][K1][16] fp16"""
+def rfft2_emu(S, x, tma=False):
+    """x [S][S][8] fp16 -> spec [S][K1][16] fp16.  tma: the TMA kernel's buffers - a dense X tile (pitch 16 S, + 256 zero bytes) in front of
+    the padded Y tile - instead of the in-place tile of the cp.async kernel."""
     c = Cfg(S)
-    sm = Smem(c.TILE)
+    xbytes = S * S * 16 + 256 if tma else 0
+    xpitch = S * 16 if tma else c.RS
+    yb = xbytes
+    sm = Smem(xbytes + c.TILE)
     a1 = [[a_frag(c.O_F1 + mt * c.KT + kt) for kt in range(c.KT)] for mt in range(c.MT1)]
     for i in range(S * S):
         h, w = divmod(i, S)
-        sm.st128(h * c.RS + w * 16, x[h, w])
+        sm.st128(h * xpitch + w * 16, x[h, w])
     for h in range(S):
-        row = h * c.RS
-        b = load_b(sm, row, 16, c.KT)
+        row = yb + h * c.RS
+        b = load_b(sm, h * xpitch, 16, c.KT)
         acc = [sum(a1[mt][kt] @ b[kt] for kt in range(c.KT)) for mt in range(c.MT1)]
         for lane in range(32):
             g, t = lane >> 2, lane & 3
@@ -157,7 +162,7 @@ def rfft2_emu(S, x):
     ai = [[a_frag(c.O_GI + mt * c.KT + kt) for kt in range(c.KT)] for mt in range(c.MT2)]
     spec = np.zeros((S, c.K1, 16), dtype=np.float16)
     for k in range(c.K1):
-        zr, zi = complex_pass(c, sm, k, ar, ai)
+        zr, zi = complex_pass(c, sm, k, ar, ai, base=yb)
         for lane in range(32):
             g, t = lane >> 2, lane & 3
             for mt in range(c.MT2):
@@ -171,19 +176,21 @@ def rfft2_emu(S, x):
     return spec
 
 
-def irfft2_emu(S, spec, add):
-    """spec [S][K1][16] fp16, add [S][S][8] fp16 -> y [S][S][8] fp16"""
+def irfft2_emu(S, spec, add, tma=False):
+    """spec [S][K1][16] fp16, add [S][S][8] fp16 -> y [S][S][8] fp16.  tma: the TMA kernels' spec buffer - dense rows of 32 K1 bytes,
+    KP rows + 256 zero bytes - instead of the padded in-place tile."""
     c = Cfg(S)
-    sm = Smem(c.TILE)
+    pitch = c.K1 * 32 if tma else c.RS
+    sm = Smem((c.KP * pitch + 256 + 127) // 128 * 128 if tma else c.TILE)
     for i in range(S * c.K1):
         kh, k = divmod(i, c.K1)
         u = spec[kh, k]
-        sm.st128(kh * c.RS + k * 32, u[0::2])
-        sm.st128(kh * c.RS + k * 32 + 16, u[1::2])
+        sm.st128(kh * pitch + k * 32, u[0::2])
+        sm.st128(kh * pitch + k * 32 + 16, u[1::2])
     ar = [[a_frag(c.O_WR + mt * c.KT + kt) for kt in range(c.KT)] for mt in range(c.MT2)]
     ai = [[a_frag(c.O_WI + mt * c.KT + kt) for kt in range(c.KT)] for mt in range(c.MT2)]
     for k in range(c.K1):
-        zr, zi = complex_pass(c, sm, k, ar, ai)
+        zr, zi = complex_pass(c, sm, k, ar, ai, pitch=pitch)
         for lane in range(32):
             g, t = lane >> 2, lane & 3
             for mt in range(c.MT2):
@@ -191,15 +198,15 @@ def irfft2_emu(S, spec, add):
                 h0, h1 = mt * 16 + g, mt * 16 + g + 8
                 c0 = (2 * k) * 16 + t * 4
                 if h0 < S:
-                    sm.st32(c0 + h0 * c.RS, pack(r[0], r[1]))
-                    sm.st32(c0 + h0 * c.RS + 16, pack(i[0], i[1]))
+                    sm.st32(c0 + h0 * pitch, pack(r[0], r[1]))
+                    sm.st32(c0 + h0 * pitch + 16, pack(i[0], i[1]))
                 if h1 < S:
-                    sm.st32(c0 + h1 * c.RS, pack(r[2], r[3]))
-                    sm.st32(c0 + h1 * c.RS + 16, pack(i[2], i[3]))
+                    sm.st32(c0 + h1 * pitch, pack(r[2], r[3]))
+                    sm.st32(c0 + h1 * pitch + 16, pack(i[2], i[3]))
     a2 = [[a_frag(c.O_A2 + mt * c.KT2 + kt) for kt in range(c.KT2)] for mt in range(c.MT2)]
     y = np.zeros((S, S, 8), dtype=np.float16)
     for h in range(S):
-        b = load_b(sm, h * c.RS, 16, c.KT2)
+        b = load_b(sm, h * pitch, 16, c.KT2)
         for mt in range(c.MT2):
             acc = sum(a2[mt][kt] @ b[kt] for kt in range(c.KT2))
             for lane in range(32):
@@ -218,16 +225,21 @@ if __name__ == "__main__":
     for S in (12, 24, 48):
         K1 = S // 2 + 1
         x = rng.standard_normal((S, S, 8)).astype(np.float16)
-        spec = rfft2_emu(S, x)
         ref = np.fft.rfft2(x.astype(np.float64), axes=(0, 1), norm="ortho")            # [S][K1][8]
         refi = np.stack((ref.real, ref.imag), axis=-1).reshape(S, K1, 16)
-        e = np.abs(spec.astype(np.float64) - refi).max() / np.abs(refi).max()
         z = np.maximum(rng.standard_normal((S, K1, 16)), 0).astype(np.float16)
         add = rng.standard_normal((S, S, 8)).astype(np.float16)
-        y = irfft2_emu(S, z, add)
         zc = z.astype(np.float64).reshape(S, K1, 8, 2)
         refy = np.fft.irfft2(zc[..., 0] + 1j * zc[..., 1], s=(S, S), axes=(0, 1), norm="ortho") + add.astype(np.float64)
-        ei = np.abs(y.astype(np.float64) - refy).max() / np.abs(refy).max()
-        print("S=%d  rfft2 rel-to-max err %.2e   irfft2 %.2e" % (S, e, ei))
-        assert e < 2e-3 and ei < 2e-3
+        outs = {}
+        for tma in (False, True):              # the cp.async kernels' in-place tile / the TMA kernels' dense buffers
+            spec = rfft2_emu(S, x, tma)
+            e = np.abs(spec.astype(np.float64) - refi).max() / np.abs(refi).max()
+            y = irfft2_emu(S, z, add, tma)
+            ei = np.abs(y.astype(np.float64) - refy).max() / np.abs(refy).max()
+            print("S=%d %-8s rfft2 rel-to-max err %.2e   irfft2 %.2e" % (S, "tma" if tma else "cp.async", e, ei))
+            assert e < 2e-3 and ei < 2e-3
+            outs[tma] = (spec, y)
+        # same arithmetic in both buffer layouts: bit-identical results
+        assert np.array_equal(outs[False][0], outs[True][0]) and np.array_equal(outs[False][1], outs[True][1])
     print("ok")
